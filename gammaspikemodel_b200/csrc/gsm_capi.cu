@@ -1,0 +1,489 @@
+// gsm_capi.cu — the C ABI declared in include/gsm_b200.h: handle management, host<->device staging,
+// chunked streaming for host-resident batches, and the launches.  No compute happens on the CPU here
+// and there is no fallback: without a usable CUDA device gsm_create fails.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/gsm_b200.h"
+#include "gsm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {  // one staging slot of the streaming path
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    double *height = nullptr, *rate = nullptr, *spike = nullptr, *params = nullptr, *out = nullptr;
+    double *out_rates = nullptr, *out_wsp = nullptr;
+    int32_t *parent = nullptr, *nstubs = nullptr, *node_count = nullptr;
+    uint8_t* use_spike = nullptr;
+};
+
+}  // namespace
+
+struct gsm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t max_trees = 0;
+    int32_t max_nodes = 0;
+    int64_t max_stride = 0;
+    uint32_t flags = 0;
+    int32_t stub_mode = GSM_STUBS_COUNTS;
+    // handle-owned resident batch
+    double *d_height = nullptr, *d_rate = nullptr, *d_spike = nullptr, *d_params = nullptr, *d_out = nullptr;
+    double *d_out_rates = nullptr, *d_out_wsp = nullptr;
+    int32_t *d_parent = nullptr, *d_nstubs = nullptr, *d_node_count = nullptr;
+    uint8_t* d_use = nullptr;
+    double* d_cdf = nullptr;  // scratch for gsm_stub_cdf
+    int32_t cdf_cap = 0;
+    bool have_trees = false, have_rate = false, have_spike = false, have_nstubs = false, have_params = false;
+    bool have_use = false, have_node_count = false, external = false;
+    GsmBatch cur{};
+    // streaming slots (gsm_eval_host)
+    Slot slots[2];
+    int64_t slot_trees = 0;
+    int64_t slot_stride = 0;
+    bool slot_rates = false, slot_wsp = false;
+    std::string err;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(gsm_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define GSM_CUDA(h, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail((h), GSM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+cudaError_t dalloc(T** p, int64_t count) {
+    if (count <= 0) count = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), static_cast<size_t>(count) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, static_cast<size_t>(count) * sizeof(T));
+    return e;
+}
+
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// dense host [T][n] -> pitched device [T][stride]
+template <typename T>
+cudaError_t h2d_rows(T* dst, int64_t stride, const T* src, int64_t n, int64_t rows, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(dst, static_cast<size_t>(stride) * sizeof(T), src, static_cast<size_t>(n) * sizeof(T),
+                             static_cast<size_t>(n) * sizeof(T), static_cast<size_t>(rows), cudaMemcpyHostToDevice, st);
+}
+template <typename T>
+cudaError_t d2h_rows(T* dst, int64_t n, const T* src, int64_t stride, int64_t rows, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(dst, static_cast<size_t>(n) * sizeof(T), src, static_cast<size_t>(stride) * sizeof(T),
+                             static_cast<size_t>(n) * sizeof(T), static_cast<size_t>(rows), cudaMemcpyDeviceToHost, st);
+}
+
+void free_slots(gsm_handle* h) {
+    for (Slot& s : h->slots) {
+        dfree(s.height); dfree(s.rate); dfree(s.spike); dfree(s.params); dfree(s.out);
+        dfree(s.out_rates); dfree(s.out_wsp); dfree(s.parent); dfree(s.nstubs); dfree(s.node_count);
+        dfree(s.use_spike);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = Slot{};
+    }
+    h->slot_trees = 0;
+    h->slot_stride = 0;
+}
+
+int check_mode(gsm_handle* h, bool have_rate, bool have_nstubs) {
+    if ((h->flags & GSM_F_HAS_RATES) && !have_rate)
+        return fail(h, GSM_E_STATE, "GSM_F_HAS_RATES is set but no rate array was provided");
+    const bool needs_counts = h->stub_mode != GSM_STUBS_NOSTUB &&
+                              (h->flags & (GSM_F_STUBS_TO_CLOCK | GSM_F_STUBS_TO_SPIKE_PRIOR | GSM_F_STUBS_TO_TREE_PRIOR));
+    if (needs_counts && !have_nstubs)
+        return fail(h, GSM_E_STATE, "stub counts are wired (stub_mode=%d) but no nstubs array was provided", h->stub_mode);
+    return GSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsm_abi_version(void) { return GSM_ABI_VERSION; }
+
+int gsm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t gsm_device_stride(int32_t n_nodes) { return n_nodes <= 0 ? 32 : round_up(n_nodes, 32); }
+
+const char* gsm_last_error(const gsm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gsm_create(gsm_handle** out, int32_t device_id, int64_t max_trees, int32_t max_nodes) {
+    if (!out) return fail(nullptr, GSM_E_ARG, "gsm_create: out is NULL");
+    *out = nullptr;
+    if (max_trees < 0 || max_nodes < 0) return fail(nullptr, GSM_E_ARG, "gsm_create: negative capacity");
+    if (max_nodes > GSM_MAX_NODES)
+        return fail(nullptr, GSM_E_UNSUPPORTED, "gsm_create: max_nodes %d exceeds GSM_MAX_NODES %d", max_nodes, GSM_MAX_NODES);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, GSM_E_CUDA, "gsm_create: no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device_id < 0 || device_id >= ndev) return fail(nullptr, GSM_E_ARG, "gsm_create: device %d of %d", device_id, ndev);
+    gsm_handle* h = new (std::nothrow) gsm_handle();
+    if (!h) return fail(nullptr, GSM_E_NOMEM, "gsm_create: out of host memory");
+    h->device = device_id;
+    h->max_trees = max_trees;
+    h->max_nodes = max_nodes;
+    h->max_stride = gsm_device_stride(max_nodes);
+    auto bail = [&](cudaError_t ce, const char* what) {
+        int rc = fail(nullptr, ce == cudaErrorMemoryAllocation ? GSM_E_NOMEM : GSM_E_CUDA, "gsm_create: %s: %s", what,
+                      cudaGetErrorString(ce));
+        gsm_destroy(h);
+        return rc;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = gsm_init_tables()) != cudaSuccess) return bail(e, "table upload");
+    if (max_trees > 0 && max_nodes > 0) {
+        const int64_t cells = max_trees * h->max_stride;
+        if ((e = dalloc(&h->d_height, cells)) != cudaSuccess) return bail(e, "alloc height");
+        if ((e = dalloc(&h->d_rate, cells)) != cudaSuccess) return bail(e, "alloc rate");
+        if ((e = dalloc(&h->d_spike, cells)) != cudaSuccess) return bail(e, "alloc spike");
+        if ((e = dalloc(&h->d_parent, cells)) != cudaSuccess) return bail(e, "alloc parent");
+        if ((e = dalloc(&h->d_nstubs, cells)) != cudaSuccess) return bail(e, "alloc nstubs");
+        if ((e = dalloc(&h->d_node_count, max_trees)) != cudaSuccess) return bail(e, "alloc node_count");
+        if ((e = dalloc(&h->d_params, max_trees * GSM_NPARAM)) != cudaSuccess) return bail(e, "alloc params");
+        if ((e = dalloc(&h->d_use, max_trees)) != cudaSuccess) return bail(e, "alloc use_spike");
+        if ((e = dalloc(&h->d_out, max_trees * GSM_NOUT)) != cudaSuccess) return bail(e, "alloc out");
+    }
+    *out = h;
+    return GSM_OK;
+}
+
+int gsm_destroy(gsm_handle* h) {
+    if (!h) return GSM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_slots(h);
+    dfree(h->d_height); dfree(h->d_rate); dfree(h->d_spike); dfree(h->d_parent); dfree(h->d_nstubs);
+    dfree(h->d_node_count); dfree(h->d_params); dfree(h->d_use); dfree(h->d_out); dfree(h->d_out_rates);
+    dfree(h->d_out_wsp); dfree(h->d_cdf);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return GSM_OK;
+}
+
+int gsm_set_mode(gsm_handle* h, int32_t stub_mode, uint32_t flags) {
+    if (!h) return GSM_E_ARG;
+    if (stub_mode < GSM_STUBS_NOSTUB || stub_mode > GSM_STUBS_EXACT) return fail(h, GSM_E_ARG, "gsm_set_mode: stub_mode %d", stub_mode);
+    if ((flags & GSM_F_COND_SAMPLING) && (flags & GSM_F_COND_RHO_SAMPLING))   // STP:92-94
+        return fail(h, GSM_E_ARG, "gsm_set_mode: conditionOnSampling and conditionOnRhoSampling are exclusive");
+    if ((flags & GSM_F_ORIGIN) && (flags & GSM_F_COND_ROOT))                  // STP:89-91
+        return fail(h, GSM_E_ARG, "gsm_set_mode: origin and conditionOnRoot are exclusive");
+    if ((flags & GSM_F_COND_ROOT) && !(flags & (GSM_F_COND_SAMPLING | GSM_F_COND_RHO_SAMPLING)))   // STP:95-98
+        return fail(h, GSM_E_ARG, "gsm_set_mode: conditionOnRoot needs conditionOnSampling or conditionOnRhoSampling");
+    h->stub_mode = stub_mode;
+    h->flags = flags;
+    return GSM_OK;
+}
+
+int gsm_upload_trees(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double* height, const int32_t* parent,
+                     const int32_t* node_count) {
+    if (!h) return GSM_E_ARG;
+    if (n_trees < 0 || n_nodes < 0) return fail(h, GSM_E_ARG, "gsm_upload_trees: negative size");
+    if (n_trees > h->max_trees || n_nodes > h->max_nodes)
+        return fail(h, GSM_E_ARG, "gsm_upload_trees: %lld x %d exceeds the handle capacity %lld x %d", (long long)n_trees,
+                    n_nodes, (long long)h->max_trees, h->max_nodes);
+    if (n_trees > 0 && n_nodes > 0 && (!height || !parent)) return fail(h, GSM_E_ARG, "gsm_upload_trees: NULL array");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t stride = gsm_device_stride(n_nodes);
+    GSM_CUDA(h, h2d_rows(h->d_height, stride, height, n_nodes, n_trees, h->stream));
+    GSM_CUDA(h, h2d_rows(h->d_parent, stride, parent, n_nodes, n_trees, h->stream));
+    if (node_count && n_trees > 0)
+        GSM_CUDA(h, cudaMemcpyAsync(h->d_node_count, node_count, n_trees * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->external = false;
+    h->have_trees = true;
+    h->have_node_count = node_count != nullptr;
+    h->have_rate = h->have_spike = h->have_nstubs = false;  // branch arrays belong to a tree upload
+    h->cur = GsmBatch{};
+    h->cur.n_trees = n_trees;
+    h->cur.n_nodes = n_nodes;
+    h->cur.stride = stride;
+    return GSM_OK;
+}
+
+int gsm_upload_branch_params(gsm_handle* h, const double* rate, const double* spike, const int32_t* nstubs) {
+    if (!h) return GSM_E_ARG;
+    if (!h->have_trees || h->external) return fail(h, GSM_E_STATE, "gsm_upload_branch_params: call gsm_upload_trees first");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t T = h->cur.n_trees, n = h->cur.n_nodes, S = h->cur.stride;
+    if (rate) GSM_CUDA(h, h2d_rows(h->d_rate, S, rate, n, T, h->stream));
+    if (spike) GSM_CUDA(h, h2d_rows(h->d_spike, S, spike, n, T, h->stream));
+    if (nstubs) GSM_CUDA(h, h2d_rows(h->d_nstubs, S, nstubs, n, T, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_rate |= rate != nullptr;
+    h->have_spike |= spike != nullptr;
+    h->have_nstubs |= nstubs != nullptr;
+    return GSM_OK;
+}
+
+int gsm_upload_tree_params(gsm_handle* h, const double* params, const uint8_t* use_spike) {
+    if (!h) return GSM_E_ARG;
+    if (!h->have_trees || h->external) return fail(h, GSM_E_STATE, "gsm_upload_tree_params: call gsm_upload_trees first");
+    if (!params) return fail(h, GSM_E_ARG, "gsm_upload_tree_params: params is NULL");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t T = h->cur.n_trees;
+    if (T > 0) {
+        GSM_CUDA(h, cudaMemcpyAsync(h->d_params, params, T * GSM_NPARAM * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (use_spike) GSM_CUDA(h, cudaMemcpyAsync(h->d_use, use_spike, T, cudaMemcpyHostToDevice, h->stream));
+    }
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_params = true;
+    h->have_use = use_spike != nullptr;
+    return GSM_OK;
+}
+
+static int resident_batch(gsm_handle* h, GsmBatch* b) {
+    if (!h->have_trees) return fail(h, GSM_E_STATE, "no tree batch: call gsm_upload_trees or gsm_bind_device first");
+    if (h->external) {
+        *b = h->cur;
+    } else {
+        if (!h->have_params) return fail(h, GSM_E_STATE, "no per-tree parameters: call gsm_upload_tree_params first");
+        if (!h->have_spike) return fail(h, GSM_E_STATE, "no spikes: call gsm_upload_branch_params first");
+        *b = h->cur;
+        b->height = h->d_height;
+        b->parent = h->d_parent;
+        b->node_count = h->have_node_count ? h->d_node_count : nullptr;
+        b->rate = h->have_rate ? h->d_rate : nullptr;
+        b->spike = h->d_spike;
+        b->nstubs = h->have_nstubs ? h->d_nstubs : nullptr;
+        b->params = h->d_params;
+        b->use_spike = h->have_use ? h->d_use : nullptr;
+    }
+    b->flags = h->flags;
+    b->stub_mode = h->stub_mode;
+    return check_mode(h, b->rate != nullptr, b->nstubs != nullptr);
+}
+
+int gsm_eval(gsm_handle* h, double* out_tree, double* out_rates, double* out_wspikes) {
+    if (!h) return GSM_E_ARG;
+    if (h->external) return fail(h, GSM_E_STATE, "gsm_eval: batch is device-bound; use gsm_eval_device");
+    GsmBatch b;
+    int rc = resident_batch(h, &b);
+    if (rc != GSM_OK) return rc;
+    if (b.n_trees == 0) return GSM_OK;
+    if (!out_tree) return fail(h, GSM_E_ARG, "gsm_eval: out_tree is NULL");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t cells = h->max_trees * h->max_stride;
+    if (out_rates && !h->d_out_rates) GSM_CUDA(h, dalloc(&h->d_out_rates, cells));
+    if (out_wspikes && !h->d_out_wsp) GSM_CUDA(h, dalloc(&h->d_out_wsp, cells));
+    int nl = gsm_launch_eval(b, h->d_out, out_rates ? h->d_out_rates : nullptr, out_wspikes ? h->d_out_wsp : nullptr, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    GSM_CUDA(h, cudaMemcpyAsync(out_tree, h->d_out, b.n_trees * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out_rates) GSM_CUDA(h, d2h_rows(out_rates, (int64_t)b.n_nodes, h->d_out_rates, b.stride, b.n_trees, h->stream));
+    if (out_wspikes) GSM_CUDA(h, d2h_rows(out_wspikes, (int64_t)b.n_nodes, h->d_out_wsp, b.stride, b.n_trees, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GSM_OK;
+}
+
+static int ensure_slots(gsm_handle* h, int64_t chunk, int64_t stride, bool rates, bool wsp) {
+    if (h->slot_trees >= chunk && h->slot_stride >= stride && (!rates || h->slot_rates) && (!wsp || h->slot_wsp)) return GSM_OK;
+    free_slots(h);
+    const int64_t cells = chunk * stride;
+    for (Slot& s : h->slots) {
+        GSM_CUDA(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        GSM_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        GSM_CUDA(h, dalloc(&s.height, cells));
+        GSM_CUDA(h, dalloc(&s.rate, cells));
+        GSM_CUDA(h, dalloc(&s.spike, cells));
+        GSM_CUDA(h, dalloc(&s.parent, cells));
+        GSM_CUDA(h, dalloc(&s.nstubs, cells));
+        GSM_CUDA(h, dalloc(&s.node_count, chunk));
+        GSM_CUDA(h, dalloc(&s.params, chunk * GSM_NPARAM));
+        GSM_CUDA(h, dalloc(&s.use_spike, chunk));
+        GSM_CUDA(h, dalloc(&s.out, chunk * GSM_NOUT));
+        if (rates) GSM_CUDA(h, dalloc(&s.out_rates, cells));
+        if (wsp) GSM_CUDA(h, dalloc(&s.out_wsp, cells));
+    }
+    h->slot_trees = chunk;
+    h->slot_stride = stride;
+    h->slot_rates = rates;
+    h->slot_wsp = wsp;
+    return GSM_OK;
+}
+
+int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double* height, const int32_t* parent,
+                  const int32_t* node_count, const double* rate, const double* spike, const int32_t* nstubs,
+                  const double* params, const uint8_t* use_spike, double* out_tree, double* out_rates, double* out_wspikes) {
+    if (!h) return GSM_E_ARG;
+    if (n_trees < 0 || n_nodes < 0) return fail(h, GSM_E_ARG, "gsm_eval_host: negative size");
+    if (n_nodes > GSM_MAX_NODES) return fail(h, GSM_E_UNSUPPORTED, "gsm_eval_host: n_nodes %d exceeds GSM_MAX_NODES", n_nodes);
+    if (n_trees == 0 || n_nodes == 0) return GSM_OK;
+    if (!height || !parent || !spike || !params || !out_tree) return fail(h, GSM_E_ARG, "gsm_eval_host: NULL required array");
+    int rc = check_mode(h, rate != nullptr, nstubs != nullptr);
+    if (rc != GSM_OK) return rc;
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t stride = gsm_device_stride(n_nodes);
+    // ~256 MB of inputs per slot: long enough transfers for full PCIe rate, short enough to overlap
+    int64_t chunk = std::max<int64_t>(1, (int64_t(256) << 20) / (stride * 32));
+    chunk = std::min(chunk, n_trees);
+    rc = ensure_slots(h, chunk, stride, out_rates != nullptr, out_wspikes != nullptr);
+    if (rc != GSM_OK) return rc;
+    chunk = std::min(h->slot_trees, n_trees);
+    int64_t k = 0;
+    for (int64_t t0 = 0; t0 < n_trees; t0 += chunk, ++k) {
+        const int64_t T = std::min(chunk, n_trees - t0);
+        Slot& s = h->slots[k & 1];
+        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+        const int64_t off = t0 * n_nodes;
+        GSM_CUDA(h, h2d_rows(s.height, stride, height + off, (int64_t)n_nodes, T, s.stream));
+        GSM_CUDA(h, h2d_rows(s.parent, stride, parent + off, (int64_t)n_nodes, T, s.stream));
+        GSM_CUDA(h, h2d_rows(s.spike, stride, spike + off, (int64_t)n_nodes, T, s.stream));
+        if (rate) GSM_CUDA(h, h2d_rows(s.rate, stride, rate + off, (int64_t)n_nodes, T, s.stream));
+        if (nstubs) GSM_CUDA(h, h2d_rows(s.nstubs, stride, nstubs + off, (int64_t)n_nodes, T, s.stream));
+        if (node_count) GSM_CUDA(h, cudaMemcpyAsync(s.node_count, node_count + t0, T * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
+        GSM_CUDA(h, cudaMemcpyAsync(s.params, params + t0 * GSM_NPARAM, T * GSM_NPARAM * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        if (use_spike) GSM_CUDA(h, cudaMemcpyAsync(s.use_spike, use_spike + t0, T, cudaMemcpyHostToDevice, s.stream));
+        GsmBatch b{};
+        b.n_trees = T; b.n_nodes = n_nodes; b.stride = stride;
+        b.height = s.height; b.parent = s.parent; b.node_count = node_count ? s.node_count : nullptr;
+        b.rate = rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = nstubs ? s.nstubs : nullptr;
+        b.params = s.params; b.use_spike = use_spike ? s.use_spike : nullptr;
+        b.flags = h->flags; b.stub_mode = h->stub_mode;
+        int nl = gsm_launch_eval(b, s.out, out_rates ? s.out_rates : nullptr, out_wspikes ? s.out_wsp : nullptr, s.stream);
+        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_host launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+        h->launches += nl;
+        GSM_CUDA(h, cudaMemcpyAsync(out_tree + t0 * GSM_NOUT, s.out, T * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (out_rates) GSM_CUDA(h, d2h_rows(out_rates + off, (int64_t)n_nodes, s.out_rates, stride, T, s.stream));
+        if (out_wspikes) GSM_CUDA(h, d2h_rows(out_wspikes + off, (int64_t)n_nodes, s.out_wsp, stride, T, s.stream));
+        GSM_CUDA(h, cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (Slot& s : h->slots) {
+        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+        s.busy = false;
+    }
+    return GSM_OK;
+}
+
+int gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t cap, int32_t* len) {
+    if (!h) return GSM_E_ARG;
+    if (!cdf || !len || cap <= 0) return fail(h, GSM_E_ARG, "gsm_stub_cdf: bad output arguments");
+    GsmBatch b;
+    int rc = resident_batch(h, &b);
+    if (rc != GSM_OK) return rc;
+    if (tree < 0 || tree >= b.n_trees || node < 0 || node >= b.n_nodes) return fail(h, GSM_E_ARG, "gsm_stub_cdf: (tree,node) out of range");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    if (h->cdf_cap < cap + 1) {
+        dfree(h->d_cdf);
+        GSM_CUDA(h, dalloc(&h->d_cdf, (int64_t)cap + 1));
+        h->cdf_cap = cap + 1;
+    }
+    int32_t* d_len = reinterpret_cast<int32_t*>(h->d_cdf + cap);
+    int nl = gsm_launch_stub_cdf(b, tree, node, h->d_cdf, cap, d_len, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_stub_cdf launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    int32_t n = 0;
+    GSM_CUDA(h, cudaMemcpyAsync(&n, d_len, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    GSM_CUDA(h, cudaMemcpy(cdf, h->d_cdf, sizeof(double) * std::min(n, cap), cudaMemcpyDeviceToHost));
+    *len = n;
+    return GSM_OK;
+}
+
+int gsm_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return GSM_E_ARG;
+    cudaError_t e = cudaHostAlloc(out, static_cast<size_t>(bytes > 0 ? bytes : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gsm_host_alloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? GSM_E_NOMEM : GSM_E_CUDA;
+    }
+    return GSM_OK;
+}
+
+int gsm_host_free(void* p) {
+    if (!p) return GSM_OK;
+    return cudaFreeHost(p) == cudaSuccess ? GSM_OK : GSM_E_CUDA;
+}
+
+int gsm_bind_device(gsm_handle* h, int64_t n_trees, int32_t n_nodes, int64_t stride, const double* d_height,
+                    const int32_t* d_parent, const int32_t* d_node_count, const double* d_rate, const double* d_spike,
+                    const int32_t* d_nstubs, const double* d_params, const uint8_t* d_use_spike) {
+    if (!h) return GSM_E_ARG;
+    if (n_trees < 0 || n_nodes < 0) return fail(h, GSM_E_ARG, "gsm_bind_device: negative size");
+    if (n_nodes > GSM_MAX_NODES) return fail(h, GSM_E_UNSUPPORTED, "gsm_bind_device: n_nodes %d exceeds GSM_MAX_NODES", n_nodes);
+    if (stride < n_nodes || (stride % 32) != 0) return fail(h, GSM_E_ARG, "gsm_bind_device: stride must be >= n_nodes and a multiple of 32");
+    if (n_trees > 0 && (!d_height || !d_parent || !d_spike || !d_params)) return fail(h, GSM_E_ARG, "gsm_bind_device: NULL required array");
+    if ((reinterpret_cast<uintptr_t>(d_height) | reinterpret_cast<uintptr_t>(d_parent)) & 15u)
+        return fail(h, GSM_E_ARG, "gsm_bind_device: height/parent must be 16-byte aligned");
+    h->external = true;
+    h->have_trees = true;
+    GsmBatch b{};
+    b.n_trees = n_trees; b.n_nodes = n_nodes; b.stride = stride;
+    b.height = d_height; b.parent = d_parent; b.node_count = d_node_count;
+    b.rate = d_rate; b.spike = d_spike; b.nstubs = d_nstubs; b.params = d_params; b.use_spike = d_use_spike;
+    h->cur = b;
+    return GSM_OK;
+}
+
+int gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, double* d_out_wspikes, void* cuda_stream) {
+    if (!h) return GSM_E_ARG;
+    GsmBatch b;
+    int rc = resident_batch(h, &b);
+    if (rc != GSM_OK) return rc;
+    if (b.n_trees == 0) return GSM_OK;
+    if (!d_out_tree) return fail(h, GSM_E_ARG, "gsm_eval_device: d_out_tree is NULL");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+    int nl = gsm_launch_eval(b, d_out_tree, d_out_rates, d_out_wspikes, st);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_device launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    return GSM_OK;
+}
+
+int gsm_sync(gsm_handle* h) {
+    if (!h) return GSM_E_ARG;
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GSM_OK;
+}
+
+int64_t gsm_launch_count(const gsm_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

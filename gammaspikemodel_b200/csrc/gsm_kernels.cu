@@ -1,0 +1,351 @@
+// gsm_kernels.cu — sm_100a kernels of the GammaSpikeModel per-branch hot path.
+//
+// gsm_eval_kernel: one CTA per tree state.
+//   phase 0  one elected thread issues two TMA bulk copies (cp.async.bulk, mbarrier complete_tx) that bring
+//            the tree's height row and parent row into shared memory; meanwhile one warp computes the
+//            per-tree constants (c1, c2, logs, lgamma(shape*m) table) and the rest clear the flag bytes.
+//   phase 1  every node marks its parent as non-leaf                         (Node.isLeaf)
+//   phase 2  every leaf whose parent has the same height marks the parent fake (Node.isDirectAncestor /
+//            Node.isFake) and every node stores its aux value (exp(-c1 h) or log(l e^{(l-m)h} - m))
+//   phase 3  per-branch terms: rate/spike/stub-count rows are streamed from HBM with coalesced loads
+//            (each byte is read exactly once), parent height/aux/flags are gathered from shared memory
+//   phase 4  fixed-order warp-shuffle + cross-warp reduction, per-tree epilogue, one 64-byte result row.
+// The math is in gsm_node_math.cuh (shared with the CPU-side logic tests).
+
+#include "gsm_kernels.cuh"
+#include "gsm_node_math.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+__device__ double g_logfact[GSM_LOGFACT_N];
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared::cluster, completion on an mbarrier)
+// ---------------------------------------------------------------------------------------------------------
+static __device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+static __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+static __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GSM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GSM_DONE_%=;\n"
+        "bra GSM_WAIT_%=;\n"
+        "GSM_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned
+static __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+static __device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
+                                                         double* __restrict__ out_rates,
+                                                         double* __restrict__ out_wspikes) {
+    constexpr int NWARP = BLOCK / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int64_t S = b.stride;
+    double* sh_h = reinterpret_cast<double*>(smem_raw);
+    double* sh_aux = sh_h + S;
+    int32_t* sh_par = reinterpret_cast<int32_t*>(sh_aux + S);
+    uint8_t* sh_nonleaf = reinterpret_cast<uint8_t*>(sh_par + S);
+    uint8_t* sh_fake = sh_nonleaf + S;
+
+    __shared__ GsmTreeConsts K;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int32_t sh_root;
+    __shared__ double sh_red[6][NWARP];
+    __shared__ int32_t sh_redi[5][NWARP];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int64_t t = blockIdx.x;
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    double* orow = out_tree + t * GSM_NOUT;
+    if (n <= 0) {
+        if (tid < GSM_NOUT) orow[tid] = NAN;
+        return;
+    }
+    const int64_t row = t * S;
+
+    // ---- phase 0 ----
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+        sh_root = -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
+        const uint32_t bytes_p = (static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
+        mbar_arrive_expect_tx(&mbar, bytes_h + bytes_p);
+        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &mbar);
+        tma_bulk_g2s(sh_par, b.parent + row, bytes_p, &mbar);
+    }
+    {
+        // clear both flag arrays (2*S bytes, S % 32 == 0) with 32-bit stores
+        uint32_t* w = reinterpret_cast<uint32_t*>(sh_nonleaf);
+        const int nw = static_cast<int>(S >> 1);
+        for (int i = tid; i < nw; i += BLOCK) w[i] = 0u;
+    }
+    if (warp == NWARP - 1) {
+        const double* prow = b.params + t * GSM_NPARAM;
+        if (lane == 0) {
+            gsm_setup_consts(K, prow, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
+            K.lg[0] = 0.0;
+        } else if (lane <= GSM_LUT_M) {
+            K.lg[lane] = gsm_lut_entry(prow[GSM_P_SPIKE_SHAPE], lane);
+        }
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+
+    // ---- phase 1: non-leaf marks, root, parent sanitising ----
+    for (int i = tid; i < n; i += BLOCK) {
+        const int32_t p = sh_par[i];
+        if (static_cast<uint32_t>(p) < static_cast<uint32_t>(n)) sh_nonleaf[p] = 1;
+        else {
+            if (p < 0) sh_root = i;
+            else sh_par[i] = -1;  // out-of-range parent: treated as detached (never dereferenced)
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: sampled ancestors -> fake parents; aux values ----
+    const int aux_kind = K.aux_kind;
+    for (int i = tid; i < n; i += BLOCK) {
+        const double h = sh_h[i];
+        const int32_t p = sh_par[i];
+        if (!sh_nonleaf[i] && p >= 0 && sh_h[p] == h) sh_fake[p] = 1;
+        if (aux_kind != GSM_AUX_NONE) sh_aux[i] = gsm_aux(K, h);
+    }
+    __syncthreads();
+
+    // ---- phase 3: per-branch terms ----
+    GsmAcc A;
+    gsm_acc_zero(A);
+    const double* rate_row = b.rate ? b.rate + row : nullptr;
+    const double* spike_row = b.spike + row;
+    const int32_t* nst_row = b.nstubs ? b.nstubs + row : nullptr;
+    double* orate = (WANT_RATES && out_rates) ? out_rates + row : nullptr;
+    double* owsp = (WANT_RATES && out_wspikes) ? out_wspikes + row : nullptr;
+
+    int i = tid;
+    double rate_n = 1.0, spike_n = 0.0;
+    int32_t nst_n = 0;
+    if (i < n) {
+        if (rate_row) rate_n = __ldg(rate_row + i);
+        spike_n = __ldg(spike_row + i);
+        if (nst_row) nst_n = __ldg(nst_row + i);
+    }
+    while (i < n) {
+        const double rate = rate_n, spike = spike_n;
+        const int32_t nst = nst_n;
+        const int inext = i + BLOCK;
+        if (inext < n) {  // software prefetch of the next strip
+            if (rate_row) rate_n = __ldg(rate_row + inext);
+            spike_n = __ldg(spike_row + inext);
+            if (nst_row) nst_n = __ldg(nst_row + inext);
+        }
+        const double h = sh_h[i];
+        const int32_t p = sh_par[i];
+        uint32_t nf = 0;
+        double hp = h, aux = 0.0, auxp = 0.0;
+        if (aux_kind != GSM_AUX_NONE) aux = sh_aux[i];
+        if (sh_nonleaf[i]) nf |= GSM_NF_NONLEAF;
+        if (sh_fake[i]) nf |= GSM_NF_FAKE;
+        if (p < 0) {
+            nf |= GSM_NF_ROOT;
+            auxp = aux;
+        } else {
+            hp = sh_h[p];
+            if (aux_kind != GSM_AUX_NONE) auxp = sh_aux[p];
+            if (sh_fake[p]) nf |= GSM_NF_PARENT_FAKE;
+            if (!(nf & GSM_NF_NONLEAF) && hp == h) nf |= GSM_NF_DA;
+        }
+        gsm_node_terms<WANT_RATES>(K, g_logfact, A, i, n, nf, h, hp, aux, auxp, rate, spike, nst,
+                                   orate ? orate + i : nullptr, owsp ? owsp + i : nullptr);
+        i = inext;
+    }
+
+    // ---- phase 4: reductions (fixed order) + epilogue ----
+    double v0 = warp_sum(A.tree), v1 = warp_sum(A.stub), v2 = warp_sum(A.spike), v3 = warp_sum(A.rate),
+           v4 = warp_sum(A.burst), v5 = warp_sum(A.dist);
+    int32_t c0 = __reduce_add_sync(0xffffffffu, A.n_extant), c1 = __reduce_add_sync(0xffffffffu, A.n_leaf),
+            c2 = __reduce_add_sync(0xffffffffu, A.n_da), c3 = __reduce_add_sync(0xffffffffu, A.n_extinct),
+            c4 = static_cast<int32_t>(__reduce_or_sync(0xffffffffu, static_cast<uint32_t>(A.bad)));
+    if (lane == 0) {
+        sh_red[0][warp] = v0; sh_red[1][warp] = v1; sh_red[2][warp] = v2;
+        sh_red[3][warp] = v3; sh_red[4][warp] = v4; sh_red[5][warp] = v5;
+        sh_redi[0][warp] = c0; sh_redi[1][warp] = c1; sh_redi[2][warp] = c2; sh_redi[3][warp] = c3; sh_redi[4][warp] = c4;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        GsmAcc R;
+        gsm_acc_zero(R);
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+            R.tree += sh_red[0][w]; R.stub += sh_red[1][w]; R.spike += sh_red[2][w];
+            R.rate += sh_red[3][w]; R.burst += sh_red[4][w]; R.dist += sh_red[5][w];
+            R.n_extant += sh_redi[0][w]; R.n_leaf += sh_redi[1][w]; R.n_da += sh_redi[2][w];
+            R.n_extinct += sh_redi[3][w]; R.bad |= sh_redi[4][w];
+        }
+        const int32_t root = sh_root;
+        double res[GSM_NOUT];
+        if (root < 0) {
+#pragma unroll
+            for (int k = 0; k < GSM_NOUT; k++) res[k] = NAN;  // no root: not a tree
+        } else {
+            gsm_finish_consts(K, sh_h[root]);
+            gsm_finalize(K, R, n, sh_fake[root] != 0, res);
+        }
+#pragma unroll
+        for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BranchSpikePrior.getCumulativeProbs (BSP:315-389) for one branch; log-time only, one thread.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gsm_stub_cdf_kernel(const GsmBatch b, int64_t t, int32_t node, double* __restrict__ cdf, int32_t cap,
+                                    int32_t* __restrict__ len_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    GsmTreeConsts K;
+    gsm_setup_consts(K, b.params + t * GSM_NPARAM, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags,
+                     b.stub_mode);
+    K.lg[0] = 0.0;
+    for (int m = 1; m <= GSM_LUT_M; m++) K.lg[m] = gsm_lut_entry(K.shape, m);
+    // the CDF always needs the Poisson mean, whatever the evaluation mode
+    K.aux_kind = K.stub_sampling ? GSM_AUX_EXP_C1 : GSM_AUX_LB;
+    const int64_t row = t * b.stride;
+    const double h = b.height[row + node];
+    const int32_t p = b.parent[row + node];
+    const double hp = p < 0 ? h : b.height[row + p];
+    double mu = 0.0;                                                        // STP:876-878
+    if (hp > h) mu = gsm_expected_stubs(K, h, hp, gsm_aux(K, h), gsm_aux(K, hp));
+    const double x = b.spike[row + node];                                   // BSP:328
+    const bool use_gamma = (b.flags & GSM_F_BSP_HAS_INDICATOR) && K.use_spike;   // BSP:347
+    const double log_mu = log(mu);
+    int32_t k = 0, len = 0;
+    double pcs = 0.0, psum = 0.0;
+    while (pcs < GSM_MAX_CUM_SUM && k < GSM_K_CAP) {                        // BSP:334
+        double branchP = 0.0;
+        double pl = -mu + k * log_mu;                                       // BSP:339
+        pl -= gsm_logfact(g_logfact, k);                                    // BSP:340
+        const double pReal = exp(pl);
+        if (use_gamma) {
+            const double g = gsm_gamma_logdens(K, k + 1, x);                // BSP:344-350 (table is per handle's shape)
+            if (g == -INFINITY || g != g) {
+                if (pcs > 0) break;                                         // BSP:352
+            } else {
+                branchP += exp(pl + g);                                     // BSP:355
+            }
+        } else {
+            branchP += pReal;                                               // BSP:361
+        }
+        pcs += pReal;
+        psum += branchP;
+        if (len < cap) cdf[len] = branchP;
+        len++;
+        k++;
+    }
+    const int32_t w = len < cap ? len : cap;
+    double cum = 0.0;
+    for (int32_t i = 0; i < w; i++) {                                       // BSP:374-387
+        const double pr = cdf[i] / psum;
+        cdf[i] = pr + cum;
+        cum += pr;
+    }
+    *len_out = len;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------------------
+cudaError_t gsm_init_tables() {
+    double h[GSM_LOGFACT_N];
+    h[0] = 0.0;
+    h[1] = 0.0;
+    double s = 0.0;
+    for (int i = 2; i < GSM_LOGFACT_N; i++) {  // same ascending order as the Java loops (STP:567, BSP:121)
+        s += log(static_cast<double>(i));
+        h[i] = s;
+    }
+    return cudaMemcpyToSymbol(g_logfact, h, sizeof(h));
+}
+
+static size_t eval_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
+
+template <int BLOCK>
+static cudaError_t launch_block(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
+    const size_t smem = eval_smem_bytes(b.stride);
+    const dim3 grid(static_cast<unsigned>(b.n_trees));
+    cudaError_t e;
+    if (r || w) {
+        e = cudaFuncSetAttribute(gsm_eval_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gsm_eval_kernel<BLOCK, true><<<grid, BLOCK, smem, st>>>(b, o, r, w);
+    } else {
+        e = cudaFuncSetAttribute(gsm_eval_kernel<BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gsm_eval_kernel<BLOCK, false><<<grid, BLOCK, smem, st>>>(b, o, r, w);
+    }
+    return cudaGetLastError();
+}
+
+int gsm_launch_eval(const GsmBatch& b, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
+                    cudaStream_t stream) {
+    if (b.n_trees <= 0) return 0;
+    int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 512);
+    if (const char* env = getenv("GSM_BLOCK")) {
+        int v = atoi(env);
+        if (v == 64 || v == 128 || v == 256 || v == 512) block = v;
+    }
+    cudaError_t e;
+    switch (block) {
+        case 64: e = launch_block<64>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
+        case 128: e = launch_block<128>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
+        case 256: e = launch_block<256>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
+        default: e = launch_block<512>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
+    }
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}
+
+int gsm_launch_stub_cdf(const GsmBatch& b, int64_t tree, int32_t node, double* d_cdf, int32_t cap, int32_t* d_len,
+                        cudaStream_t stream) {
+    gsm_stub_cdf_kernel<<<1, 32, 0, stream>>>(b, tree, node, d_cdf, cap, d_len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}

@@ -1,0 +1,145 @@
+"""Thin Python holder of one gsm_handle (one chain / one batch) — plumbing only: it moves pointers
+across the C ABI of include/gsm_b200.h and never computes a branch term itself."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+from . import _lib
+
+
+class GsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gsm_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _np(a, dtype, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class GsmEngine:
+    def __init__(self, max_trees=0, max_nodes=0, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.gsm_create(C.byref(self._h), int(device), int(max_trees), int(max_nodes))
+        if rc != abi.OK:
+            raise GsmError(rc, (self._lib.gsm_last_error(None) or b"").decode())
+        self.device = int(device)
+        self.n_trees = 0
+        self.n_nodes = 0
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self._lib.gsm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != abi.OK:
+            raise GsmError(rc, (self._lib.gsm_last_error(self._h) or b"").decode())
+
+    # ---- wiring ----
+    def set_mode(self, stub_mode, flags):
+        self._ck(self._lib.gsm_set_mode(self._h, int(stub_mode), int(flags)))
+
+    # ---- host-buffer path ----
+    def upload_trees(self, height, parent, node_count=None):
+        height = _np(height, np.float64)
+        T, N = height.shape
+        parent = _np(parent, np.int32, (T, N))
+        node_count = _np(node_count, np.int32, (T,))
+        self._ck(self._lib.gsm_upload_trees(self._h, T, N, _p(height), _p(parent), _p(node_count)))
+        self.n_trees, self.n_nodes = T, N
+
+    def upload_branch_params(self, rate=None, spike=None, nstubs=None):
+        shp = (self.n_trees, self.n_nodes)
+        rate, spike, nstubs = _np(rate, np.float64, shp), _np(spike, np.float64, shp), _np(nstubs, np.int32, shp)
+        self._ck(self._lib.gsm_upload_branch_params(self._h, _p(rate), _p(spike), _p(nstubs)))
+
+    def upload_tree_params(self, params, use_spike=None):
+        params = _np(params, np.float64, (self.n_trees, abi.NPARAM))
+        use_spike = _np(use_spike, np.uint8, (self.n_trees,))
+        self._ck(self._lib.gsm_upload_tree_params(self._h, _p(params), _p(use_spike)))
+
+    def eval(self, want_rates=False, want_wspikes=False):
+        T, N = self.n_trees, self.n_nodes
+        out = np.empty((T, abi.NOUT), np.float64)
+        rates = np.empty((T, N), np.float64) if want_rates else None
+        wsp = np.empty((T, N), np.float64) if want_wspikes else None
+        self._ck(self._lib.gsm_eval(self._h, _p(out), _p(rates), _p(wsp)))
+        return {"out": out, "rates": rates, "wspikes": wsp}
+
+    def eval_host(self, height, parent, spike, params, rate=None, nstubs=None, use_spike=None, node_count=None,
+                  want_rates=False, want_wspikes=False, out=None):
+        height = _np(height, np.float64)
+        T, N = height.shape
+        parent = _np(parent, np.int32, (T, N))
+        spike = _np(spike, np.float64, (T, N))
+        rate = _np(rate, np.float64, (T, N))
+        nstubs = _np(nstubs, np.int32, (T, N))
+        params = _np(params, np.float64, (T, abi.NPARAM))
+        use_spike = _np(use_spike, np.uint8, (T,))
+        node_count = _np(node_count, np.int32, (T,))
+        if out is None:
+            out = np.empty((T, abi.NOUT), np.float64)
+        rates = np.empty((T, N), np.float64) if want_rates else None
+        wsp = np.empty((T, N), np.float64) if want_wspikes else None
+        self._ck(self._lib.gsm_eval_host(self._h, T, N, _p(height), _p(parent), _p(node_count), _p(rate), _p(spike),
+                                         _p(nstubs), _p(params), _p(use_spike), _p(out), _p(rates), _p(wsp)))
+        return {"out": out, "rates": rates, "wspikes": wsp}
+
+    def eval_host_ptrs(self, T, N, height, parent, node_count, rate, spike, nstubs, params, use_spike, out_tree,
+                       out_rates=None, out_wspikes=None):
+        """Raw-pointer form (ints / c_void_p), e.g. pinned torch tensors' data_ptr()."""
+        vp = lambda x: None if x is None else C.c_void_p(int(x))
+        self._ck(self._lib.gsm_eval_host(self._h, int(T), int(N), vp(height), vp(parent), vp(node_count), vp(rate),
+                                         vp(spike), vp(nstubs), vp(params), vp(use_spike), vp(out_tree), vp(out_rates),
+                                         vp(out_wspikes)))
+
+    def stub_cdf(self, tree, node, cap=4096):
+        buf = np.empty(cap, np.float64)
+        n = C.c_int32(0)
+        self._ck(self._lib.gsm_stub_cdf(self._h, int(tree), int(node), _p(buf), cap, C.byref(n)))
+        return buf[: min(n.value, cap)].copy(), n.value
+
+    # ---- device-resident path (torch tensors own the memory) ----
+    def bind_batch(self, batch):
+        """batch: synthetic.Batch (or anything with the same tensor attributes) already on this device."""
+        self._keep = batch
+        self._ck(self._lib.gsm_bind_device(self._h, batch.n_trees, batch.n_nodes, batch.stride, _dp(batch.height),
+                                           _dp(batch.parent), _dp(getattr(batch, "node_count", None)), _dp(batch.rate),
+                                           _dp(batch.spike), _dp(batch.nstubs), _dp(batch.params), _dp(batch.use_spike)))
+        self.n_trees, self.n_nodes = batch.n_trees, batch.n_nodes
+
+    def eval_device(self, out_tree, out_rates=None, out_wspikes=None, stream=None):
+        """Asynchronous launch on `stream` (an int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self._lib.gsm_eval_device(self._h, _dp(out_tree), _dp(out_rates), _dp(out_wspikes),
+                                           C.c_void_p(stream) if stream else None))
+
+    def sync(self):
+        self._ck(self._lib.gsm_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.gsm_launch_count(self._h))

@@ -1,0 +1,226 @@
+"""Deterministic synthetic tree-state batches of the shapes BASELINE.json names.
+
+This is input generation only (bench / tests); it evaluates nothing on the hot path.  It is written in
+device-agnostic torch so the same code makes small CPU batches for the parity tests and full-size
+batches directly in HBM for the bench.
+
+Conventions follow the reference's simulators (ForwardTimeSimulatorResub.java:297-308,
+BirthDeathStubSimulator.java:366-377): leaves are nodes 0..n-1, internal nodes follow, the root is
+node N-1 (N = 2n-1); a sampled ancestor is a zero-length leaf under a "fake" internal node; stub
+counts live on branches (root: none).
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _abi as abi
+
+SEEDS = {"C2": 20261019, "C3": 20261020, "C4": 20261021, "C5": 20261022}
+
+
+@dataclass
+class Batch:
+    n_trees: int
+    n_taxa: int
+    n_nodes: int
+    stride: int
+    flags: int
+    stub_mode: int
+    height: torch.Tensor      # [T, stride] f64
+    parent: torch.Tensor      # [T, stride] i32, -1 = root
+    rate: torch.Tensor        # [T, stride] f64
+    spike: torch.Tensor       # [T, stride] f64
+    nstubs: torch.Tensor      # [T, stride] i32
+    params: torch.Tensor      # [T, NPARAM] f64
+    use_spike: torch.Tensor   # [T] u8
+    kind: str = ""
+
+    def to(self, device):
+        kw = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
+        return Batch(**kw)
+
+    def dense(self, name):
+        """[T, n_nodes] contiguous host numpy view of a branch array (the layout the C ABI takes)."""
+        return getattr(self, name)[:, : self.n_nodes].contiguous().cpu().numpy()
+
+    def branch_count(self):
+        return self.n_trees * self.n_nodes
+
+
+DEFAULT_FLAGS = (abi.F_HAS_INDICATOR | abi.F_HAS_RATES | abi.F_STUBS_TO_CLOCK | abi.F_STUBS_TO_SPIKE_PRIOR
+                 | abi.F_STUBS_TO_TREE_PRIOR)
+
+
+def device_stride(n_nodes):
+    return max(32, (n_nodes + 31) // 32 * 32)
+
+
+def _topology(T, n, gen, device):
+    """Random binary trees by uniformly joining pairs of active lineages (Yule-like).  Internal node
+    n+k is created at step k, so node numbers increase with height and the root is node 2n-2."""
+    N = 2 * n - 1
+    parent = torch.full((T, N), -1, dtype=torch.int64, device=device)
+    active = torch.arange(n, device=device).expand(T, n).clone()
+    ar = torch.arange(T, device=device)
+    u = torch.rand((n - 1, T, 2), generator=gen, device=device, dtype=torch.float64) if n > 1 else None
+    for k in range(n - 1):
+        m = n - k
+        i = (u[k, :, 0] * m).long().clamp_(max=m - 1)
+        j = (u[k, :, 1] * (m - 1)).long().clamp_(max=m - 2)
+        j = j + (j >= i).long()
+        lo = torch.minimum(i, j)
+        hi = torch.maximum(i, j)
+        a = active[ar, lo]
+        b = active[ar, hi]
+        new = n + k
+        parent[ar, a] = new
+        parent[ar, b] = new
+        active[ar, lo] = new
+        active[ar, hi] = active[ar, m - 1]
+    return parent
+
+
+def _expected_stubs(h1, h0, lam, mu, psi, rho):
+    """Poisson mean of the stub count on a branch (StumpedTreePrior.java:749-769), vectorised; only
+    used to draw plausible stub counts."""
+    lam, mu, psi, rho = (x.unsqueeze(1) for x in (lam, mu, psi, rho))
+    c1 = torch.sqrt(torch.abs((lam - mu - psi) ** 2 + 4 * lam * psi))
+    c2 = -(lam - mu - 2 * lam * rho - psi) / c1
+    f = ((c2 - 1) * torch.exp(-c1 * h1) - c2 - 1) / ((c2 - 1) * torch.exp(-c1 * h0) - c2 - 1)
+    e_s = (h0 - h1) * (lam + mu + psi - c1) + 2 * torch.log(f)
+    lb1 = torch.log(lam * torch.exp((lam - mu) * h1) - mu)
+    lb0 = torch.log(lam * torch.exp((lam - mu) * h0) - mu)
+    e_n = 2 * ((lb1 - lb0) + lam * (h0 - h1))
+    nos = (psi == 0) & (rho == 1)
+    e = torch.where(nos, e_n, e_s)
+    return torch.nan_to_num(e, nan=0.0, posinf=0.0, neginf=0.0).clamp_(min=0.0, max=50.0)
+
+
+def make_batch(kind, n_trees, n_taxa, seed=None, device="cpu", tree_offset=0):
+    """kind: 'C2' (BDWS: psi=0, rho=1, ultrametric, spikes on), 'C3' (FBDWS: psi>0, rho<1, dated tips,
+    5% sampled ancestors, indicator Bernoulli(0.5) per state), 'C4' (ultrametric; rho=1 for even trees,
+    U(0.1,1) for odd trees)."""
+    kind = kind.upper()
+    if kind not in ("C2", "C3", "C4"):
+        raise ValueError("kind must be C2, C3 or C4")
+    if seed is None:
+        seed = SEEDS[kind]
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed) + 7919 * int(tree_offset))
+    T, n = int(n_trees), int(n_taxa)
+    N = 2 * n - 1
+    S = device_stride(N)
+    f64 = torch.float64
+
+    def rand(*shape):
+        return torch.rand(shape, generator=gen, device=device, dtype=f64)
+
+    def randn(*shape):
+        return torch.randn(shape, generator=gen, device=device, dtype=f64)
+
+    def expo(*shape):
+        return -torch.log1p(-rand(*shape))
+
+    # ---- per-tree parameters (template defaults / priors, fxtemplates/GammaSpikeClockModel.xml:31-70) ----
+    lam = torch.exp(0.5 * randn(T)).clamp_(0.05, 5.0)
+    r0 = 1.0 + expo(T)
+    mu = lam / r0
+    if kind == "C3":
+        # Beta(1,5) via inverse CDF: 1 - (1-u)^(1/5)
+        s = 1.0 - torch.pow(1.0 - rand(T), 0.2)
+        s = s.clamp_(1e-3, 0.9)
+        psi = s * mu / (1 - s)
+        rho = 0.1 + 0.9 * rand(T)
+    elif kind == "C4":
+        psi = torch.zeros(T, dtype=f64, device=device)
+        odd = ((torch.arange(T, device=device) + tree_offset) % 2) == 1
+        rho = torch.where(odd, 0.1 + 0.9 * rand(T), torch.ones(T, dtype=f64, device=device))
+    else:
+        psi = torch.zeros(T, dtype=f64, device=device)
+        rho = torch.ones(T, dtype=f64, device=device)
+    shape = torch.exp(torch.log(torch.tensor(2.0, dtype=f64)) - 0.125 + 0.5 * randn(T)).clamp_(min=0.2)
+    spike_mean = torch.exp(torch.log(torch.tensor(0.01, dtype=f64)) - 0.72 + 1.2 * randn(T)).clamp_(1e-6, 1.0)
+    clock_sd = torch._standard_gamma(torch.full((T,), 5.0, dtype=f64, device=device), generator=gen) * 0.05
+    clock_rate = torch.ones(T, dtype=f64, device=device)
+
+    # ---- topology + ultrametric heights ----
+    parent = _topology(T, n, gen, device)
+    height = torch.zeros((T, N), dtype=f64, device=device)
+    if n > 1:
+        lineages = torch.arange(n, 1, -1, device=device, dtype=f64)           # n, n-1, ..., 2
+        inc = expo(T, n - 1) / lineages
+        ih = torch.cumsum(inc, dim=1)
+        t_target = torch.minimum(1.0 + 19.0 * rand(T), 50.0 / lam)
+        ih = ih * (t_target / ih[:, -1]).unsqueeze(1)
+        height[:, n:] = ih
+    root_h = height[:, N - 1].clone()
+
+    ar = torch.arange(T, device=device).unsqueeze(1)
+    leaf_parent = parent[:, :n].clamp(min=0)
+    is_sa = torch.zeros((T, N), dtype=torch.bool, device=device)
+    if kind == "C3" and n > 1:
+        ph = height[ar, leaf_parent]                                          # parent heights of leaves
+        dated = rand(T, n) >= 0.6
+        lh = torch.where(dated, 0.8 * rand(T, n) * ph, torch.zeros_like(ph))
+        # sampled ancestors: ~5% of leaves, at most one per parent; height == parent height exactly
+        pick = rand(T, n) < 0.05
+        idx = torch.arange(n, device=device).expand(T, n)
+        big = torch.full((T, N), n, dtype=torch.int64, device=device)
+        first = big.scatter_reduce(1, leaf_parent, torch.where(pick, idx, torch.full_like(idx, n)), reduce="amin")
+        sa = pick & (first[ar, leaf_parent] == idx)
+        lh = torch.where(sa, ph, lh)
+        height[:, :n] = lh
+        is_sa[:, :n] = sa
+
+    # ---- derived predicates (as Node.isDirectAncestor / isFake define them) ----
+    par_c = parent.clamp(min=0)
+    hp = height[ar, par_c]
+    is_root = parent < 0
+    hp = torch.where(is_root, height, hp)
+    fake = torch.zeros((T, N), dtype=torch.int64, device=device).scatter_reduce(
+        1, par_c, (is_sa & ~is_root).long(), reduce="amax").bool()      # a fake node has a direct-ancestor child
+    parent_fake = fake[ar, par_c] & ~is_root
+
+    # ---- per-branch values ----
+    e = _expected_stubs(height, hp, lam, mu, psi, rho)
+    e = torch.where(is_root | is_sa | (hp <= height), torch.zeros_like(e), e)
+    nstubs = torch.poisson(e, generator=gen).to(torch.int64)
+    nstubs[:, N - 1] = 0
+    m = torch.where(is_root, nstubs + 1, torch.where(is_sa, torch.zeros_like(nstubs),
+                                                      torch.where(parent_fake, nstubs, nstubs + 1)))
+    alpha = (shape.unsqueeze(1) * m.to(f64)).clamp_(min=1e-3)
+    g = torch._standard_gamma(alpha, generator=gen) / shape.unsqueeze(1)
+    spike = torch.where(m > 0, g.clamp_(min=1e-300), torch.zeros_like(g))
+    sd = clock_sd.unsqueeze(1)
+    rate = torch.exp(-0.5 * sd * sd + sd * randn(T, N))
+
+    if kind == "C3":
+        use_spike = (rand(T) < 0.5).to(torch.uint8)
+    else:
+        use_spike = torch.ones(T, dtype=torch.uint8, device=device)
+
+    params = torch.stack([clock_rate, spike_mean, shape, clock_sd, lam, mu, psi, rho, root_h * 1.1], dim=1).contiguous()
+
+    def pad(x, dtype, fill=0):
+        out = torch.full((T, S), fill, dtype=dtype, device=device)
+        out[:, :N] = x.to(dtype)
+        return out
+
+    return Batch(n_trees=T, n_taxa=n, n_nodes=N, stride=S, flags=DEFAULT_FLAGS, stub_mode=abi.STUBS_COUNTS,
+                 height=pad(height, f64), parent=pad(parent, torch.int32, -1), rate=pad(rate, f64, 1.0),
+                 spike=pad(spike, f64), nstubs=pad(nstubs, torch.int32), params=params, use_spike=use_spike, kind=kind)
+
+
+def make_batch_chunked(kind, n_trees, n_taxa, seed=None, device="cpu", chunk=16384):
+    """Same distribution as make_batch, generated in chunks to bound temporary memory (full-size bench batches)."""
+    parts = []
+    for t0 in range(0, n_trees, chunk):
+        parts.append(make_batch(kind, min(chunk, n_trees - t0), n_taxa, seed=seed, device=device, tree_offset=t0))
+    if len(parts) == 1:
+        return parts[0]
+    b0 = parts[0]
+    cat = lambda name: torch.cat([getattr(p, name) for p in parts], dim=0)
+    return Batch(n_trees=n_trees, n_taxa=b0.n_taxa, n_nodes=b0.n_nodes, stride=b0.stride, flags=b0.flags,
+                 stub_mode=b0.stub_mode, height=cat("height"), parent=cat("parent"), rate=cat("rate"),
+                 spike=cat("spike"), nstubs=cat("nstubs"), params=cat("params"), use_spike=cat("use_spike"), kind=b0.kind)

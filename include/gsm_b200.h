@@ -1,0 +1,171 @@
+/*
+ * gsm_b200.h — C ABI of libgsm_b200.so: the B200 (sm_100a) implementation of GammaSpikeModel's
+ * per-branch compute, evaluated for batches of tree states at once.
+ *
+ * This is the drop-in boundary.  The reference is a pure-Java BEAST 2 package with
+ * no native interface of its own, so each entry point below names the Java method(s) whose body it
+ * replaces; the Java classes keep their public API and call these through Panama (java.lang.foreign)
+ * or JNI — see INTEGRATION.md for the binding stub.  Signatures use only int32_t / int64_t /
+ * uint32_t / double / pointers: no structs by value, no callbacks, no C++ or torch types.
+ *
+ * Citations are relative to the reference tree (/root/reference):
+ *   PRCM  src/gammaspike/clockmodel/PunctuatedRelaxedClockModel.java
+ *   BSP   src/gammaspike/distribution/BranchSpikePrior.java
+ *   BRP   src/gammaspike/distribution/BranchRatePrior.java
+ *   STP   src/gammaspike/distribution/StumpedTreePrior.java
+ *   Stubs src/gammaspike/tree/Stubs.java
+ *   SPL   src/gammaspike/logger/SaltativeProportionLogger.java
+ *   SpikeSize src/gammaspike/clockmodel/SpikeSize.java
+ *
+ * Conventions
+ *   - A batch is T trees ("states") of at most N nodes each.  Host arrays are tree-major, dense:
+ *     element (t, i) at [t * n_nodes + i].  Node numbering is BEAST's (Node.getNr()).
+ *   - parent[i] = -1 for the root.  Leaf / sampled-ancestor / "fake" status is derived on the device
+ *     from (height, parent) exactly as beast.base.evolution.tree.Node does (isLeaf, isDirectAncestor,
+ *     isFake), so topology is one int32 per node.
+ *   - Every function returns GSM_OK (0) or a GSM_E_* code; gsm_last_error() gives the text.
+ *     An invalid *state* (e.g. lambda <= mu, a negative spike) is NOT an error: the reference returns
+ *     Double.NEGATIVE_INFINITY (STP:160-164, BSP:60-75, BRP:36-50) and so do we, in the result row.
+ *   - One handle = one chain/batch; calls on one handle are serialised by the caller; different
+ *     handles may be used from different threads (one CUDA stream per handle, no global state).
+ *   - There is no CPU fallback: if no CUDA device is usable gsm_create fails.
+ */
+#ifndef GSM_B200_H
+#define GSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSM_ABI_VERSION 1
+
+/* ---- status codes ---- */
+#define GSM_OK             0
+#define GSM_E_ARG          1   /* bad argument */
+#define GSM_E_CUDA         2   /* CUDA runtime error (text in gsm_last_error) */
+#define GSM_E_STATE        3   /* call order: e.g. eval before upload */
+#define GSM_E_UNSUPPORTED  4   /* e.g. n_nodes above GSM_MAX_NODES */
+#define GSM_E_NOMEM        5
+
+/* ---- wiring flags: which optional BEAST Inputs are connected (gsm_set_mode) ---- */
+#define GSM_F_HAS_INDICATOR        (1u << 0)   /* PRCM.indicator wired (PRCM:34); value per tree = use_spike[t] */
+#define GSM_F_NO_SPIKE_DATED_TIPS  (1u << 1)   /* PRCM.noSpikeOnDatedTips = true (PRCM:42, 185-187) */
+#define GSM_F_HAS_RATES            (1u << 2)   /* PRCM.rates wired (PRCM:36, 213) */
+#define GSM_F_RELAXED_FALSE        (1u << 3)   /* PRCM.relaxed wired and false (PRCM:216-220) */
+#define GSM_F_STUBS_TO_CLOCK       (1u << 4)   /* PRCM.stubs wired (PRCM:30, 192-195) */
+#define GSM_F_STUBS_TO_SPIKE_PRIOR (1u << 5)   /* BSP.stubs wired (BSP:28, 77) */
+#define GSM_F_STUBS_TO_TREE_PRIOR  (1u << 6)   /* STP.stubs wired (STP:46, 219) */
+#define GSM_F_IGNORE_TREE_PRIOR    (1u << 7)   /* STP.ignoreTreePrior (STP:49, 174) */
+#define GSM_F_IGNORE_STUB_PRIOR    (1u << 8)   /* STP.ignoreStubPrior (STP:50, 219) */
+#define GSM_F_COND_SAMPLING        (1u << 9)   /* STP.conditionOnSampling (STP:26, 446) */
+#define GSM_F_COND_RHO_SAMPLING    (1u << 10)  /* STP.conditionOnRhoSampling (STP:28, 455) */
+#define GSM_F_COND_ROOT            (1u << 11)  /* STP.conditionOnRoot (STP:31, 179) */
+#define GSM_F_ORIGIN               (1u << 12)  /* STP.origin wired (STP:24, 179-180); value = params[GSM_P_ORIGIN] */
+#define GSM_F_BSP_HAS_INDICATOR    (1u << 13)  /* BSP.indicator wired (BSP:35, 347) — used by gsm_stub_cdf only */
+
+/* ---- Stubs.StubMode (Stubs:36-40) ---- */
+#define GSM_STUBS_NOSTUB  0   /* integrate over stub counts: getNStubsOnBranch == -1 (Stubs:348-350) */
+#define GSM_STUBS_COUNTS  1   /* stubsPerBranch, dimension N-1 (Stubs:200, 352-355) */
+#define GSM_STUBS_EXACT   2   /* RJ placement; evaluated through per-branch counts (Stubs:357-364) */
+
+/* ---- per-tree parameter row: params[t * GSM_NPARAM + k] ---- */
+#define GSM_NPARAM 9
+#define GSM_P_CLOCK_RATE  0   /* clock.rate / GSMclockRate  (PRCM:228) */
+#define GSM_P_SPIKE_MEAN  1   /* GSMspikeMean               (PRCM:204) */
+#define GSM_P_SPIKE_SHAPE 2   /* GSMspikeShape              (BSP:58)   */
+#define GSM_P_CLOCK_SD    3   /* GSMclockSD                 (BRP:33)   */
+#define GSM_P_LAMBDA      4   /* STP.getLambda()            (STP:672-690) */
+#define GSM_P_MU          5   /* STP.getMu()                (STP:692-708) */
+#define GSM_P_PSI         6   /* STP.getPsi()               (STP:710-728) */
+#define GSM_P_RHO         7   /* STP.getRho()               (STP:730-737) */
+#define GSM_P_ORIGIN      8   /* STP.origin                 (STP:668-670) */
+
+/* ---- per-tree result row: out_tree[t * GSM_NOUT + k] ---- */
+#define GSM_NOUT 8
+#define GSM_O_STP_LOGP    0   /* StumpedTreePrior.calculateTreeLogLikelihood (STP:150-284), before the host-side
+                                 nExtantTaxa check (STP:196-200; cross-call state kept by the caller) */
+#define GSM_O_TREE_LOGP   1   /* its treeLogP component (STP:167) */
+#define GSM_O_STUB_LOGP   2   /* its stubLogP component (STP:168) */
+#define GSM_O_SPIKE_LOGP  3   /* BranchSpikePrior.calculateLogP (BSP:53-187) */
+#define GSM_O_RATE_LOGP   4   /* BranchRatePrior.calculateLogP (BRP:29-65) == template Prior+LogNormal */
+#define GSM_O_SUM_BURST   5   /* SaltativeProportionLogger abruptChange (SPL:36, 53-54) */
+#define GSM_O_SUM_DIST    6   /* SaltativeProportionLogger totalChange  (SPL:35, 44-49); ProportionOfSaltation = [5]/[6] */
+#define GSM_O_N_EXTANT    7   /* number of extant leaves n (STP:190-195) */
+
+#define GSM_MAX_NODES 8192    /* largest tree (nodes) the one-CTA-per-tree kernels stage in shared memory */
+
+typedef struct gsm_handle gsm_handle;
+
+/* ---- lifecycle ---- */
+int  gsm_abi_version(void);
+int  gsm_device_count(void);                 /* number of visible CUDA devices; 0 => nothing will work */
+int  gsm_create(gsm_handle** out, int32_t device_id, int64_t max_trees, int32_t max_nodes);
+int  gsm_destroy(gsm_handle* h);
+const char* gsm_last_error(const gsm_handle* h);   /* h may be NULL: error of the last failed gsm_create on this thread */
+
+/* Which Inputs are wired and which Stubs mode is used (replaces the `Input.get() != null` tests at
+ * PRCM:181,185,192-195,213-216; BSP:77; STP:174,179,219 and Stubs.initAndValidate mode selection Stubs:138-245). */
+int  gsm_set_mode(gsm_handle* h, int32_t stub_mode, uint32_t flags);
+
+/* ---- host-buffer path (what the Java plugin calls) ---------------------------------------------
+ * All host arrays are caller-owned and are copied before the call returns. */
+
+/* Tree states: Tree.getNodesAsArray() heights and parents.  node_count may be NULL (every tree has
+ * n_nodes nodes) or give a per-tree count <= n_nodes (ragged batch; trailing entries ignored). */
+int  gsm_upload_trees(gsm_handle* h, int64_t n_trees, int32_t n_nodes,
+                      const double* height, const int32_t* parent, const int32_t* node_count);
+/* GSMbranchRates (PRCM.rates), GSMspikes (PRCM.spikes / BSP.spikes), stubsPerBranch (Stubs:50).  A NULL
+ * pointer leaves that array as it was.  nstubs has n_nodes entries per tree; entry i >= n-1 is ignored
+ * in COUNTS mode (Stubs:200, 354). */
+int  gsm_upload_branch_params(gsm_handle* h, const double* rate, const double* spike, const int32_t* nstubs);
+/* Per-tree scalars (GSM_P_*) and the GSMuseSpikeModel indicator (NULL => true for every tree). */
+int  gsm_upload_tree_params(gsm_handle* h, const double* params, const uint8_t* use_spike);
+
+/* Evaluate the resident batch.  out_tree [T][GSM_NOUT] is required.  out_rates [T][n_nodes] (optional)
+ * receives PRCM.getRatesArray() (PRCM:267-276; getRateForBranch PRCM:225-242); out_wspikes [T][n_nodes]
+ * (optional) receives GSMweightedSpikes = SpikeSize.getArrayValue(i) with clockModel wired
+ * (SpikeSize:48-56 -> PRCM.getBurstSize PRCM:167-208).  Blocks until the outputs are written. */
+int  gsm_eval(gsm_handle* h, double* out_tree, double* out_rates, double* out_wspikes);
+
+/* One call = upload + eval + download for a whole host-resident batch, streamed through the device in
+ * chunks so that copies overlap the kernels (use pinned host memory, gsm_host_alloc, for full PCIe speed).
+ * Arguments as in the gsm_upload_* functions and gsm_eval. */
+int  gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes,
+                   const double* height, const int32_t* parent, const int32_t* node_count,
+                   const double* rate, const double* spike, const int32_t* nstubs,
+                   const double* params, const uint8_t* use_spike,
+                   double* out_tree, double* out_rates, double* out_wspikes);
+
+/* BranchSpikePrior.getCumulativeProbs(mu, nodeNr) (BSP:315-389) for one branch of one resident tree, with
+ * mu = StumpedTreePrior.getMeanStubNumber(h_node, h_parent) (STP:876-892) as Stubs.sampleNStubsOnBranch
+ * computes it (Stubs:424-447).  Writes min(*len, cap) cumulative probabilities; *len = the Java array length. */
+int  gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t cap, int32_t* len);
+
+/* Pinned host memory for the arrays above (optional; any host pointer is accepted). */
+int  gsm_host_alloc(void** out, int64_t bytes);
+int  gsm_host_free(void* p);
+
+/* ---- device-resident path (inputs already in HBM; used by the bench and by multi-GPU hosts) ------
+ * Row pitch on the device is `stride` elements (>= n_nodes; use gsm_device_stride(n_nodes) so that
+ * every row starts 128-byte aligned).  Pointers are device pointers owned by the caller (e.g. torch
+ * tensors); they must stay valid until the evaluation that uses them has completed. */
+int64_t gsm_device_stride(int32_t n_nodes);
+int  gsm_bind_device(gsm_handle* h, int64_t n_trees, int32_t n_nodes, int64_t stride,
+                     const double* d_height, const int32_t* d_parent, const int32_t* d_node_count,
+                     const double* d_rate, const double* d_spike, const int32_t* d_nstubs,
+                     const double* d_params, const uint8_t* d_use_spike);
+/* Launch on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) and return without
+ * synchronising.  d_out_rates / d_out_wspikes have pitch `stride` and may be NULL. */
+int  gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
+                     void* cuda_stream);
+int  gsm_sync(gsm_handle* h);
+
+/* Number of kernels this handle has launched since creation (bench "gpu_launches"). */
+int64_t gsm_launch_count(const gsm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSM_B200_H */

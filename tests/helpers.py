@@ -1,0 +1,109 @@
+"""Shared helpers of the test-suite: oracle / emulator / C-ABI runners on a synthetic.Batch and comparisons."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import oracle
+from gammaspikemodel_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-10   # north_star tolerance for fp64 log-densities, rates and ProportionOfSaltation
+ATOL = 1e-9    # floor for sums of O(1e3) terms that happen to land near zero
+
+_emu = None
+
+
+def emu():
+    global _emu
+    if _emu is None:
+        _emu = C.CDLL(os.path.join(ROOT, "tests", "_emu", "libgsm_emu.so"))
+        _emu.gsm_emu_eval_batch.argtypes = [C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 11
+        _emu.gsm_emu_eval_batch.restype = C.c_int
+    return _emu
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_arrays(b):
+    """dense [T][N] numpy arrays of a synthetic.Batch (the layout the C ABI takes)"""
+    return dict(height=b.dense("height"), parent=b.dense("parent"), rate=b.dense("rate"), spike=b.dense("spike"),
+                nstubs=b.dense("nstubs"), params=b.params.cpu().numpy().copy(), use_spike=b.use_spike.cpu().numpy().copy())
+
+
+def run_oracle(a, flags, mode, node_count=None, rates=True, threads=0):
+    r = oracle.eval_batch(flags, mode, a["height"], a["parent"], a["rate"], a["spike"], a["nstubs"], a["params"],
+                          a["use_spike"], node_count=node_count, want_rates=rates, want_wspikes=rates, n_threads=threads)
+    return r
+
+
+def run_emu(a, flags, mode, node_count=None, rates=True):
+    T, N = a["height"].shape
+    out = np.empty((T, abi.NOUT))
+    r = np.full((T, N), np.nan) if rates else None
+    w = np.full((T, N), np.nan) if rates else None
+    nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
+    emu().gsm_emu_eval_batch(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
+                             _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w))
+    return {"out": out, "rates": r, "wspikes": w}
+
+
+def run_capi(a, flags, mode, node_count=None, rates=True, engine=None):
+    from gammaspikemodel_b200 import GsmEngine
+    T, N = a["height"].shape
+    eng = engine or GsmEngine(max_trees=max(T, 1), max_nodes=max(N, 1))
+    eng.set_mode(mode, flags)
+    eng.upload_trees(a["height"], a["parent"], node_count)
+    eng.upload_branch_params(a["rate"], a["spike"], a["nstubs"])
+    eng.upload_tree_params(a["params"], a["use_spike"])
+    r = eng.eval(want_rates=rates, want_wspikes=rates)
+    if engine is None:
+        eng.close()
+    return r
+
+
+def rel_err(got, ref):
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    with np.errstate(all="ignore"):
+        d = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    return np.where(same, 0.0, d)
+
+
+def assert_close(got, ref, rtol=RTOL, atol=ATOL, what=""):
+    """got == ref within rtol (relative) or atol (absolute); NaN matches NaN, inf matches the same inf."""
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    with np.errstate(all="ignore"):
+        ok = same | (np.abs(got - ref) <= atol + rtol * np.abs(ref))
+    if not np.all(ok):
+        bad = np.argwhere(~ok)
+        i = tuple(bad[0])
+        raise AssertionError("%s: %d mismatches; first at %s: got %r, ref %r (rel %.3g)"
+                             % (what, len(bad), i, got[i], ref[i], rel_err(got[i], ref[i])))
+
+
+def assert_results_match(got, ref, n_nodes=None, node_count=None, what=""):
+    assert_close(got["out"], ref["out"], what=what + " out_tree")
+    # integer-valued output: bit-exact
+    assert np.array_equal(got["out"][:, abi.O_N_EXTANT], ref["out"][:, abi.O_N_EXTANT]), what + " nExtant"
+    for key in ("rates", "wspikes"):
+        if got.get(key) is not None and ref.get(key) is not None:
+            g, r = got[key], ref[key]
+            if node_count is not None:
+                mask = np.arange(g.shape[1])[None, :] < np.asarray(node_count)[:, None]
+                g, r = np.where(mask, g, 0.0), np.where(mask, r, 0.0)
+            assert_close(g, r, atol=0.0, what=what + " " + key)
+
+
+def variant(a, flags, **edits):
+    """copy of the host arrays with per-tree parameter edits, e.g. psi=0.0, rho=1.0"""
+    b = {k: v.copy() for k, v in a.items()}
+    idx = dict(clock_rate=abi.P_CLOCK_RATE, spike_mean=abi.P_SPIKE_MEAN, shape=abi.P_SPIKE_SHAPE, sigma=abi.P_CLOCK_SD,
+               lam=abi.P_LAMBDA, mu=abi.P_MU, psi=abi.P_PSI, rho=abi.P_RHO, origin=abi.P_ORIGIN)
+    for k, v in edits.items():
+        b["params"][:, idx[k]] = v
+    return b
