@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — branch logP evaluations / second of the B200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4shard|c2|c3] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path (clock-rate map + spike / rate / stub prior logP + tree prior +
+ProportionOfSaltation sums) over one resident synthetic batch: one launch of gsm_eval_kernel per rank,
+followed at N>1 by the NCCL all-gather of the per-tree result rows (the only collective on the path).
+Default workload: the per-GPU shard of BASELINE config 4 (1M trees x 2,000 taxa over 8 GPUs =
+125,000 trees x 3,999 nodes per GPU, 16 GB of inputs, far larger than L2); scaling is weak, so N=8 is
+exactly the 1M-tree configuration.
+
+Prints ONE JSON line (rank 0).  `--impl reference` instead times the CPU restatement of the reference
+(oracle/, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "branch_logp_evals_per_sec"
+UNIT = "branch evals/s"
+BYTES_PER_BRANCH = 32      # height 8 + rate 8 + spike 8 + stub count 4 + parent 4
+BYTES_PER_TREE = 72 + 1 + 64  # params row + indicator in, result row out
+
+WORKLOADS = {
+    # name: (kind, trees per GPU, taxa, description)
+    "c4shard": ("C4", 125_000, 2000, "BASELINE config 4 shard: 125,000 trees x 2,000 taxa per GPU (1M trees at 8 GPUs), "
+                                     "BDWS stub counts, rho=1 / rho<1 alternating, spikes on"),
+    "c3": ("C3", 100_000, 1000, "BASELINE config 3: 100k trees x 1,000 taxa, FBDWS, sampled ancestors, rho<1, indicator per state"),
+    "c2": ("C2", 10_000, 200, "BASELINE config 2: 10k trees x 200 taxa, BDWS, spikes on"),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self.stop_flag:
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        vals = sorted(m for m, _ in self.samples)
+        return {"sm_mhz": vals[len(vals) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(vals)}
+
+
+def cpu_sample(kind, taxa, trees, seed, threads):
+    """Time the CPU restatement of the reference (oracle/) on a bounded sample of the workload."""
+    import oracle
+    from gammaspikemodel_b200 import synthetic
+    b = synthetic.make_batch(kind, trees, taxa, seed=seed)
+    a = dict(height=b.dense("height"), parent=b.dense("parent"), rate=b.dense("rate"), spike=b.dense("spike"),
+             nstubs=b.dense("nstubs"), params=b.params.numpy(), use_spike=b.use_spike.numpy())
+    oracle.eval_batch(b.flags, b.stub_mode, a["height"][:8], a["parent"][:8], a["rate"][:8], a["spike"][:8],
+                      a["nstubs"][:8], a["params"][:8], a["use_spike"][:8], n_threads=threads)  # warm
+    t0 = time.perf_counter()
+    r = oracle.eval_batch(b.flags, b.stub_mode, a["height"], a["parent"], a["rate"], a["spike"], a["nstubs"],
+                          a["params"], a["use_spike"], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return b.n_trees * b.n_nodes / dt, dt, r
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Java/BEAST 2 and
+    cannot run here (no JVM), so this is its C restatement (oracle/, kind "port"), all host threads."""
+    if rank != 0:
+        return
+    import oracle
+    kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
+    threads = oracle.max_threads()
+    n_nodes = 2 * taxa - 1
+    # size one step at ~2 s of CPU work (about 2e6 branch evals / s / thread)
+    trees = max(64, min(trees_per_gpu, int(2.0 * 2.0e6 * threads / n_nodes)))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, _ = cpu_sample(kind, taxa, trees, 4242 + s, threads)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    total_dt = sum(dt for _, dt in vals)
+    value = len(vals) * trees * n_nodes / total_dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(1, len(vals)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "trees_per_step": trees, "taxa": taxa, "nodes_per_tree": n_nodes},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d trees x %d nodes per step (bounded sample of the workload), OpenMP over trees, "
+                                       "C restatement of the Java reference (no JVM in this image)" % (trees, n_nodes)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4shard", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--want-rates", action="store_true", help="also write per-branch effective rates (44 B/branch)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gammaspikemodel_b200 import GsmEngine, abi, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
+    if args.trees:
+        trees_per_gpu = args.trees
+    seed = synthetic.SEEDS[kind] + rank
+    t_gen = time.perf_counter()
+    batch = synthetic.make_batch_chunked(kind, trees_per_gpu, taxa, seed=seed, device=dev, chunk=31250)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    T, N, S = batch.n_trees, batch.n_nodes, batch.stride
+    branches = T * N
+
+    eng = GsmEngine(device=local_rank)
+    eng.set_mode(batch.stub_mode, batch.flags)
+    eng.bind_batch(batch)
+    out = torch.empty((T, abi.NOUT), dtype=torch.float64, device=dev)
+    out_rates = torch.empty((T, S), dtype=torch.float64, device=dev) if args.want_rates else None
+    gathered = torch.empty((world * T, abi.NOUT), dtype=torch.float64, device=dev) if distributed else None
+    # a real (non-default) stream: the kernels, the NCCL gather and the timing events all go on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+
+    def step():
+        eng.eval_device(out, out_rates, None, stream)
+        if distributed:
+            dist.all_gather_into_tensor(gathered, out)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count
+    e0.record()
+    for s in range(args.steps):
+        k_ev[s][0].record()
+        eng.eval_device(out, out_rates, None, stream)
+        k_ev[s][1].record()
+        if distributed:
+            dist.all_gather_into_tensor(gathered, out)
+    e1.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = eng.launch_count - launches0
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
+    tmax = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms_max = float(tmax[0]), float(tmax[1])
+    value = world * branches * args.steps / (total_ms * 1e-3)
+
+    # ---- parity spot check of the timed outputs against the oracle (rank 0, 48 trees) ----
+    parity = None
+    if rank == 0:
+        import oracle
+        idx = torch.linspace(0, T - 1, 48, device=dev).long()
+        sub = lambda x: x[idx].cpu().numpy()
+        ref = oracle.eval_batch(batch.flags, batch.stub_mode, sub(batch.height)[:, :N], sub(batch.parent)[:, :N],
+                                sub(batch.rate)[:, :N], sub(batch.spike)[:, :N], sub(batch.nstubs)[:, :N],
+                                sub(batch.params), sub(batch.use_spike), n_threads=0)["out"]
+        got = out[idx].cpu().numpy()
+        with np.errstate(all="ignore"):
+            err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        err = np.where((got == ref) | (np.isnan(got) & np.isnan(ref)), 0.0, err)
+        parity = {"trees": 48, "max_rel_err_vs_oracle": float(err.max())}
+        if not err.max() <= 1e-10:
+            raise SystemExit("bench.py: device results differ from the oracle (max rel err %g)" % err.max())
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host inputs, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        Te = min(T, 16384)
+        pin = lambda x: x[:Te, :N].contiguous().cpu().pin_memory()
+        hb = dict(height=pin(batch.height), parent=pin(batch.parent), rate=pin(batch.rate), spike=pin(batch.spike),
+                  nstubs=pin(batch.nstubs), params=batch.params[:Te].cpu().pin_memory(),
+                  use_spike=batch.use_spike[:Te].cpu().pin_memory())
+        hout = torch.empty((Te, abi.NOUT), dtype=torch.float64).pin_memory()
+        eng2 = GsmEngine(device=local_rank)
+        eng2.set_mode(batch.stub_mode, batch.flags)
+
+        def e2e_step():
+            eng2.eval_host_ptrs(Te, N, hb["height"].data_ptr(), hb["parent"].data_ptr(), None, hb["rate"].data_ptr(),
+                                hb["spike"].data_ptr(), hb["nstubs"].data_ptr(), hb["params"].data_ptr(),
+                                hb["use_spike"].data_ptr(), hout.data_ptr())
+        for _ in range(2):
+            e2e_step()
+        if distributed:
+            dist.barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        l0 = eng2.launch_count
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        e2e_launches = eng2.launch_count - l0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        if rank == 0:
+            a_, b_ = hout.numpy(), out[:Te].cpu().numpy()
+            if not np.array_equal(a_, b_, equal_nan=True):
+                bad = np.argwhere(~((a_ == b_) | (np.isnan(a_) & np.isnan(b_))))
+                raise SystemExit("bench.py: host-buffer path and device-resident path disagree at %d entries, first %s: %r vs %r"
+                                 % (len(bad), bad[0], a_[tuple(bad[0])], b_[tuple(bad[0])]))
+        e2e = {"value": world * Te * N * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": Te * N * BYTES_PER_BRANCH + Te * 73, "d2h_bytes_per_step": Te * 64,
+               "trees_per_step": Te, "steps": e2e_steps, "launches": e2e_launches,
+               "note": "gsm_eval_host on pinned host arrays, chunked + double-buffered; bounded batch of the same workload"}
+        eng2.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        threads = oracle.max_threads()
+        trees = max(64, min(T, int(1.5 * 2.0e6 * threads / N)))
+        v_all, dt_all, _ = cpu_sample(kind, taxa, trees, seed, threads)
+        v_one, dt_one, _ = cpu_sample(kind, taxa, max(32, trees // threads), seed, 1)
+        cpu = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": v_one,
+               "sample": "%d trees x %d nodes (%.1f s, %d threads) and %d trees on 1 thread (%.1f s); C restatement of the "
+                         "Java reference, no JVM in this image" % (trees, N, dt_all, threads, max(32, trees // threads), dt_one)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_bytes = branches * (BYTES_PER_BRANCH + (8 if args.want_rates else 0)) + T * BYTES_PER_TREE
+        achieved = per_launch_bytes / (kern_ms_max * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+                if tj.get("workload") == args.workload:
+                    traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "trees_per_gpu": T, "taxa": taxa, "nodes_per_tree": N,
+                       "branches_per_step": world * branches, "outputs": "logP+rates" if args.want_rates else "logP",
+                       "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
+                       if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
+                       "gather": "nccl all_gather of [T,8] result rows each step" if distributed else "none (1 GPU)",
+                       "generate_s": round(t_gen, 1), "parity_sample": parity},
+            "clocks": sampler.summary(),
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "gsm_eval_kernel", "kernel_ms": kern_ms_max,
+                         "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

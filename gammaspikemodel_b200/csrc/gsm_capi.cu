@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -84,6 +85,8 @@ cudaError_t dalloc(T** p, int64_t count) {
     if (count <= 0) count = 1;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), static_cast<size_t>(count) * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(*p, 0, static_cast<size_t>(count) * sizeof(T));
+    // the memset runs on the legacy default stream; the handle's streams are non-blocking, so finish it here
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
 }
 
@@ -323,7 +326,7 @@ int gsm_eval(gsm_handle* h, double* out_tree, double* out_rates, double* out_wsp
 }
 
 static int ensure_slots(gsm_handle* h, int64_t chunk, int64_t stride, bool rates, bool wsp) {
-    if (h->slot_trees >= chunk && h->slot_stride >= stride && (!rates || h->slot_rates) && (!wsp || h->slot_wsp)) return GSM_OK;
+    if (h->slot_trees >= chunk && h->slot_stride == stride && (!rates || h->slot_rates) && (!wsp || h->slot_wsp)) return GSM_OK;
     free_slots(h);
     const int64_t cells = chunk * stride;
     for (Slot& s : h->slots) {
@@ -361,7 +364,9 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
     GSM_CUDA(h, cudaSetDevice(h->device));
     const int64_t stride = gsm_device_stride(n_nodes);
     // ~256 MB of inputs per slot: long enough transfers for full PCIe rate, short enough to overlap
-    int64_t chunk = std::max<int64_t>(1, (int64_t(256) << 20) / (stride * 32));
+    int64_t chunk_mb = 256;
+    if (const char* env = getenv("GSM_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));   // test hook: force small chunks
+    int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (stride * 32));
     chunk = std::min(chunk, n_trees);
     rc = ensure_slots(h, chunk, stride, out_rates != nullptr, out_wspikes != nullptr);
     if (rc != GSM_OK) return rc;

@@ -5,9 +5,9 @@
 //            the tree's height row and parent row into shared memory; meanwhile one warp computes the
 //            per-tree constants (c1, c2, logs, lgamma(shape*m) table) and the rest clear the flag bytes.
 //   phase 1  every node marks its parent as non-leaf                         (Node.isLeaf)
-//   phase 2  every leaf whose parent has the same height marks the parent fake (Node.isDirectAncestor /
-//            Node.isFake) and every node stores its aux value (exp(-c1 h) or log(l e^{(l-m)h} - m))
-//   phase 3  per-branch terms: rate/spike/stub-count rows are streamed from HBM with coalesced loads
+//   phase 1b every leaf whose parent has the same height marks the parent fake (Node.isDirectAncestor / isFake)
+//   phase 2  pass A per node: leaf census, the node's own tree-density term, aux(h) = log G(h) -> shared memory
+//   phase 3  pass B per branch: rate/spike/stub-count rows are streamed from HBM with coalesced loads
 //            (each byte is read exactly once), parent height/aux/flags are gathered from shared memory
 //   phase 4  fixed-order warp-shuffle + cross-warp reduction, per-tree epilogue, one 64-byte result row.
 // The math is in gsm_node_math.cuh (shared with the CPU-side logic tests).
@@ -66,8 +66,9 @@ static __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int BLOCK, bool WANT_RATES>
-__global__ void __launch_bounds__(BLOCK) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
+// MINB = CTAs per SM the register allocation is sized for (__launch_bounds__): BLOCK*MINB resident threads.
+template <int BLOCK, int MINB, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
                                                          double* __restrict__ out_rates,
                                                          double* __restrict__ out_wspikes) {
     constexpr int NWARP = BLOCK / 32;
@@ -122,9 +123,8 @@ __global__ void __launch_bounds__(BLOCK) gsm_eval_kernel(const GsmBatch b, doubl
         const double* prow = b.params + t * GSM_NPARAM;
         if (lane == 0) {
             gsm_setup_consts(K, prow, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
-            K.lg[0] = 0.0;
-        } else if (lane <= GSM_LUT_M) {
-            K.lg[lane] = gsm_lut_entry(prow[GSM_P_SPIKE_SHAPE], lane);
+        } else if (lane <= GSM_LUT_M + 1) {
+            gsm_lut_entry(K, prow[GSM_P_SPIKE_SHAPE], lane - 1);  // m = 0..GSM_LUT_M
         }
     }
     __syncthreads();
@@ -141,19 +141,33 @@ __global__ void __launch_bounds__(BLOCK) gsm_eval_kernel(const GsmBatch b, doubl
     }
     __syncthreads();
 
-    // ---- phase 2: sampled ancestors -> fake parents; aux values ----
-    const int aux_kind = K.aux_kind;
+    // ---- phase 1b: sampled ancestors -> fake parents ----
     for (int i = tid; i < n; i += BLOCK) {
-        const double h = sh_h[i];
         const int32_t p = sh_par[i];
-        if (!sh_nonleaf[i] && p >= 0 && sh_h[p] == h) sh_fake[p] = 1;
-        if (aux_kind != GSM_AUX_NONE) sh_aux[i] = gsm_aux(K, h);
+        if (!sh_nonleaf[i] && p >= 0 && sh_h[p] == sh_h[i]) sh_fake[p] = 1;
     }
     __syncthreads();
 
-    // ---- phase 3: per-branch terms ----
+    // ---- phase 2: pass A (census, own tree-density term, aux) ----
     GsmAcc A;
     gsm_acc_zero(A);
+    for (int i = tid; i < n; i += BLOCK) {
+        const double h = sh_h[i];
+        const int32_t p = sh_par[i];
+        uint32_t nf = 0;
+        double hp = h;
+        if (sh_nonleaf[i]) nf |= GSM_NF_NONLEAF;
+        if (sh_fake[i]) nf |= GSM_NF_FAKE;
+        if (p < 0) nf |= GSM_NF_ROOT;
+        else {
+            hp = sh_h[p];
+            if (!(nf & GSM_NF_NONLEAF) && hp == h) nf |= GSM_NF_DA;
+        }
+        sh_aux[i] = gsm_node_pass_a(K, A, nf, h, hp);
+    }
+    __syncthreads();
+
+    // ---- phase 3: pass B (branch parameters streamed from HBM) ----
     const double* rate_row = b.rate ? b.rate + row : nullptr;
     const double* spike_row = b.spike + row;
     const int32_t* nst_row = b.nstubs ? b.nstubs + row : nullptr;
@@ -179,22 +193,21 @@ __global__ void __launch_bounds__(BLOCK) gsm_eval_kernel(const GsmBatch b, doubl
         }
         const double h = sh_h[i];
         const int32_t p = sh_par[i];
+        const double aux = sh_aux[i];
         uint32_t nf = 0;
-        double hp = h, aux = 0.0, auxp = 0.0;
-        if (aux_kind != GSM_AUX_NONE) aux = sh_aux[i];
+        double hp = h, auxp = aux;
         if (sh_nonleaf[i]) nf |= GSM_NF_NONLEAF;
         if (sh_fake[i]) nf |= GSM_NF_FAKE;
         if (p < 0) {
             nf |= GSM_NF_ROOT;
-            auxp = aux;
         } else {
             hp = sh_h[p];
-            if (aux_kind != GSM_AUX_NONE) auxp = sh_aux[p];
+            auxp = sh_aux[p];
             if (sh_fake[p]) nf |= GSM_NF_PARENT_FAKE;
             if (!(nf & GSM_NF_NONLEAF) && hp == h) nf |= GSM_NF_DA;
         }
-        gsm_node_terms<WANT_RATES>(K, g_logfact, A, i, n, nf, h, hp, aux, auxp, rate, spike, nst,
-                                   orate ? orate + i : nullptr, owsp ? owsp + i : nullptr);
+        gsm_node_pass_b<WANT_RATES>(K, g_logfact, A, i, n, nf, h, hp, aux, auxp, rate, spike, nst,
+                                    orate ? orate + i : nullptr, owsp ? owsp + i : nullptr);
         i = inext;
     }
 
@@ -243,19 +256,21 @@ __global__ void gsm_stub_cdf_kernel(const GsmBatch b, int64_t t, int32_t node, d
     GsmTreeConsts K;
     gsm_setup_consts(K, b.params + t * GSM_NPARAM, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags,
                      b.stub_mode);
-    K.lg[0] = 0.0;
-    for (int m = 1; m <= GSM_LUT_M; m++) K.lg[m] = gsm_lut_entry(K.shape, m);
-    // the CDF always needs the Poisson mean, whatever the evaluation mode
-    K.aux_kind = K.stub_sampling ? GSM_AUX_EXP_C1 : GSM_AUX_LB;
+    for (int m = 0; m <= GSM_LUT_M; m++) gsm_lut_entry(K, K.shape, m);
     const int64_t row = t * b.stride;
     const double h = b.height[row + node];
     const int32_t p = b.parent[row + node];
     const double hp = p < 0 ? h : b.height[row + p];
     double mu = 0.0;                                                        // STP:876-878
-    if (hp > h) mu = gsm_expected_stubs(K, h, hp, gsm_aux(K, h), gsm_aux(K, hp));
+    if (hp > h) {                                                           // STP:749-769 through aux = log G
+        const double a1 = gsm_log(fma(K.omc2, gsm_exp(-K.c1 * h), K.opc2));
+        const double a0 = gsm_log(fma(K.omc2, gsm_exp(-K.c1 * hp), K.opc2));
+        mu = fma(hp - h, K.kE, 2 * (a1 - a0));
+    }
     const double x = b.spike[row + node];                                   // BSP:328
     const bool use_gamma = (b.flags & GSM_F_BSP_HAS_INDICATOR) && K.use_spike;   // BSP:347
     const double log_mu = log(mu);
+    const double xs = x * K.shape, lxs = log(xs);
     int32_t k = 0, len = 0;
     double pcs = 0.0, psum = 0.0;
     while (pcs < GSM_MAX_CUM_SUM && k < GSM_K_CAP) {                        // BSP:334
@@ -264,7 +279,7 @@ __global__ void gsm_stub_cdf_kernel(const GsmBatch b, int64_t t, int32_t node, d
         pl -= gsm_logfact(g_logfact, k);                                    // BSP:340
         const double pReal = exp(pl);
         if (use_gamma) {
-            const double g = gsm_gamma_logdens(K, k + 1, x);                // BSP:344-350 (table is per handle's shape)
+            const double g = gsm_gamma_logdens(K, k + 1, x, xs, lxs);       // BSP:344-350
             if (g == -INFINITY || g != g) {
                 if (pcs > 0) break;                                         // BSP:352
             } else {
@@ -306,38 +321,47 @@ cudaError_t gsm_init_tables() {
 
 static size_t eval_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
 
-template <int BLOCK>
+template <int BLOCK, int MINB>
 static cudaError_t launch_block(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
     const size_t smem = eval_smem_bytes(b.stride);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     cudaError_t e;
     if (r || w) {
-        e = cudaFuncSetAttribute(gsm_eval_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = gsm_eval_kernel<BLOCK, MINB, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gsm_eval_kernel<BLOCK, true><<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     } else {
-        e = cudaFuncSetAttribute(gsm_eval_kernel<BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = gsm_eval_kernel<BLOCK, MINB, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gsm_eval_kernel<BLOCK, false><<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     }
     return cudaGetLastError();
 }
 
+// Launch configuration: one CTA per tree.  The shared-memory footprint (22 B per node) bounds the number of
+// resident trees per SM; BLOCK and the register budget (MINB) are picked so that the resident CTAs give
+// ~1024 threads per SM.  GSM_BLOCK / GSM_MINB override the choice for tuning runs.
 int gsm_launch_eval(const GsmBatch& b, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                     cudaStream_t stream) {
     if (b.n_trees <= 0) return 0;
-    int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 512);
-    if (const char* env = getenv("GSM_BLOCK")) {
-        int v = atoi(env);
-        if (v == 64 || v == 128 || v == 256 || v == 512) block = v;
-    }
-    cudaError_t e;
-    switch (block) {
-        case 64: e = launch_block<64>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
-        case 128: e = launch_block<128>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
-        case 256: e = launch_block<256>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
-        default: e = launch_block<512>(b, d_out_tree, d_out_rates, d_out_wspikes, stream); break;
-    }
+    // measured on B200 (profiles/r01_tuning.md): 128x6 for <=512 nodes, 256x3 up to 2048, 384x2 above
+    int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
+    int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
+    if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
+    if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
+    cudaError_t e = cudaErrorInvalidConfiguration;
+#define GSM_CFG(B, M) \
+    if (block == B && minb == M) e = launch_block<B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
+    GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
+    GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
+    GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
+#undef GSM_CFG
     if (e != cudaSuccess) return -static_cast<int>(e);
     return 1;
 }

@@ -34,8 +34,7 @@ static void eval_tree(uint32_t flags, int32_t stub_mode, int32_t n, const double
     }
     GsmTreeConsts K;
     gsm_setup_consts(K, params, use_spike, flags, stub_mode);
-    K.lg[0] = 0.0;
-    for (int m = 1; m <= GSM_LUT_M; m++) K.lg[m] = gsm_lut_entry(params[GSM_P_SPIKE_SHAPE], m);
+    for (int m = 0; m <= GSM_LUT_M; m++) gsm_lut_entry(K, params[GSM_P_SPIKE_SHAPE], m);
     std::vector<int32_t> par(par_in, par_in + n);
     std::vector<uint8_t> nonleaf(n, 0), fake(n, 0);
     std::vector<double> aux(n, 0.0);
@@ -46,30 +45,41 @@ static void eval_tree(uint32_t flags, int32_t stub_mode, int32_t n, const double
         else if (p < 0) root = i;
         else par[i] = -1;
     }
-    for (int i = 0; i < n; i++) {  // phase 2
+    for (int i = 0; i < n; i++) {  // phase 1b
         int32_t p = par[i];
         if (!nonleaf[i] && p >= 0 && h[p] == h[i]) fake[p] = 1;
-        if (K.aux_kind != GSM_AUX_NONE) aux[i] = gsm_aux(K, h[i]);
     }
     GsmAcc A;
     gsm_acc_zero(A);
-    for (int i = 0; i < n; i++) {  // phase 3
+    for (int i = 0; i < n; i++) {  // phase 2: pass A
         int32_t p = par[i];
         uint32_t nf = 0;
-        double hp = h[i], auxp = 0.0;
+        double hp = h[i];
+        if (nonleaf[i]) nf |= GSM_NF_NONLEAF;
+        if (fake[i]) nf |= GSM_NF_FAKE;
+        if (p < 0) nf |= GSM_NF_ROOT;
+        else {
+            hp = h[p];
+            if (!(nf & GSM_NF_NONLEAF) && hp == h[i]) nf |= GSM_NF_DA;
+        }
+        aux[i] = gsm_node_pass_a(K, A, nf, h[i], hp);
+    }
+    for (int i = 0; i < n; i++) {  // phase 3: pass B
+        int32_t p = par[i];
+        uint32_t nf = 0;
+        double hp = h[i], auxp = aux[i];
         if (nonleaf[i]) nf |= GSM_NF_NONLEAF;
         if (fake[i]) nf |= GSM_NF_FAKE;
         if (p < 0) {
             nf |= GSM_NF_ROOT;
-            auxp = aux[i];
         } else {
             hp = h[p];
             auxp = aux[p];
             if (fake[p]) nf |= GSM_NF_PARENT_FAKE;
             if (!(nf & GSM_NF_NONLEAF) && hp == h[i]) nf |= GSM_NF_DA;
         }
-        gsm_node_terms<WANT>(K, g_logfact_host, A, i, n, nf, h[i], hp, aux[i], auxp, rate ? rate[i] : 1.0, spike[i],
-                             nstubs ? nstubs[i] : 0, out_rates ? out_rates + i : nullptr, out_wsp ? out_wsp + i : nullptr);
+        gsm_node_pass_b<WANT>(K, g_logfact_host, A, i, n, nf, h[i], hp, aux[i], auxp, rate ? rate[i] : 1.0, spike[i],
+                              nstubs ? nstubs[i] : 0, out_rates ? out_rates + i : nullptr, out_wsp ? out_wsp + i : nullptr);
     }
     if (root < 0) {
         for (int k = 0; k < GSM_NOUT; k++) out[k] = NAN;
@@ -97,4 +107,12 @@ extern "C" int gsm_emu_eval_batch(uint32_t flags, int32_t stub_mode, int64_t n_t
                              out_tree + t * GSM_NOUT, nullptr, nullptr);
     }
     return 0;
+}
+
+// ---- table-driven log / exp of the kernels, exposed for accuracy tests ----
+extern "C" void gsm_emu_log_vec(const double* x, double* y, int64_t n) {
+    for (int64_t i = 0; i < n; i++) y[i] = gsm_log(x[i]);
+}
+extern "C" void gsm_emu_exp_vec(const double* x, double* y, int64_t n) {
+    for (int64_t i = 0; i < n; i++) y[i] = gsm_exp(x[i]);
 }

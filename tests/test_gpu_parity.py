@@ -4,16 +4,19 @@ bit-exact for integer outputs (nExtant) and for values that are pure selections 
 import numpy as np
 import pytest
 
-from gammaspikemodel_b200 import abi, synthetic
-from helpers import assert_results_match, host_arrays, run_capi, run_oracle, variant
+import oracle
+from gammaspikemodel_b200 import GsmEngine, GsmError, abi, synthetic
+from cases import build_cases, empty_batch
+from helpers import assert_close, assert_results_match, host_arrays, run_capi, run_oracle
 
 pytestmark = pytest.mark.gpu
 
 F = synthetic.DEFAULT_FLAGS
+CASES = build_cases()
 
 
 @pytest.mark.parametrize("kind,T,n", [("C2", 256, 200), ("C3", 128, 200), ("C4", 64, 500), ("C3", 32, 1000), ("C4", 8, 2000),
-                                      ("C2", 300, 5), ("C3", 100, 2), ("C2", 50, 1)])
+                                      ("C2", 300, 5), ("C3", 100, 2), ("C2", 50, 1), ("C3", 3, 4000)])
 def test_default_wiring_matches_oracle(kind, T, n):
     b = synthetic.make_batch(kind, T, n)
     a = host_arrays(b)
@@ -22,10 +25,142 @@ def test_default_wiring_matches_oracle(kind, T, n):
     assert_results_match(got, ref, what="%s %dx%d" % (kind, T, n))
 
 
-def test_logp_only_path_matches_rates_path():
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_case_table_matches_oracle(case):
+    name, a, flags, mode, nc = case
+    if name in ("c3-lambda-le-mu", "c3-lambda-eq-mu") and mode == abi.STUBS_NOSTUB:
+        pytest.skip("mixture-mode spike prior is not defined for lambda <= mu")
+    ref = run_oracle(a, flags, mode, node_count=nc)
+    got = run_capi(a, flags, mode, node_count=nc)
+    assert_results_match(got, ref, node_count=nc, what=name)
+
+
+def test_logp_only_launch_matches_oracle():
     b = synthetic.make_batch("C3", 64, 300)
     a = host_arrays(b)
     ref = run_oracle(a, b.flags, b.stub_mode)
     got = run_capi(a, b.flags, b.stub_mode, rates=False)
     assert got["rates"] is None
     assert_results_match(got, ref, what="logp-only")
+
+
+def test_empty_batch_and_argument_errors():
+    a = empty_batch()
+    eng = GsmEngine(max_trees=4, max_nodes=9)
+    eng.set_mode(abi.STUBS_COUNTS, F)
+    eng.upload_trees(a["height"], a["parent"])
+    eng.upload_branch_params(a["rate"], a["spike"], a["nstubs"])
+    eng.upload_tree_params(a["params"], a["use_spike"])
+    assert eng.eval()["out"].shape == (0, abi.NOUT)
+    with pytest.raises(GsmError):                       # exceeds the handle capacity
+        eng.upload_trees(np.zeros((5, 9)), np.zeros((5, 9), np.int32))
+    with pytest.raises(GsmError):                       # conditionOnSampling + conditionOnRhoSampling (STP:92-94)
+        eng.set_mode(abi.STUBS_COUNTS, abi.F_COND_SAMPLING | abi.F_COND_RHO_SAMPLING)
+    with pytest.raises(GsmError):                       # too many nodes for the shared-memory kernels
+        GsmEngine(max_trees=1, max_nodes=abi.MAX_NODES + 1)
+    eng2 = GsmEngine(max_trees=2, max_nodes=9)
+    with pytest.raises(GsmError):                       # eval before upload
+        eng2.eval()
+    eng.close()
+    eng2.close()
+
+
+def test_state_updates_between_evals():
+    """MCMC-style use of one handle: re-upload only what changed (rates / spikes / per-tree scalars)."""
+    b = synthetic.make_batch("C3", 32, 100)
+    a = host_arrays(b)
+    eng = GsmEngine(max_trees=32, max_nodes=b.n_nodes)
+    first = run_capi(a, b.flags, b.stub_mode, engine=eng)
+    a2 = {k: v.copy() for k, v in a.items()}
+    a2["rate"] *= 1.3
+    a2["params"][:, abi.P_CLOCK_SD] *= 0.9
+    a2["use_spike"][:] = 1 - a2["use_spike"]
+    eng.upload_branch_params(rate=a2["rate"])
+    eng.upload_tree_params(a2["params"], a2["use_spike"])
+    second = eng.eval(want_rates=True, want_wspikes=True)
+    assert_results_match(second, run_oracle(a2, b.flags, b.stub_mode), what="after update")
+    assert not np.array_equal(first["out"], second["out"])
+    eng.close()
+
+
+@pytest.mark.parametrize("kind,T,n", [("C3", 700, 150), ("C4", 37, 1200)])
+def test_streaming_host_path_equals_resident_path(kind, T, n, monkeypatch):
+    """gsm_eval_host (chunked, double-buffered) must return bit-identical rows to upload + gsm_eval."""
+    monkeypatch.setenv("GSM_HOST_CHUNK_MB", "1")        # force many chunks
+    b = synthetic.make_batch(kind, T, n)
+    a = host_arrays(b)
+    eng = GsmEngine(max_trees=T, max_nodes=b.n_nodes)
+    resident = run_capi(a, b.flags, b.stub_mode, engine=eng)
+    eng.set_mode(b.stub_mode, b.flags)
+    streamed = eng.eval_host(a["height"], a["parent"], a["spike"], a["params"], rate=a["rate"], nstubs=a["nstubs"],
+                             use_spike=a["use_spike"], want_rates=True, want_wspikes=True)
+    for k in ("out", "rates", "wspikes"):
+        assert np.array_equal(streamed[k], resident[k], equal_nan=True), k
+    eng.close()
+
+
+def test_device_resident_path_equals_host_path():
+    import torch
+    b = synthetic.make_batch("C3", 200, 120)
+    a = host_arrays(b)
+    host = run_capi(a, b.flags, b.stub_mode)
+    d = b.to("cuda")
+    eng = GsmEngine()
+    eng.set_mode(b.stub_mode, b.flags)
+    eng.bind_batch(d)
+    out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device="cuda")
+    rates = torch.full((b.n_trees, b.stride), float("nan"), dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    eng.eval_device(out, rates, None, st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host["out"], equal_nan=True)
+    assert np.array_equal(rates[:, : b.n_nodes].cpu().numpy(), host["rates"])
+    assert eng.launch_count == 1
+    eng.close()
+
+
+def test_stub_cdf_matches_oracle():
+    """BranchSpikePrior.getCumulativeProbs (BSP:315-389) with mu from StumpedTreePrior.getMeanStubNumber."""
+    b = synthetic.make_batch("C3", 8, 40)
+    a = host_arrays(b)
+    flags = b.flags | abi.F_BSP_HAS_INDICATOR
+    eng = GsmEngine(max_trees=8, max_nodes=b.n_nodes)
+    run_capi(a, flags, abi.STUBS_NOSTUB, engine=eng)
+    L = oracle.lib()
+    checked = 0
+    for t in range(8):
+        lam, mu_, psi, rho = a["params"][t, abi.P_LAMBDA:abi.P_RHO + 1]
+        T_root = a["height"][t].max()
+        for node in range(0, b.n_nodes - 1, 7):
+            h, hp = a["height"][t, node], a["height"][t, a["parent"][t, node]]
+            mean = L.gsmo_mean_stub_number(h, hp, lam, mu_, psi, rho, T_root)
+            if not mean > 0:
+                continue
+            ref, n_ref = oracle.cumulative_probs(mean, a["spike"][t, node], a["params"][t, abi.P_SPIKE_SHAPE], a["use_spike"][t])
+            got, n_got = eng.stub_cdf(t, node)
+            if a["spike"][t, node] == 0 and a["use_spike"][t]:
+                continue                                  # all-zero weights: 0/0 in the Java as well
+            assert n_got == n_ref
+            assert_close(got, ref, rtol=1e-9, atol=1e-12, what="cdf t=%d node=%d" % (t, node))
+            checked += 1
+    assert checked > 20
+    eng.close()
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full size (10k x 200 taxa): size-independent checks instead of a full oracle run:
+    tree-permutation equivariance, batch-split invariance, a random 2% sample against the oracle."""
+    import torch
+    b = synthetic.make_batch("C2", 10_000, 200)
+    a = host_arrays(b)
+    full = run_capi(a, b.flags, b.stub_mode, rates=False)["out"]
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(b.n_trees)
+    ap = {k: v[perm] for k, v in a.items()}
+    assert np.array_equal(run_capi(ap, b.flags, b.stub_mode, rates=False)["out"], full[perm], equal_nan=True)
+    half = {k: v[:5000] for k, v in a.items()}
+    assert np.array_equal(run_capi(half, b.flags, b.stub_mode, rates=False)["out"], full[:5000], equal_nan=True)
+    idx = np.sort(rng.choice(b.n_trees, 200, replace=False))
+    sub = {k: v[idx] for k, v in a.items()}
+    assert_close(full[idx], run_oracle(sub, b.flags, b.stub_mode, rates=False)["out"], what="C2 sample")
+    assert np.array_equal(full[:, abi.O_N_EXTANT], np.full(b.n_trees, 200.0))

@@ -1,0 +1,39 @@
+"""Invariants of the synthetic batch generator: valid BEAST-style numbering, heights, sampled
+ancestors, and values the reference would accept (finite logP)."""
+import numpy as np
+import pytest
+
+from gammaspikemodel_b200 import abi, synthetic
+from helpers import host_arrays, run_oracle
+
+
+@pytest.mark.parametrize("kind,T,n", [("C2", 16, 50), ("C3", 16, 80), ("C4", 16, 31)])
+def test_batches_are_valid_trees(kind, T, n):
+    b = synthetic.make_batch(kind, T, n)
+    N = 2 * n - 1
+    assert b.n_nodes == N and b.stride % 32 == 0 and b.stride >= N
+    a = host_arrays(b)
+    h, p = a["height"], a["parent"]
+    assert np.all(p[:, N - 1] == -1) and np.all(p[:, : N - 1] >= n)          # leaves first, root last
+    for t in range(T):
+        assert np.all(np.bincount(p[t, : N - 1], minlength=N)[n:] == 2)     # binary
+        assert np.all(h[t, p[t, : N - 1]] >= h[t, : N - 1])                 # parents are not below children
+    lam, mu = a["params"][:, abi.P_LAMBDA], a["params"][:, abi.P_MU]
+    assert np.all(lam > mu) and np.all(lam * h[:, N - 1] <= 50 + 1e-9)
+    if kind == "C3":
+        sa = h[:, :n] == np.take_along_axis(h, p[:, :n], axis=1)
+        assert 0.01 < sa.mean() < 0.1
+        assert np.all(a["spike"][:, :n][sa] == 0) and np.all(a["nstubs"][:, :n][sa] == 0)
+        assert set(np.unique(a["use_spike"])) <= {0, 1}
+    else:
+        assert np.all(h[:, :n] == 0)
+    out = run_oracle(a, b.flags, b.stub_mode, rates=False)["out"]
+    assert np.all(np.isfinite(out))
+
+
+def test_generation_is_deterministic_and_chunking_is_consistent():
+    a = synthetic.make_batch("C4", 8, 20)
+    b = synthetic.make_batch("C4", 8, 20)
+    assert all(np.array_equal(a.dense(k), b.dense(k)) for k in ("height", "parent", "rate", "spike", "nstubs"))
+    c = synthetic.make_batch_chunked("C4", 10, 20, chunk=4)
+    assert c.n_trees == 10 and c.height.shape == (10, c.stride)

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Times gsm_eval_kernel launch configurations on one resident batch (GPU box only; tuning aid)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gammaspikemodel_b200 import GsmEngine, abi, synthetic
+
+kind, trees, taxa = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+cfgs = [tuple(map(int, c.split("x"))) for c in sys.argv[4:]]
+dev = torch.device("cuda", 0)
+b = synthetic.make_batch_chunked(kind, trees, taxa, device=dev, chunk=31250)
+eng = GsmEngine(device=0); eng.set_mode(b.stub_mode, b.flags); eng.bind_batch(b)
+out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
+st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+ref = None
+for blk, minb in cfgs:
+    os.environ["GSM_BLOCK"], os.environ["GSM_MINB"] = str(blk), str(minb)
+    for _ in range(3): eng.eval_device(out, None, None, st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): eng.eval_device(out, None, None, st.cuda_stream)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    cur = out.clone()
+    same = True if ref is None else bool(torch.equal(torch.nan_to_num(cur), torch.nan_to_num(ref)))
+    maxdiff = 0.0 if ref is None else float((torch.nan_to_num(cur) - torch.nan_to_num(ref)).abs().max())
+    if ref is None: ref = cur
+    br = b.n_trees * b.n_nodes
+    print(json.dumps({"kind": kind, "trees": trees, "taxa": taxa, "block": blk, "minb": minb, "ms": round(ms, 4),
+                      "branch_evals_per_s": br / ms * 1e3, "GBps": br * 32 / ms / 1e6, "bitwise_same_as_first": same, "max_abs_diff_vs_first": maxdiff}), flush=True)
