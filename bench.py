@@ -100,47 +100,63 @@ class ClockSampler(threading.Thread):
                 "samples": len(vals)}
 
 
-def cpu_sample(kind, taxa, trees, seed, threads):
-    """Time the CPU restatement of the reference (oracle/) on a bounded sample of the workload."""
+def cpu_time(a, flags, mode, threads, target_s):
+    """Time the CPU restatement of the reference (oracle/) on host arrays `a`, repeating the pass until about
+    `target_s` seconds of work have been measured.  Returns (branch evals / s, seconds, passes)."""
     import oracle
-    from gammaspikemodel_b200 import synthetic
-    b = synthetic.make_batch(kind, trees, taxa, seed=seed)
-    a = dict(height=b.dense("height"), parent=b.dense("parent"), rate=b.dense("rate"), spike=b.dense("spike"),
-             nstubs=b.dense("nstubs"), params=b.params.numpy(), use_spike=b.use_spike.numpy())
-    oracle.eval_batch(b.flags, b.stub_mode, a["height"][:8], a["parent"][:8], a["rate"][:8], a["spike"][:8],
-                      a["nstubs"][:8], a["params"][:8], a["use_spike"][:8], n_threads=threads)  # warm
+    T, N = a["height"].shape
+
+    def one():
+        oracle.eval_batch(flags, mode, a["height"], a["parent"], a["rate"], a["spike"], a["nstubs"], a["params"],
+                          a["use_spike"], n_threads=threads)
     t0 = time.perf_counter()
-    r = oracle.eval_batch(b.flags, b.stub_mode, a["height"], a["parent"], a["rate"], a["spike"], a["nstubs"],
-                          a["params"], a["use_spike"], n_threads=threads)
+    one()                                   # warm-up pass, also the speed estimate
+    est = time.perf_counter() - t0
+    reps = max(1, int(target_s / max(est, 1e-3)))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
     dt = time.perf_counter() - t0
-    return b.n_trees * b.n_nodes / dt, dt, r
+    return reps * T * N / dt, dt, reps
+
+
+def host_sample(batch, trees):
+    """first `trees` trees of a synthetic.Batch as dense host arrays (the layout the oracle and the C ABI take)"""
+    N = batch.n_nodes
+    g = lambda x: x[:trees, :N].contiguous().cpu().numpy()
+    return dict(height=g(batch.height), parent=g(batch.parent), rate=g(batch.rate), spike=g(batch.spike),
+                nstubs=g(batch.nstubs), params=batch.params[:trees].cpu().numpy(), use_spike=batch.use_spike[:trees].cpu().numpy())
 
 
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Java/BEAST 2 and
-    cannot run here (no JVM), so this is its C restatement (oracle/, kind "port"), all host threads."""
+    cannot run here (no JVM), so this is its C restatement (oracle/, kind "port") on all host threads.  One step =
+    a bounded sample of the workload (8,192 trees, or fewer for small workloads) evaluated for about 2 s."""
     if rank != 0:
         return
     import oracle
+    from gammaspikemodel_b200 import synthetic
     kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
     threads = oracle.max_threads()
-    n_nodes = 2 * taxa - 1
-    # size one step at ~2 s of CPU work (about 2e6 branch evals / s / thread)
-    trees = max(64, min(trees_per_gpu, int(2.0 * 2.0e6 * threads / n_nodes)))
-    vals = []
+    trees = min(trees_per_gpu, 8192)
+    batch = synthetic.make_batch_chunked(kind, trees, taxa, seed=synthetic.SEEDS[kind], chunk=2048)
+    a = host_sample(batch, trees)
+    n_nodes = batch.n_nodes
+    done, total_dt, total_br = 0, 0.0, 0
     for s in range(args.warmup + args.steps):
-        v, dt, _ = cpu_sample(kind, taxa, trees, 4242 + s, threads)
+        v, dt, reps = cpu_time(a, batch.flags, batch.stub_mode, threads, 2.0)
         if s >= args.warmup:
-            vals.append((v, dt))
-    total_dt = sum(dt for _, dt in vals)
-    value = len(vals) * trees * n_nodes / total_dt
+            done += 1
+            total_dt += dt
+            total_br += reps * trees * n_nodes
+    value = total_br / total_dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(1, len(vals)), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(1, done), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "trees_per_step": trees, "taxa": taxa, "nodes_per_tree": n_nodes},
+            "config": {"workload": desc, "trees_in_sample": trees, "taxa": taxa, "nodes_per_tree": n_nodes},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d trees x %d nodes per step (bounded sample of the workload), OpenMP over trees, "
-                                       "C restatement of the Java reference (no JVM in this image)" % (trees, n_nodes)},
+                             "sample": "%d trees x %d nodes, passes repeated for ~2 s per step (bounded sample of the workload), "
+                                       "OpenMP over trees, C restatement of the Java reference (no JVM in this image)" % (trees, n_nodes)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -307,17 +323,18 @@ def main():
                "note": "gsm_eval_host on pinned host arrays, chunked + double-buffered; bounded batch of the same workload"}
         eng2.close()
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same batch ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         threads = oracle.max_threads()
-        trees = max(64, min(T, int(1.5 * 2.0e6 * threads / N)))
-        v_all, dt_all, _ = cpu_sample(kind, taxa, trees, seed, threads)
-        v_one, dt_one, _ = cpu_sample(kind, taxa, max(32, trees // threads), seed, 1)
+        t_all, t_one = min(T, 8192), min(T, 512)
+        v_all, dt_all, reps_all = cpu_time(host_sample(batch, t_all), batch.flags, batch.stub_mode, threads, 10.0)
+        v_one, dt_one, reps_one = cpu_time(host_sample(batch, t_one), batch.flags, batch.stub_mode, 1, 5.0)
         cpu = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": v_one,
-               "sample": "%d trees x %d nodes (%.1f s, %d threads) and %d trees on 1 thread (%.1f s); C restatement of the "
-                         "Java reference, no JVM in this image" % (trees, N, dt_all, threads, max(32, trees // threads), dt_one)}
+               "sample": "first %d trees x %d nodes of the batch, %d passes (%.1f s) on %d threads; first %d trees, %d passes "
+                         "(%.1f s) on 1 thread; C restatement of the Java reference (no JVM in this image)"
+                         % (t_all, N, reps_all, dt_all, threads, t_one, reps_one, dt_one)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -164,3 +164,15 @@ def test_full_size_properties_c2():
     sub = {k: v[idx] for k, v in a.items()}
     assert_close(full[idx], run_oracle(sub, b.flags, b.stub_mode, rates=False)["out"], what="C2 sample")
     assert np.array_equal(full[:, abi.O_N_EXTANT], np.full(b.n_trees, 200.0))
+
+
+def test_cpp_host_mirror_runs_the_reference_junit_test():
+    """gammaspikemodel_b200/host/stumped_tree_prior_test.cpp = StumpedTreePriorTest.java through the C++ host
+    mirror and the C ABI."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gammaspikemodel_b200", "host",
+                       "stumped_tree_prior_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all passed" in r.stdout
