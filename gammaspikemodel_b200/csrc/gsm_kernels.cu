@@ -63,8 +63,25 @@ static __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// streaming (read-once) global loads: read-only path, do not allocate in L1
+static __device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+static __device__ __forceinline__ int2 ld_stream(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+static __device__ __forceinline__ int32_t ld_stream(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// main kernel
+// generic kernel (every wiring)
 // ---------------------------------------------------------------------------------------------------------
 // MINB = CTAs per SM the register allocation is sized for (__launch_bounds__): BLOCK*MINB resident threads.
 template <int BLOCK, int MINB, bool WANT_RATES>
@@ -248,6 +265,290 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// fast kernel: default wiring family (gsm_fast_path_ok), one CTA per tree.
+//   shared memory per node: height 8 B + aux 8 B + packed word (parent index + NL/FAKE/DA/PF bits) 2 or 4 B
+//   -> 18 B/node for trees of <= 4096 nodes (72 KB at 3,999 nodes: three trees resident per SM).
+//   phase 0  TMA bulk copy of the height row; parent row read with coalesced loads and packed into words;
+//            last warp computes the per-tree constants
+//   phase 1  children mark parents non-leaf (idempotent 16/32-bit read-modify-write, no atomics needed)
+//   phase 1b zero-length leaves mark parents fake
+//   phase 2  pass A (per-variant loop): census, own tree term, aux -> smem, DA / parent-fake bits -> word
+//   phase 3  pass B, two adjacent nodes per thread, 128-bit global and shared loads, one-strip prefetch
+//   phase 4  fixed-order reduction + epilogue
+// ---------------------------------------------------------------------------------------------------------
+template <typename WORD, int VARIANT, int BLOCK>
+static __device__ __forceinline__ void fast_pass_a_loop(const GsmFastA& fa, const GsmTabs& T, GsmAcc& A, int n, int tid,
+                                                        const double* sh_h, double* sh_aux, WORD* sh_w) {
+    using W = GsmWord<WORD>;
+    const int nfull = n >> 1;   // full pairs; an odd last node is handled below
+    for (int j = tid; j < nfull; j += BLOCK) {
+        const int i0 = 2 * j;
+        const double2 h2 = *reinterpret_cast<const double2*>(sh_h + i0);
+        const double h[2] = {h2.x, h2.y};
+        uint32_t w[2];
+        double hp[2];
+        bool leaf[2], fake_self[2], da[2], root[2], pf[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            w[k] = sh_w[i0 + k];
+            const int p = static_cast<int>(w[k] & W::IDX);
+            hp[k] = sh_h[p];
+            const uint32_t wp = sh_w[p];
+            root[k] = (p == i0 + k);
+            leaf[k] = !(w[k] & W::NL);
+            fake_self[k] = (w[k] & W::FAKE) != 0;
+            da[k] = leaf[k] && !root[k] && hp[k] == h[k];
+            pf[k] = !root[k] && (wp & W::FAKE);
+        }
+        double aux[2];
+        const bool sp = !fa.safe || gsm_fast_a_special(fa, h[0]) || gsm_fast_a_special(fa, h[1]);
+        if (__any_sync(__activemask(), sp)) {
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                aux[k] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf[k], fake_self[k], da[k], root[k], h[k], hp[k]);
+        } else {
+            gsm_fast_pass_a_pair<VARIANT>(fa, T, A, leaf, fake_self, da, root, h, hp, aux);
+        }
+        *reinterpret_cast<double2*>(sh_aux + i0) = make_double2(aux[0], aux[1]);
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            sh_w[i0 + k] = static_cast<WORD>(w[k] | (da[k] ? W::DA : 0u) | (pf[k] ? W::PF : 0u));
+    }
+    if ((n & 1) && tid == (nfull % BLOCK)) {
+        const int i = n - 1;
+        const uint32_t w = sh_w[i];
+        const int p = static_cast<int>(w & W::IDX);
+        const double h = sh_h[i], hp = sh_h[p];
+        const bool root = (p == i), leaf = !(w & W::NL), fake_self = (w & W::FAKE) != 0;
+        const bool da = leaf && !root && hp == h;
+        const bool pf = !root && (sh_w[p] & W::FAKE);
+        sh_aux[i] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf, fake_self, da, root, h, hp);
+        sh_w[i] = static_cast<WORD>(w | (da ? W::DA : 0u) | (pf ? W::PF : 0u));
+    }
+}
+
+template <typename WORD, int BLOCK, int MINB, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_fast_kernel(const GsmBatch b, double* __restrict__ out_tree,
+                                                                    double* __restrict__ out_rates,
+                                                                    double* __restrict__ out_wspikes) {
+    using W = GsmWord<WORD>;
+    constexpr int NWARP = BLOCK / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int64_t S = b.stride;
+    double* sh_h = reinterpret_cast<double*>(smem_raw);
+    double* sh_aux = sh_h + S;
+    WORD* sh_w = reinterpret_cast<WORD*>(sh_aux + S);
+
+    __shared__ GsmLogEntry sh_logtab[GSM_LOG_TAB_N];
+    __shared__ uint64_t sh_exptab[GSM_EXP_TAB_N];
+    __shared__ GsmTreeConsts K;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int32_t sh_root;
+    __shared__ int32_t sh_anyzero;
+    __shared__ double sh_red[6][NWARP];
+    __shared__ int32_t sh_redi[5][NWARP];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int64_t t = blockIdx.x;
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    double* orow = out_tree + t * GSM_NOUT;
+    if (n <= 0) {
+        if (tid < GSM_NOUT) orow[tid] = NAN;
+        return;
+    }
+    const int64_t row = t * S;
+
+    // ---- phase 0 ----
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+        sh_root = -1;
+        sh_anyzero = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
+        mbar_arrive_expect_tx(&mbar, bytes_h);
+        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &mbar);
+    }
+    for (int i = tid; i < GSM_LOG_TAB_N; i += BLOCK) {   // log / exp tables -> shared memory (3 KB, L2-resident source)
+        const double2 e = gsm_log_tab_d[i];
+        sh_logtab[i].invc = e.x;
+        sh_logtab[i].logc = e.y;
+        sh_exptab[i] = gsm_exp_tab_d[i];
+    }
+    {
+        const int32_t* prow = b.parent + row;
+        for (int i = tid; i < n; i += BLOCK) {
+            int32_t p = ld_stream(prow + i);
+            if (static_cast<uint32_t>(p) >= static_cast<uint32_t>(n)) {   // root (-1) or out of range: points to itself
+                if (p < 0) sh_root = i;
+                p = i;
+            }
+            sh_w[i] = static_cast<WORD>(p);
+        }
+    }
+    if (warp == NWARP - 1) {
+        const double* prm = b.params + t * GSM_NPARAM;
+        if (lane == 0) {
+            gsm_setup_consts(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
+        } else if (lane <= GSM_LUT_M + 1) {
+            gsm_lut_entry(K, prm[GSM_P_SPIKE_SHAPE], lane - 1);
+        }
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+
+    // ---- phase 1: non-leaf marks; note whether any branch has zero length (only then can there be sampled ancestors) ----
+    for (int i = tid; i < n; i += BLOCK) {
+        const int p = static_cast<int>(sh_w[i] & W::IDX);
+        if (p != i) {
+            sh_w[p] = static_cast<WORD>(sh_w[p] | W::NL);
+            if (sh_h[p] == sh_h[i]) sh_anyzero = 1;
+        }
+    }
+    __syncthreads();
+    // ---- phase 1b: sampled ancestors -> fake parents ----
+    if (sh_anyzero) {
+        for (int i = tid; i < n; i += BLOCK) {
+            const uint32_t w = sh_w[i];
+            const int p = static_cast<int>(w & W::IDX);
+            if (!(w & W::NL) && p != i && sh_h[p] == sh_h[i]) sh_w[p] = static_cast<WORD>(sh_w[p] | W::FAKE);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: pass A ----
+    GsmAcc A;
+    gsm_acc_zero(A);
+    GsmFastA fa;
+    GsmFastB fb;
+    gsm_fast_consts(K, fa, fb, n);
+    GsmTabs T;
+    T.logtab = sh_logtab;
+    T.exptab = sh_exptab;
+    switch (fa.variant) {
+        case GSM_TV_COMPLETE_RHO: fast_pass_a_loop<WORD, GSM_TV_COMPLETE_RHO, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
+        case GSM_TV_NO_PSI: fast_pass_a_loop<WORD, GSM_TV_NO_PSI, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
+        case GSM_TV_PSI: fast_pass_a_loop<WORD, GSM_TV_PSI, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
+        case GSM_TV_CONDITIONED: fast_pass_a_loop<WORD, GSM_TV_CONDITIONED, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
+        default: fast_pass_a_loop<WORD, GSM_TV_NONE, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
+    }
+    __syncthreads();
+
+    // ---- phase 3: pass B, two adjacent nodes per thread ----
+    {
+        const double* rate_row = b.rate + row;
+        const double* spike_row = b.spike + row;
+        const int32_t* nst_row = b.nstubs ? b.nstubs + row : nullptr;
+        const double2* rate2 = reinterpret_cast<const double2*>(rate_row);
+        const double2* spike2 = reinterpret_cast<const double2*>(spike_row);
+        const int2* nst2 = reinterpret_cast<const int2*>(nst_row);
+        double* orate = (WANT_RATES && out_rates) ? out_rates + row : nullptr;
+        double* owsp = (WANT_RATES && out_wspikes) ? out_wspikes + row : nullptr;
+        double dummy[2];
+        const int nfull = n >> 1;
+        int j = tid;
+        double2 r_n = make_double2(1.0, 1.0), s_n = make_double2(1.0, 1.0);
+        int2 k_n = make_int2(0, 0);
+        if (j < nfull) {
+            r_n = ld_stream(rate2 + j);
+            s_n = ld_stream(spike2 + j);
+            if (nst2) k_n = ld_stream(nst2 + j);
+        }
+        while (j < nfull) {
+            const double rate[2] = {r_n.x, r_n.y}, spike[2] = {s_n.x, s_n.y};
+            const int32_t nst_raw[2] = {k_n.x, k_n.y};
+            const int jn = j + BLOCK;
+            if (jn < nfull) {  // prefetch the next strip
+                r_n = ld_stream(rate2 + jn);
+                s_n = ld_stream(spike2 + jn);
+                if (nst2) k_n = ld_stream(nst2 + jn);
+            }
+            const int i0 = 2 * j;
+            const double2 h2 = *reinterpret_cast<const double2*>(sh_h + i0);
+            const double2 a2 = *reinterpret_cast<const double2*>(sh_aux + i0);
+            const double h[2] = {h2.x, h2.y}, aux[2] = {a2.x, a2.y};
+            bool da[2], pf[2], root[2];
+            double hp[2], auxp[2], len[2], dA[2], E[2];
+            bool sp = false;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t w = sh_w[i0 + k];
+                const int p = static_cast<int>(w & W::IDX);
+                da[k] = (w & W::DA) != 0;
+                pf[k] = (w & W::PF) != 0;
+                root[k] = (p == i0 + k);
+                hp[k] = sh_h[p];
+                auxp[k] = sh_aux[p];
+                len[k] = hp[k] - h[k];                                      // a root points to itself: len == 0
+                dA[k] = aux[k] - auxp[k];
+                E[k] = fma(len[k], fb.kE, 2 * dA[k]);                       // STP:749-769 via aux
+                sp = sp || gsm_fast_b_special(fb, i0 + k, da[k], pf[k], root[k], len[k], E[k], rate[k], spike[k], nst_raw[k]);
+            }
+            if (__any_sync(__activemask(), sp)) {
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                    gsm_fast_pass_b_checked<WANT_RATES>(fb, K, T, g_logfact, A, i0 + k, da[k], pf[k], root[k], h[k], hp[k], aux[k],
+                                                        auxp[k], rate[k], spike[k], nst_raw[k], orate ? orate + i0 + k : dummy,
+                                                        owsp ? owsp + i0 + k : dummy);
+            } else {
+                gsm_fast_pass_b_pair<WANT_RATES>(fb, K, T, g_logfact, A, i0, da, pf, root, len, E, dA, rate, spike, nst_raw,
+                                                 orate ? orate + i0 : dummy, owsp ? owsp + i0 : dummy);
+            }
+            j = jn;
+        }
+        if ((n & 1) && tid == (nfull % BLOCK)) {   // odd last node
+            const int i = n - 1;
+            const uint32_t w = sh_w[i];
+            const int p = static_cast<int>(w & W::IDX);
+            gsm_fast_pass_b_checked<WANT_RATES>(fb, K, T, g_logfact, A, i, (w & W::DA) != 0, (w & W::PF) != 0, p == i, sh_h[i], sh_h[p],
+                                                sh_aux[i], sh_aux[p], __ldg(rate_row + i), __ldg(spike_row + i),
+                                                nst_row ? __ldg(nst_row + i) : 0, orate ? orate + i : dummy, owsp ? owsp + i : dummy);
+        }
+    }
+
+    // ---- phase 4: reductions (fixed order) + epilogue ----
+    double v0 = warp_sum(A.tree), v1 = warp_sum(A.stub), v2 = warp_sum(A.spike), v3 = warp_sum(A.rate),
+           v4 = warp_sum(A.burst), v5 = warp_sum(A.dist);
+    int32_t c0 = __reduce_add_sync(0xffffffffu, A.n_extant), c1 = __reduce_add_sync(0xffffffffu, A.n_leaf),
+            c2 = __reduce_add_sync(0xffffffffu, A.n_da), c3 = __reduce_add_sync(0xffffffffu, A.n_extinct),
+            c4 = static_cast<int32_t>(__reduce_or_sync(0xffffffffu, static_cast<uint32_t>(A.bad)));
+    if (lane == 0) {
+        sh_red[0][warp] = v0; sh_red[1][warp] = v1; sh_red[2][warp] = v2;
+        sh_red[3][warp] = v3; sh_red[4][warp] = v4; sh_red[5][warp] = v5;
+        sh_redi[0][warp] = c0; sh_redi[1][warp] = c1; sh_redi[2][warp] = c2; sh_redi[3][warp] = c3; sh_redi[4][warp] = c4;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        GsmAcc R;
+        gsm_acc_zero(R);
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+            R.tree += sh_red[0][w]; R.stub += sh_red[1][w]; R.spike += sh_red[2][w];
+            R.rate += sh_red[3][w]; R.burst += sh_red[4][w]; R.dist += sh_red[5][w];
+            R.n_extant += sh_redi[0][w]; R.n_leaf += sh_redi[1][w]; R.n_da += sh_redi[2][w];
+            R.n_extinct += sh_redi[3][w]; R.bad |= sh_redi[4][w];
+        }
+        const int32_t root = sh_root;
+        double res[GSM_NOUT];
+        if (root < 0) {
+#pragma unroll
+            for (int k = 0; k < GSM_NOUT; k++) res[k] = NAN;
+        } else {
+            gsm_fast_fix_acc(K, R, n);
+            gsm_finish_consts(K, sh_h[root]);
+            gsm_finalize(K, R, n, (sh_w[root] & W::FAKE) != 0, res);
+        }
+#pragma unroll
+        for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // BranchSpikePrior.getCumulativeProbs (BSP:315-389) for one branch; log-time only, one thread.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void gsm_stub_cdf_kernel(const GsmBatch b, int64_t t, int32_t node, double* __restrict__ cdf, int32_t cap,
@@ -344,24 +645,65 @@ static cudaError_t launch_block(const GsmBatch& b, double* o, double* r, double*
     return cudaGetLastError();
 }
 
-// Launch configuration: one CTA per tree.  The shared-memory footprint (22 B per node) bounds the number of
-// resident trees per SM; BLOCK and the register budget (MINB) are picked so that the resident CTAs give
-// ~1024 threads per SM.  GSM_BLOCK / GSM_MINB override the choice for tuning runs.
+template <typename WORD, int BLOCK, int MINB>
+static cudaError_t launch_fast(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(b.stride) * (16u + sizeof(WORD));
+    const dim3 grid(static_cast<unsigned>(b.n_trees));
+    cudaError_t e;
+    if (r || w) {
+        auto kern = gsm_eval_fast_kernel<WORD, BLOCK, MINB, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+    } else {
+        auto kern = gsm_eval_fast_kernel<WORD, BLOCK, MINB, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+    }
+    return cudaGetLastError();
+}
+
+// Launch configuration: one CTA per tree.  The shared-memory footprint per node (18-22 B) bounds the number of
+// resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in
+// profiles/.  GSM_BLOCK / GSM_MINB / GSM_GENERIC override the choice for tuning runs.
 int gsm_launch_eval(const GsmBatch& b, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                     cudaStream_t stream) {
     if (b.n_trees <= 0) return 0;
-    // measured on B200 (profiles/r01_tuning.md): 128x6 for <=512 nodes, 256x3 up to 2048, 384x2 above
-    int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
-    int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
+    const bool fast = gsm_fast_path_ok(b.flags, b.stub_mode) && b.rate != nullptr && !getenv("GSM_GENERIC");
+    int block, minb;
+    if (fast) {
+        block = b.n_nodes <= 512 ? 128 : 256;
+        minb = b.n_nodes <= 512 ? 6 : 3;
+    } else {
+        block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
+        minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
+    }
     if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
     if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
     cudaError_t e = cudaErrorInvalidConfiguration;
+    if (fast) {
+        const bool w16 = b.n_nodes <= 4096;
+#define GSM_CFG(B, M)                                                                                      \
+    if (block == B && minb == M)                                                                           \
+        e = w16 ? launch_fast<uint16_t, B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream)           \
+                : launch_fast<uint32_t, B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
+        GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
+        GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
+        GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
+#undef GSM_CFG
+    } else {
 #define GSM_CFG(B, M) \
     if (block == B && minb == M) e = launch_block<B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
-    GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
-    GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
-    GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
+        GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
+        GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
+        GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
 #undef GSM_CFG
+    }
     if (e != cudaSuccess) return -static_cast<int>(e);
     return 1;
 }

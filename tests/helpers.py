@@ -20,6 +20,8 @@ def emu():
         _emu = C.CDLL(os.path.join(ROOT, "tests", "_emu", "libgsm_emu.so"))
         _emu.gsm_emu_eval_batch.argtypes = [C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 11
         _emu.gsm_emu_eval_batch.restype = C.c_int
+        _emu.gsm_emu_eval_batch_fast.argtypes = _emu.gsm_emu_eval_batch.argtypes
+        _emu.gsm_emu_eval_batch_fast.restype = C.c_int
     return _emu
 
 
@@ -47,6 +49,20 @@ def run_emu(a, flags, mode, node_count=None, rates=True):
     nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
     emu().gsm_emu_eval_batch(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
                              _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w))
+    return {"out": out, "rates": r, "wspikes": w}
+
+
+def run_emu_fast(a, flags, mode, node_count=None, rates=True):
+    """host build of the fast-path math (gsm_eval_fast_kernel); returns None when the wiring is outside its family"""
+    T, N = a["height"].shape
+    out = np.empty((T, abi.NOUT))
+    r = np.full((T, N), np.nan) if rates else None
+    w = np.full((T, N), np.nan) if rates else None
+    nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
+    rc = emu().gsm_emu_eval_batch_fast(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
+                                       _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w))
+    if rc != 0:
+        return None
     return {"out": out, "rates": r, "wspikes": w}
 
 

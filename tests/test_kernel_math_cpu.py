@@ -7,7 +7,7 @@ import pytest
 
 from gammaspikemodel_b200 import abi
 from cases import build_cases
-from helpers import assert_results_match, run_emu, run_oracle
+from helpers import assert_results_match, run_emu, run_emu_fast, run_oracle
 
 CASES = build_cases()
 
@@ -28,3 +28,13 @@ def test_logp_only_variant_equals_rates_variant():
     without = run_emu(a, flags, mode, rates=False)
     # the logP-only kernel skips the division of PRCM:236; SPL's sum differs by <= 1 ulp per branch
     assert np.allclose(with_rates["out"], without["out"], rtol=1e-13, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_emulated_fast_path_matches_oracle(case):
+    """the register-hoisted fast path (gsm_eval_fast_kernel's math) on every case of its wiring family"""
+    name, a, flags, mode, nc = case
+    got = run_emu_fast(a, flags, mode, node_count=nc)
+    if got is None:
+        pytest.skip("wiring outside the fast-path family (generic kernel handles it)")
+    assert_results_match(got, run_oracle(a, flags, mode, node_count=nc), node_count=nc, what=name)
