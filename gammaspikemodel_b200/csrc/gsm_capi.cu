@@ -27,6 +27,8 @@ struct Slot {  // one staging slot of the streaming path
     double *out_rates = nullptr, *out_wsp = nullptr;
     int32_t *parent = nullptr, *nstubs = nullptr, *node_count = nullptr;
     uint8_t* use_spike = nullptr;
+    GsmScratch scratch;
+    int64_t scratch_trees = 0;
 };
 
 }  // namespace
@@ -54,6 +56,8 @@ struct gsm_handle {
     int64_t slot_trees = 0;
     int64_t slot_stride = 0;
     bool slot_rates = false, slot_wsp = false;
+    GsmScratch scratch;          // lean-path scratch of the handle's own stream
+    int64_t scratch_trees = 0;
     std::string err;
     int64_t launches = 0;
 };
@@ -96,6 +100,29 @@ void dfree(T*& p) {
     p = nullptr;
 }
 
+// lean-path scratch for up to `trees` trees (rows + redo list); grows, never shrinks
+cudaError_t ensure_scratch(GsmScratch& sc, int64_t& cap, int64_t trees) {
+    if (cap >= trees && sc.rows && sc.redo) return cudaSuccess;
+    if (sc.rows) cudaFree(sc.rows);
+    if (sc.redo) cudaFree(sc.redo);
+    sc = GsmScratch{};
+    cap = 0;
+    unsigned char* rows = nullptr;
+    cudaError_t e = dalloc(&rows, trees * static_cast<int64_t>(gsm_scratch_row_bytes()));
+    if (e != cudaSuccess) return e;
+    sc.rows = rows;
+    e = dalloc(&sc.redo, trees + 4);
+    if (e != cudaSuccess) return e;
+    cap = trees;
+    return cudaSuccess;
+}
+void free_scratch(GsmScratch& sc, int64_t& cap) {
+    if (sc.rows) cudaFree(sc.rows);
+    if (sc.redo) cudaFree(sc.redo);
+    sc = GsmScratch{};
+    cap = 0;
+}
+
 // dense host [T][n] -> pitched device [T][stride]
 template <typename T>
 cudaError_t h2d_rows(T* dst, int64_t stride, const T* src, int64_t n, int64_t rows, cudaStream_t st) {
@@ -115,6 +142,7 @@ void free_slots(gsm_handle* h) {
         dfree(s.height); dfree(s.rate); dfree(s.spike); dfree(s.params); dfree(s.out);
         dfree(s.out_rates); dfree(s.out_wsp); dfree(s.parent); dfree(s.nstubs); dfree(s.node_count);
         dfree(s.use_spike);
+        free_scratch(s.scratch, s.scratch_trees);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Slot{};
@@ -205,6 +233,7 @@ int gsm_destroy(gsm_handle* h) {
     dfree(h->d_height); dfree(h->d_rate); dfree(h->d_spike); dfree(h->d_parent); dfree(h->d_nstubs);
     dfree(h->d_node_count); dfree(h->d_params); dfree(h->d_use); dfree(h->d_out); dfree(h->d_out_rates);
     dfree(h->d_out_wsp); dfree(h->d_cdf);
+    free_scratch(h->scratch, h->scratch_trees);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return GSM_OK;
@@ -315,7 +344,8 @@ int gsm_eval(gsm_handle* h, double* out_tree, double* out_rates, double* out_wsp
     const int64_t cells = h->max_trees * h->max_stride;
     if (out_rates && !h->d_out_rates) GSM_CUDA(h, dalloc(&h->d_out_rates, cells));
     if (out_wspikes && !h->d_out_wsp) GSM_CUDA(h, dalloc(&h->d_out_wsp, cells));
-    int nl = gsm_launch_eval(b, h->d_out, out_rates ? h->d_out_rates : nullptr, out_wspikes ? h->d_out_wsp : nullptr, h->stream);
+    GSM_CUDA(h, ensure_scratch(h->scratch, h->scratch_trees, b.n_trees));
+    int nl = gsm_launch_eval(b, h->scratch, h->d_out, out_rates ? h->d_out_rates : nullptr, out_wspikes ? h->d_out_wsp : nullptr, h->stream);
     if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
     h->launches += nl;
     GSM_CUDA(h, cudaMemcpyAsync(out_tree, h->d_out, b.n_trees * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -343,6 +373,7 @@ static int ensure_slots(gsm_handle* h, int64_t chunk, int64_t stride, bool rates
         GSM_CUDA(h, dalloc(&s.out, chunk * GSM_NOUT));
         if (rates) GSM_CUDA(h, dalloc(&s.out_rates, cells));
         if (wsp) GSM_CUDA(h, dalloc(&s.out_wsp, cells));
+        GSM_CUDA(h, ensure_scratch(s.scratch, s.scratch_trees, chunk));
     }
     h->slot_trees = chunk;
     h->slot_stride = stride;
@@ -391,7 +422,7 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
         b.rate = rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = nstubs ? s.nstubs : nullptr;
         b.params = s.params; b.use_spike = use_spike ? s.use_spike : nullptr;
         b.flags = h->flags; b.stub_mode = h->stub_mode;
-        int nl = gsm_launch_eval(b, s.out, out_rates ? s.out_rates : nullptr, out_wspikes ? s.out_wsp : nullptr, s.stream);
+        int nl = gsm_launch_eval(b, s.scratch, s.out, out_rates ? s.out_rates : nullptr, out_wspikes ? s.out_wsp : nullptr, s.stream);
         if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_host launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
         h->launches += nl;
         GSM_CUDA(h, cudaMemcpyAsync(out_tree + t0 * GSM_NOUT, s.out, T * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -476,7 +507,8 @@ int gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, doub
     if (!d_out_tree) return fail(h, GSM_E_ARG, "gsm_eval_device: d_out_tree is NULL");
     GSM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-    int nl = gsm_launch_eval(b, d_out_tree, d_out_rates, d_out_wspikes, st);
+    GSM_CUDA(h, ensure_scratch(h->scratch, h->scratch_trees, b.n_trees));
+    int nl = gsm_launch_eval(b, h->scratch, d_out_tree, d_out_rates, d_out_wspikes, st);
     if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_device launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
     h->launches += nl;
     return GSM_OK;

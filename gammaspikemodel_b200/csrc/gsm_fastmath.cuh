@@ -156,81 +156,3 @@ GSM_HD double gsm_exp(double x) {
     tmp = fma(r2 * r2, b, tmp);
     return fma(scale, tmp, scale);
 }
-
-// ---- branch-free bodies + table pointers (fast kernel: tables staged in shared memory) -------------------------
-// The bodies assume a "regular" argument (log: positive normal finite; exp: |x| < 704).  Callers evaluate the body
-// on a sanitised argument for every lane and patch the rare special lanes afterwards with the out-of-line libdevice
-// fallback, so that several independent evaluations can be interleaved by the scheduler (no branches in between).
-struct GsmTabs {
-    const GsmLogEntry* logtab;   // GSM_LOG_TAB_N entries {invc, logc}
-    const uint64_t* exptab;      // GSM_EXP_TAB_N entries
-};
-
-GSM_HD bool gsm_log_special(double x) { return (uint32_t)(gsm_hi32(x) - 0x00100000) >= 0x7fe00000u; }
-GSM_HD bool gsm_exp_special(double x) { return ((uint32_t)gsm_hi32(x) & 0x7fffffffu) >= 0x40860000u; }
-
-GSM_HD double gsm_log_body(double x, const GsmLogEntry* __restrict__ tab) {
-    const int32_t hi = gsm_hi32(x);
-    const int32_t tmp = hi - 0x3fe60000;
-    const int32_t i = (tmp >> 13) & (GSM_LOG_TAB_N - 1);
-    const int32_t k = tmp >> 20;
-    const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
-    const GsmLogEntry e = tab[i];
-#if defined(__CUDA_ARCH__)
-    const double* __restrict__ c = gsm_log_poly_d;
-    const double ln2hi = gsm_fm_consts_d[0], ln2lo = gsm_fm_consts_d[1], kbias = gsm_fm_consts_d[6];
-#else
-    const double* c = gsm_log_poly_h;
-    const double ln2hi = GSM_LN2_HI, ln2lo = GSM_LN2_LO, kbias = 4503599627371520.0;
-#endif
-    const double r = fma(z, e.invc, -1.0);
-    const double kd = gsm_hilo(0x43300000, k + 1024) - kbias;
-    const double hi_part = fma(kd, ln2hi, e.logc);
-    const double r2 = r * r;
-    // Estrin-style split of the degree-6 polynomial keeps the dependent chain short
-    const double p01 = fma(c[1], r, c[0]);
-    const double p23 = fma(c[3], r, c[2]);
-    const double p45 = fma(c[5], r, c[4]);
-    const double r4 = r2 * r2;
-    const double q = fma(c[6], r2, p45);
-    const double p = fma(q, r4, fma(p23, r2, p01));
-    const double y = fma(p, r2, r);
-    return hi_part + fma(kd, ln2lo, y);
-}
-
-GSM_HD double gsm_exp_body(double x, const uint64_t* __restrict__ tab) {
-#if defined(__CUDA_ARCH__)
-    const double invln2n = gsm_fm_consts_d[2], nhi = gsm_fm_consts_d[3], nlo = gsm_fm_consts_d[4], shift = gsm_fm_consts_d[5];
-    const double* __restrict__ c = gsm_exp_poly_d;
-#else
-    const double invln2n = GSM_EXP_INVLN2N, nhi = GSM_EXP_NEGLN2HIN, nlo = GSM_EXP_NEGLN2LON, shift = 0x1.8p52;
-    const double* c = gsm_exp_poly_h;
-#endif
-    double kd = fma(x, invln2n, shift);
-    const int32_t ki = gsm_lo32(kd);
-    kd -= shift;
-    double r = fma(kd, nhi, x);
-    r = fma(kd, nlo, r);
-    const uint64_t t = tab[ki & (GSM_EXP_TAB_N - 1)];
-    const double scale = gsm_hilo((int32_t)(t >> 32) + (ki << 13), (int32_t)(t & 0xffffffffu));
-    const double r2 = r * r;
-    const double a = fma(r, c[1], c[0]);
-    const double b = fma(r, c[3], c[2]);
-    double tmp = fma(r2, a, r);
-    tmp = fma(r2 * r2, b, tmp);
-    return fma(scale, tmp, scale);
-}
-
-// full-range versions on caller-provided tables (body on a sanitised argument + rare fix-up)
-GSM_HD double gsm_log_t(double x, const GsmTabs& T) {
-    const bool sp = gsm_log_special(x);
-    double y = gsm_log_body(sp ? 1.0 : x, T.logtab);
-    if (sp) y = gsm_log_slow(x);
-    return y;
-}
-GSM_HD double gsm_exp_t(double x, const GsmTabs& T) {
-    const bool sp = gsm_exp_special(x);
-    double y = gsm_exp_body(sp ? 0.0 : x, T.exptab);
-    if (sp) y = gsm_exp_slow(x);
-    return y;
-}

@@ -14,11 +14,14 @@
 
 #include "gsm_kernels.cuh"
 #include "gsm_node_math.cuh"
+#include "gsm_lean.cuh"
 
 #include <cstdio>
 #include <cstdlib>
 
 __device__ double g_logfact[GSM_LOGFACT_N];
+// constant tables of the lean path (stubtab is filled by gsm_init_tables)
+__device__ GsmLeanBlob g_lean_blob = {GSM_LOG9_TAB_INIT, GSM_EXP9_TAB_INIT, {}};
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared::cluster, completion on an mbarrier)
@@ -51,7 +54,7 @@ static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 // bytes must be a multiple of 16; src and dst 16-byte aligned
 static __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
@@ -80,33 +83,86 @@ static __device__ __forceinline__ int32_t ld_stream(const int32_t* p) {
     return v;
 }
 
+static __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// shared-memory accesses by 32-bit shared-window address (the hot loops of the lean kernel keep base addresses in
+// registers; going through generic pointers costs a window-base computation per access)
+static __device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+static __device__ __forceinline__ void sts_v4u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+static __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// generic kernel (every wiring)
+// per-tree scratch row written by the lean kernel and consumed by the post kernel (128 bytes)
 // ---------------------------------------------------------------------------------------------------------
-// MINB = CTAs per SM the register allocation is sized for (__launch_bounds__): BLOCK*MINB resident threads.
-template <int BLOCK, int MINB, bool WANT_RATES>
-__global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
-                                                         double* __restrict__ out_rates,
-                                                         double* __restrict__ out_wspikes) {
+struct __align__(16) GsmLeanRow {
+    double tree, stub, spike, rate, burst, dist;   // combined factor sums (gsm_lean_combine), reduced over the CTA
+    double T;                                      // root height
+    int32_t n_nst, n_leafterm, n_plain, n_fake;
+    int32_t n_extant, n_extinct, n_da, root_fake;
+    int32_t status;                                // 1: valid, 0: tree was sent to the redo list
+    int32_t pad[9];
+};
+static_assert(sizeof(GsmLeanRow) == 128, "GsmLeanRow must be 128 bytes");
+
+// ---------------------------------------------------------------------------------------------------------
+// generic evaluation of one tree by one CTA (every wiring, every special value): the statement-by-statement
+// path.  Used directly for wirings outside the lean family and for the trees the lean kernel hands back.
+// ---------------------------------------------------------------------------------------------------------
+struct GsmGenericShared {
+    GsmTreeConsts K;
+    uint64_t mbar;
+    int32_t root;
+    double red[6][16];
+    int32_t redi[5][16];
+};
+
+template <int BLOCK, bool WANT_RATES>
+static __device__ void gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t parity, unsigned char* smem_raw,
+                                        GsmGenericShared& sh, double* __restrict__ out_tree, double* __restrict__ out_rates,
+                                        double* __restrict__ out_wspikes) {
     constexpr int NWARP = BLOCK / 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int64_t S = b.stride;
     double* sh_h = reinterpret_cast<double*>(smem_raw);
     double* sh_aux = sh_h + S;
     int32_t* sh_par = reinterpret_cast<int32_t*>(sh_aux + S);
     uint8_t* sh_nonleaf = reinterpret_cast<uint8_t*>(sh_par + S);
     uint8_t* sh_fake = sh_nonleaf + S;
-
-    __shared__ GsmTreeConsts K;
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ int32_t sh_root;
-    __shared__ double sh_red[6][NWARP];
-    __shared__ int32_t sh_redi[5][NWARP];
+    GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int64_t t = blockIdx.x;
     int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
     if (n > b.n_nodes) n = b.n_nodes;
     double* orow = out_tree + t * GSM_NOUT;
@@ -118,17 +174,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
 
     // ---- phase 0 ----
     if (tid == 0) {
-        mbar_init(&mbar, 1);
-        fence_mbar_init();
-        sh_root = -1;
-    }
-    __syncthreads();
-    if (tid == 0) {
+        sh.root = -1;
         const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
         const uint32_t bytes_p = (static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
-        mbar_arrive_expect_tx(&mbar, bytes_h + bytes_p);
-        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &mbar);
-        tma_bulk_g2s(sh_par, b.parent + row, bytes_p, &mbar);
+        mbar_arrive_expect_tx(&sh.mbar, bytes_h + bytes_p);
+        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &sh.mbar);
+        tma_bulk_g2s(sh_par, b.parent + row, bytes_p, &sh.mbar);
     }
     {
         // clear both flag arrays (2*S bytes, S % 32 == 0) with 32-bit stores
@@ -145,14 +196,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
         }
     }
     __syncthreads();
-    mbar_wait(&mbar, 0);
+    mbar_wait(&sh.mbar, parity);
 
     // ---- phase 1: non-leaf marks, root, parent sanitising ----
     for (int i = tid; i < n; i += BLOCK) {
         const int32_t p = sh_par[i];
         if (static_cast<uint32_t>(p) < static_cast<uint32_t>(n)) sh_nonleaf[p] = 1;
         else {
-            if (p < 0) sh_root = i;
+            if (p < 0) sh.root = i;
             else sh_par[i] = -1;  // out-of-range parent: treated as detached (never dereferenced)
         }
     }
@@ -235,9 +286,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
             c2 = __reduce_add_sync(0xffffffffu, A.n_da), c3 = __reduce_add_sync(0xffffffffu, A.n_extinct),
             c4 = static_cast<int32_t>(__reduce_or_sync(0xffffffffu, static_cast<uint32_t>(A.bad)));
     if (lane == 0) {
-        sh_red[0][warp] = v0; sh_red[1][warp] = v1; sh_red[2][warp] = v2;
-        sh_red[3][warp] = v3; sh_red[4][warp] = v4; sh_red[5][warp] = v5;
-        sh_redi[0][warp] = c0; sh_redi[1][warp] = c1; sh_redi[2][warp] = c2; sh_redi[3][warp] = c3; sh_redi[4][warp] = c4;
+        sh.red[0][warp] = v0; sh.red[1][warp] = v1; sh.red[2][warp] = v2;
+        sh.red[3][warp] = v3; sh.red[4][warp] = v4; sh.red[5][warp] = v5;
+        sh.redi[0][warp] = c0; sh.redi[1][warp] = c1; sh.redi[2][warp] = c2; sh.redi[3][warp] = c3; sh.redi[4][warp] = c4;
     }
     __syncthreads();
     if (tid == 0) {
@@ -245,12 +296,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
         gsm_acc_zero(R);
 #pragma unroll
         for (int w = 0; w < NWARP; w++) {
-            R.tree += sh_red[0][w]; R.stub += sh_red[1][w]; R.spike += sh_red[2][w];
-            R.rate += sh_red[3][w]; R.burst += sh_red[4][w]; R.dist += sh_red[5][w];
-            R.n_extant += sh_redi[0][w]; R.n_leaf += sh_redi[1][w]; R.n_da += sh_redi[2][w];
-            R.n_extinct += sh_redi[3][w]; R.bad |= sh_redi[4][w];
+            R.tree += sh.red[0][w]; R.stub += sh.red[1][w]; R.spike += sh.red[2][w];
+            R.rate += sh.red[3][w]; R.burst += sh.red[4][w]; R.dist += sh.red[5][w];
+            R.n_extant += sh.redi[0][w]; R.n_leaf += sh.redi[1][w]; R.n_da += sh.redi[2][w];
+            R.n_extinct += sh.redi[3][w]; R.bad |= sh.redi[4][w];
         }
-        const int32_t root = sh_root;
+        const int32_t root = sh.root;
         double res[GSM_NOUT];
         if (root < 0) {
 #pragma unroll
@@ -264,287 +315,443 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// fast kernel: default wiring family (gsm_fast_path_ok), one CTA per tree.
-//   shared memory per node: height 8 B + aux 8 B + packed word (parent index + NL/FAKE/DA/PF bits) 2 or 4 B
-//   -> 18 B/node for trees of <= 4096 nodes (72 KB at 3,999 nodes: three trees resident per SM).
-//   phase 0  TMA bulk copy of the height row; parent row read with coalesced loads and packed into words;
-//            last warp computes the per-tree constants
-//   phase 1  children mark parents non-leaf (idempotent 16/32-bit read-modify-write, no atomics needed)
-//   phase 1b zero-length leaves mark parents fake
-//   phase 2  pass A (per-variant loop): census, own tree term, aux -> smem, DA / parent-fake bits -> word
-//   phase 3  pass B, two adjacent nodes per thread, 128-bit global and shared loads, one-strip prefetch
-//   phase 4  fixed-order reduction + epilogue
-// ---------------------------------------------------------------------------------------------------------
-template <typename WORD, int VARIANT, int BLOCK>
-static __device__ __forceinline__ void fast_pass_a_loop(const GsmFastA& fa, const GsmTabs& T, GsmAcc& A, int n, int tid,
-                                                        const double* sh_h, double* sh_aux, WORD* sh_w) {
-    using W = GsmWord<WORD>;
-    const int nfull = n >> 1;   // full pairs; an odd last node is handled below
-    for (int j = tid; j < nfull; j += BLOCK) {
-        const int i0 = 2 * j;
-        const double2 h2 = *reinterpret_cast<const double2*>(sh_h + i0);
-        const double h[2] = {h2.x, h2.y};
-        uint32_t w[2];
-        double hp[2];
-        bool leaf[2], fake_self[2], da[2], root[2], pf[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            w[k] = sh_w[i0 + k];
-            const int p = static_cast<int>(w[k] & W::IDX);
-            hp[k] = sh_h[p];
-            const uint32_t wp = sh_w[p];
-            root[k] = (p == i0 + k);
-            leaf[k] = !(w[k] & W::NL);
-            fake_self[k] = (w[k] & W::FAKE) != 0;
-            da[k] = leaf[k] && !root[k] && hp[k] == h[k];
-            pf[k] = !root[k] && (wp & W::FAKE);
-        }
-        double aux[2];
-        const bool sp = !fa.safe || gsm_fast_a_special(fa, h[0]) || gsm_fast_a_special(fa, h[1]);
-        if (__any_sync(__activemask(), sp)) {
-#pragma unroll
-            for (int k = 0; k < 2; k++)
-                aux[k] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf[k], fake_self[k], da[k], root[k], h[k], hp[k]);
-        } else {
-            gsm_fast_pass_a_pair<VARIANT>(fa, T, A, leaf, fake_self, da, root, h, hp, aux);
-        }
-        *reinterpret_cast<double2*>(sh_aux + i0) = make_double2(aux[0], aux[1]);
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-            sh_w[i0 + k] = static_cast<WORD>(w[k] | (da[k] ? W::DA : 0u) | (pf[k] ? W::PF : 0u));
+// One CTA per tree (wirings outside the lean family).
+// MINB = CTAs per SM the register allocation is sized for (__launch_bounds__): BLOCK*MINB resident threads.
+template <int BLOCK, int MINB, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
+                                                               double* __restrict__ out_rates,
+                                                               double* __restrict__ out_wspikes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ GsmGenericShared sh;
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.mbar, 1);
+        fence_mbar_init();
     }
-    if ((n & 1) && tid == (nfull % BLOCK)) {
-        const int i = n - 1;
-        const uint32_t w = sh_w[i];
-        const int p = static_cast<int>(w & W::IDX);
-        const double h = sh_h[i], hp = sh_h[p];
-        const bool root = (p == i), leaf = !(w & W::NL), fake_self = (w & W::FAKE) != 0;
-        const bool da = leaf && !root && hp == h;
-        const bool pf = !root && (sh_w[p] & W::FAKE);
-        sh_aux[i] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf, fake_self, da, root, h, hp);
-        sh_w[i] = static_cast<WORD>(w | (da ? W::DA : 0u) | (pf ? W::PF : 0u));
+    __syncthreads();
+    gsm_generic_tree<BLOCK, WANT_RATES>(b, blockIdx.x, 0u, smem_raw, sh, out_tree, out_rates, out_wspikes);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// post kernel of the lean path (second and last launch of an evaluation):
+//   part 1  one THREAD per tree: per-tree constants with their logarithms, per-node constants, the
+//           dispatcher / epilogue of STP:150-284 (gsm_finalize) on the lean kernel's scratch row -> result row
+//   part 2  one CTA per tree of the redo list: the generic path
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK, int MINB, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b, const GsmLeanRow* __restrict__ rows,
+                                                               const int32_t* __restrict__ redo_count,
+                                                               const int32_t* __restrict__ redo_list,
+                                                               double* __restrict__ out_tree, double* __restrict__ out_rates,
+                                                               double* __restrict__ out_wspikes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ GsmGenericShared sh;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * BLOCK + threadIdx.x; t < b.n_trees;
+         t += static_cast<int64_t>(gridDim.x) * BLOCK) {
+        const GsmLeanRow r = rows[t];
+        if (r.status != 1) continue;
+        int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+        if (n > b.n_nodes) n = b.n_nodes;
+        GsmTreeConsts K;
+        gsm_setup_consts(K, b.params + t * GSM_NPARAM, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags,
+                         b.stub_mode);
+        GsmLeanC c;
+        gsm_lean_consts(K, c, n);
+        GsmAcc A;
+        gsm_acc_zero(A);
+        A.n_leaf = c.L;
+        A.n_extant = r.n_extant;
+        A.n_extinct = r.n_extinct;
+        A.n_da = r.n_da;
+        GsmLean6 s6;
+        s6.tree = r.tree; s6.stub = r.stub; s6.spike = r.spike; s6.rate = r.rate; s6.burst = r.burst; s6.dist = r.dist;
+        gsm_lean_finish(K, c, s6, r.n_nst, r.n_leafterm, r.n_plain, r.n_fake, n, A);
+        gsm_finish_consts(K, r.T);
+        double res[GSM_NOUT];
+        gsm_finalize(K, A, n, r.root_fake != 0, res);
+        double* orow = out_tree + t * GSM_NOUT;
+#pragma unroll
+        for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
+    }
+    const int32_t cnt = *redo_count;
+    if (static_cast<int32_t>(blockIdx.x) >= cnt) return;
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (int32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+        gsm_generic_tree<BLOCK, WANT_RATES>(b, redo_list[k], parity, smem_raw, sh, out_tree, out_rates, out_wspikes);
+        parity ^= 1u;
+        __syncthreads();
     }
 }
 
-template <typename WORD, int BLOCK, int MINB, bool WANT_RATES>
-__global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_fast_kernel(const GsmBatch b, double* __restrict__ out_tree,
-                                                                    double* __restrict__ out_rates,
-                                                                    double* __restrict__ out_wspikes) {
-    using W = GsmWord<WORD>;
+// ---------------------------------------------------------------------------------------------------------
+// lean kernel: default wiring family (gsm_lean_wiring_ok), one CTA per tree.  See gsm_lean.cuh.
+//   shared memory: height row 8 B/node (TMA) + aux row 8 B/node (first used as the TMA landing zone of the
+//   parent row) + packed word 2 B/node (parent index, FAKE bit) + 12.8 KB of log/exp/stub tables (TMA)
+//   + the per-tree Gamma table.
+//   phase 0  one thread issues three TMA bulk copies; one warp computes the arithmetic-only per-tree
+//            constants and, one m per lane, the table {shape m - 1, log shape - logGamma(shape m)}
+//   phase 1  parents int32 -> packed 16-bit words, validation of BEAST's numbering (eight nodes per step)
+//   phase 2  pass A: aux = log G(h) for node pairs; leaves detect sampled ancestors and mark fake parents
+//   phase 3  pass B: node pairs, 128-bit global / shared loads, one-strip register prefetch;
+//            CLEAN or GENERAL flavour per tree
+//   phase 4  per-thread combination to six sums, warp-shuffle + cross-warp reduction, 128-byte scratch row
+// ---------------------------------------------------------------------------------------------------------
+template <int NWARP>
+struct GsmLeanShared {
+    GsmTreeConsts K;
+    uint64_t mbar;
+    int32_t root, nroot, bad;
+    double log_shape;
+    double red[6][NWARP];
+    int32_t redi[7][NWARP];
+    uint32_t redu[4][NWARP];
+};
+
+static __device__ __forceinline__ void lean_redo(int32_t* __restrict__ redo_count, int32_t* __restrict__ redo_list,
+                                                 GsmLeanRow* __restrict__ rows, int64_t t) {
+    const int32_t k = atomicAdd(redo_count, 1);
+    redo_list[k] = static_cast<int32_t>(t);
+    rows[t].status = 0;
+}
+
+// commons-math Lanczos logGamma with the 14 quotients evaluated independently (same summation order as
+// gsm_log_gamma / the Java loop, so the same value; the divisions overlap instead of forming one chain)
+static __device__ double lean_log_gamma(double x) {
+    if (!(x > 0.0)) return NAN;
+    double q[15];
+#pragma unroll
+    for (int i = 14; i > 0; --i) q[i] = gsm_lanczos_d[i] / (x + i);
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 14; i > 0; --i) sum = sum + q[i];
+    sum = sum + gsm_lanczos_d[0];
+    const double tmp = x + 607.0 / 128.0 + .5;
+    return ((x + .5) * log(tmp)) - tmp + 0.91893853320467274178 + log(sum / x);   // libdevice: no table fetch from L2
+}
+
+// a_h / a_aux / a_w: shared-window addresses of the height row, the aux row and the packed words
+template <int LT, int NT>   // NT = worker threads of this phase
+static __device__ __forceinline__ bool lean_pass_a(const GsmLeanC& c, GsmLeanAccA& SA, int n, int tid, uint32_t a_h, uint32_t a_aux,
+                                                   uint32_t a_w) {
+    bool anyda = false;
+    const int npa = (n + 1) >> 1;
+#pragma unroll 1
+    for (int j = tid; j < npa; j += NT) {
+        const int i0 = 2 * j;
+        double2 h2 = lds_v2f64(a_h + j * 16);
+        if (i0 + 1 >= n) h2.y = h2.x;   // padding slot of the last pair
+        double e0, G0, e1, G1;
+        const double a0 = gsm_lean_aux(c, SA, h2.x, e0, G0);
+        const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
+        sts_v2f64(a_aux + j * 16, a0, a1);
+        if (i0 < c.L) {   // leaves: Node.isDirectAncestor -> parent isFake; extinct-leaf terms
+            const uint32_t w2 = lds_u32(a_w + j * 4);
+            const uint32_t p0 = w2 & 0x7fffu;
+            const bool da0 = lds_f64(a_h + p0 * 8) == h2.x;
+            if (da0) {
+                sts_u16(a_w + p0 * 2, lds_u16(a_w + p0 * 2) | 0x8000u);
+                anyda = true;
+            }
+            gsm_lean_leaf_term<LT>(c, SA, !da0, h2.x, a0, e0, G0);
+            if (i0 + 1 < c.L) {
+                const uint32_t p1 = (w2 >> 16) & 0x7fffu;
+                const bool da1 = lds_f64(a_h + p1 * 8) == h2.y;
+                if (da1) {
+                    sts_u16(a_w + p1 * 2, lds_u16(a_w + p1 * 2) | 0x8000u);
+                    anyda = true;
+                }
+                gsm_lean_leaf_term<LT>(c, SA, !da1, h2.y, a1, e1, G1);
+            }
+        }
+    }
+    return anyda;
+}
+
+template <bool GENERAL, bool WANT_RATES, int BLOCK>
+static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, const GsmBatch& b, int64_t row, int n,
+                                                   int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
+                                                   double* __restrict__ out_rates, double* __restrict__ out_wspikes) {
+    const double2* rate2 = reinterpret_cast<const double2*>(b.rate + row);
+    const double2* spike2 = reinterpret_cast<const double2*>(b.spike + row);
+    const int2* nst2 = c.use_counts ? reinterpret_cast<const int2*>(b.nstubs + row) : nullptr;
+    double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
+    double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
+    const int npairs = (n - 1) >> 1;   // main loop: nodes 0 .. n-2 (n is odd)
+
+    auto body = [&](int j, const double2& rr, const double2& ss, const int2& kk) {
+        const double2 h2 = lds_v2f64(a_h + j * 16);
+        const double2 a2 = lds_v2f64(a_aux + j * 16);
+        const uint32_t w2 = lds_u32(a_w + j * 4);
+        const uint32_t w0 = w2 & 0xffffu, w1 = w2 >> 16;
+        const uint32_t p0 = w0 & 0x7fffu, p1 = w1 & 0x7fffu;
+        const double hp0 = lds_f64(a_h + p0 * 8), hp1 = lds_f64(a_h + p1 * 8);
+        const double ap0 = lds_f64(a_aux + p0 * 8), ap1 = lds_f64(a_aux + p1 * 8);
+        uint32_t wp0 = 0u, wp1 = 0u;
+        if (GENERAL) {
+            wp0 = lds_u16(a_w + p0 * 2);
+            wp1 = lds_u16(a_w + p1 * 2);
+        }
+        double er[2], ew[2];
+        gsm_lean_b_node<GENERAL, WANT_RATES>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
+        gsm_lean_b_node<GENERAL, WANT_RATES>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1], &ew[1]);
+        if (WANT_RATES) {
+            if (orate2) orate2[j] = make_double2(er[0], er[1]);
+            if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
+        }
+    };
+    auto fetch = [&](int j, double2& rr, double2& ss, int2& kk) {
+        if (j < npairs) {
+            rr = ld_stream(rate2 + j);
+            ss = ld_stream(spike2 + j);
+            if (nst2) kk = ld_stream(nst2 + j);
+        }
+    };
+    // two register sets in ping-pong: the strip after the current one is always in flight
+    double2 rA = make_double2(1.0, 1.0), sA = rA, rB = rA, sB = rA;
+    int2 kA = make_int2(-1, -1), kB = kA;   // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
+    int j = tid;
+    fetch(j, rA, sA, kA);
+#pragma unroll 1
+    while (j < npairs) {
+        fetch(j + BLOCK, rB, sB, kB);
+        body(j, rA, sA, kA);
+        j += BLOCK;
+        if (j >= npairs) break;
+        fetch(j + BLOCK, rA, sA, kA);
+        body(j, rB, sB, kB);
+        j += BLOCK;
+    }
+}
+
+template <int BLOCK, int MINB, bool WANT_RATES>
+__global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b, GsmLeanRow* __restrict__ rows,
+                                                               int32_t* __restrict__ redo_count,
+                                                               int32_t* __restrict__ redo_count_next,
+                                                               int32_t* __restrict__ redo_list, double* __restrict__ out_rates,
+                                                               double* __restrict__ out_wspikes) {
     constexpr int NWARP = BLOCK / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int64_t S = b.stride;
+    __shared__ GsmLeanShared<NWARP> sh;
+    const int S = static_cast<int>(b.stride);
     double* sh_h = reinterpret_cast<double*>(smem_raw);
     double* sh_aux = sh_h + S;
-    WORD* sh_w = reinterpret_cast<WORD*>(sh_aux + S);
-
-    __shared__ GsmLogEntry sh_logtab[GSM_LOG_TAB_N];
-    __shared__ uint64_t sh_exptab[GSM_EXP_TAB_N];
-    __shared__ GsmTreeConsts K;
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ int32_t sh_root;
-    __shared__ int32_t sh_anyzero;
-    __shared__ double sh_red[6][NWARP];
-    __shared__ int32_t sh_redi[5][NWARP];
+    uint16_t* sh_w = reinterpret_cast<uint16_t*>(sh_aux + S);
+    GsmLeanBlob* sh_blob = reinterpret_cast<GsmLeanBlob*>(smem_raw + static_cast<size_t>(S) * 18u);
+    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_blob + 1);
+    GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int64_t t = blockIdx.x;
+    if (t == 0 && tid == 0) *redo_count_next = 0;   // counter of the next evaluation on this handle (ping-pong)
     int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
     if (n > b.n_nodes) n = b.n_nodes;
-    double* orow = out_tree + t * GSM_NOUT;
-    if (n <= 0) {
-        if (tid < GSM_NOUT) orow[tid] = NAN;
+    if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) {   // not a binary BEAST tree the lean path covers
+        if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
     const int64_t row = t * S;
+    const int L = (n + 1) >> 1;
 
     // ---- phase 0 ----
     if (tid == 0) {
-        mbar_init(&mbar, 1);
+        mbar_init(&sh.mbar, 1);
         fence_mbar_init();
-        sh_root = -1;
-        sh_anyzero = 0;
+        sh.root = -1;
+        sh.nroot = 0;
+        sh.bad = 0;
     }
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
-        mbar_arrive_expect_tx(&mbar, bytes_h);
-        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &mbar);
+        const uint32_t bytes_p = (static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
+        mbar_arrive_expect_tx(&sh.mbar, bytes_h + bytes_p + static_cast<uint32_t>(sizeof(GsmLeanBlob)));
+        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &sh.mbar);
+        tma_bulk_g2s(sh_aux, b.parent + row, bytes_p, &sh.mbar);   // landing zone; repacked in phase 1
+        tma_bulk_g2s(sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
     }
-    for (int i = tid; i < GSM_LOG_TAB_N; i += BLOCK) {   // log / exp tables -> shared memory (3 KB, L2-resident source)
-        const double2 e = gsm_log_tab_d[i];
-        sh_logtab[i].invc = e.x;
-        sh_logtab[i].logc = e.y;
-        sh_exptab[i] = gsm_exp_tab_d[i];
+    // The last warp is the setup warp: per-tree constants now, the Gamma table while the others repack and run pass A.
+    constexpr int NWORK = BLOCK - 32;
+    const bool setup_warp = warp == NWARP - 1;
+    const double* prm = b.params + t * GSM_NPARAM;
+    if (setup_warp && lane == 0)
+        gsm_setup_scalars(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
+    __syncthreads();
+    mbar_wait(&sh.mbar, 0);   // also before any early exit: the bulk copies target this CTA's shared memory
+    if (!gsm_lean_consts_ok(K)) {   // invalid state (lambda <= mu, shape <= 0, ...): the generic path reproduces the reference
+        if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
+        return;
     }
-    {
-        const int32_t* prow = b.parent + row;
-        for (int i = tid; i < n; i += BLOCK) {
-            int32_t p = ld_stream(prow + i);
-            if (static_cast<uint32_t>(p) >= static_cast<uint32_t>(n)) {   // root (-1) or out of range: points to itself
-                if (p < 0) sh_root = i;
-                p = i;
-            }
-            sh_w[i] = static_cast<WORD>(p);
-        }
-    }
-    if (warp == NWARP - 1) {
-        const double* prm = b.params + t * GSM_NPARAM;
+    const uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w);
+    if (setup_warp) {
+        // {shape m - 1, log shape - logGamma(shape m)}, m = lane + 1 (BSP:97-99 with the Lanczos logGamma of commons-math)
+        const double shape = K.shape;
+        const double lsh = log(shape);
+        if (lane == 1) sh.log_shape = lsh;
+        const int m = lane + 1;
+        GsmLogEntry e;
+        e.invc = shape * m - 1;
+        e.logc = lsh - lean_log_gamma(shape * m);
+        sh_mtab[m] = e;
         if (lane == 0) {
-            gsm_setup_consts(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
-        } else if (lane <= GSM_LUT_M + 1) {
-            gsm_lut_entry(K, prm[GSM_P_SPIKE_SHAPE], lane - 1);
+            e.invc = -1.0;
+            e.logc = 0.0;
+            sh_mtab[0] = e;
         }
-    }
-    __syncthreads();
-    mbar_wait(&mbar, 0);
-
-    // ---- phase 1: non-leaf marks; note whether any branch has zero length (only then can there be sampled ancestors) ----
-    for (int i = tid; i < n; i += BLOCK) {
-        const int p = static_cast<int>(sh_w[i] & W::IDX);
-        if (p != i) {
-            sh_w[p] = static_cast<WORD>(sh_w[p] | W::NL);
-            if (sh_h[p] == sh_h[i]) sh_anyzero = 1;
-        }
-    }
-    __syncthreads();
-    // ---- phase 1b: sampled ancestors -> fake parents ----
-    if (sh_anyzero) {
-        for (int i = tid; i < n; i += BLOCK) {
-            const uint32_t w = sh_w[i];
-            const int p = static_cast<int>(w & W::IDX);
-            if (!(w & W::NL) && p != i && sh_h[p] == sh_h[i]) sh_w[p] = static_cast<WORD>(sh_w[p] | W::FAKE);
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 2: pass A ----
-    GsmAcc A;
-    gsm_acc_zero(A);
-    GsmFastA fa;
-    GsmFastB fb;
-    gsm_fast_consts(K, fa, fb, n);
-    GsmTabs T;
-    T.logtab = sh_logtab;
-    T.exptab = sh_exptab;
-    switch (fa.variant) {
-        case GSM_TV_COMPLETE_RHO: fast_pass_a_loop<WORD, GSM_TV_COMPLETE_RHO, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
-        case GSM_TV_NO_PSI: fast_pass_a_loop<WORD, GSM_TV_NO_PSI, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
-        case GSM_TV_PSI: fast_pass_a_loop<WORD, GSM_TV_PSI, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
-        case GSM_TV_CONDITIONED: fast_pass_a_loop<WORD, GSM_TV_CONDITIONED, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
-        default: fast_pass_a_loop<WORD, GSM_TV_NONE, BLOCK>(fa, T, A, n, tid, sh_h, sh_aux, sh_w); break;
-    }
-    __syncthreads();
-
-    // ---- phase 3: pass B, two adjacent nodes per thread ----
-    {
-        const double* rate_row = b.rate + row;
-        const double* spike_row = b.spike + row;
-        const int32_t* nst_row = b.nstubs ? b.nstubs + row : nullptr;
-        const double2* rate2 = reinterpret_cast<const double2*>(rate_row);
-        const double2* spike2 = reinterpret_cast<const double2*>(spike_row);
-        const int2* nst2 = reinterpret_cast<const int2*>(nst_row);
-        double* orate = (WANT_RATES && out_rates) ? out_rates + row : nullptr;
-        double* owsp = (WANT_RATES && out_wspikes) ? out_wspikes + row : nullptr;
-        double dummy[2];
-        const int nfull = n >> 1;
-        int j = tid;
-        double2 r_n = make_double2(1.0, 1.0), s_n = make_double2(1.0, 1.0);
-        int2 k_n = make_int2(0, 0);
-        if (j < nfull) {
-            r_n = ld_stream(rate2 + j);
-            s_n = ld_stream(spike2 + j);
-            if (nst2) k_n = ld_stream(nst2 + j);
-        }
-        while (j < nfull) {
-            const double rate[2] = {r_n.x, r_n.y}, spike[2] = {s_n.x, s_n.y};
-            const int32_t nst_raw[2] = {k_n.x, k_n.y};
-            const int jn = j + BLOCK;
-            if (jn < nfull) {  // prefetch the next strip
-                r_n = ld_stream(rate2 + jn);
-                s_n = ld_stream(spike2 + jn);
-                if (nst2) k_n = ld_stream(nst2 + jn);
-            }
-            const int i0 = 2 * j;
-            const double2 h2 = *reinterpret_cast<const double2*>(sh_h + i0);
-            const double2 a2 = *reinterpret_cast<const double2*>(sh_aux + i0);
-            const double h[2] = {h2.x, h2.y}, aux[2] = {a2.x, a2.y};
-            bool da[2], pf[2], root[2];
-            double hp[2], auxp[2], len[2], dA[2], E[2];
-            bool sp = false;
+    } else {
+        // ---- phase 1: parents -> packed words; BEAST numbering check ----
+        uint32_t over = 0u;   // max of (p - L) as unsigned: >= n - L means a parent index outside [L, n)
+        const uint32_t nL = static_cast<uint32_t>(n - L);
+        bool bad = false;
+        for (int c8 = tid; c8 * 8 < n; c8 += NWORK) {
+            const int4 qa = lds_v4s32(a_aux + c8 * 32), qb = lds_v4s32(a_aux + c8 * 32 + 16);
+            int pv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            if (((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) < 0) || c8 * 8 + 8 > n) {
+                // chunk holds the root (-1) or runs past the last node: element by element
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const uint32_t w = sh_w[i0 + k];
-                const int p = static_cast<int>(w & W::IDX);
-                da[k] = (w & W::DA) != 0;
-                pf[k] = (w & W::PF) != 0;
-                root[k] = (p == i0 + k);
-                hp[k] = sh_h[p];
-                auxp[k] = sh_aux[p];
-                len[k] = hp[k] - h[k];                                      // a root points to itself: len == 0
-                dA[k] = aux[k] - auxp[k];
-                E[k] = fma(len[k], fb.kE, 2 * dA[k]);                       // STP:749-769 via aux
-                sp = sp || gsm_fast_b_special(fb, i0 + k, da[k], pf[k], root[k], len[k], E[k], rate[k], spike[k], nst_raw[k]);
+                for (int k = 0; k < 8; k++) {
+                    const int i = c8 * 8 + k;
+                    if (i >= n) pv[k] = L;
+                    else if (pv[k] < 0) {   // root: points to itself; must be an internal node
+                        sh.root = i;
+                        atomicAdd(&sh.nroot, 1);
+                        pv[k] = i;
+                        bad = bad || (i < L);
+                    }
+                }
             }
-            if (__any_sync(__activemask(), sp)) {
 #pragma unroll
-                for (int k = 0; k < 2; k++)
-                    gsm_fast_pass_b_checked<WANT_RATES>(fb, K, T, g_logfact, A, i0 + k, da[k], pf[k], root[k], h[k], hp[k], aux[k],
-                                                        auxp[k], rate[k], spike[k], nst_raw[k], orate ? orate + i0 + k : dummy,
-                                                        owsp ? owsp + i0 + k : dummy);
-            } else {
-                gsm_fast_pass_b_pair<WANT_RATES>(fb, K, T, g_logfact, A, i0, da, pf, root, len, E, dA, rate, spike, nst_raw,
-                                                 orate ? orate + i0 : dummy, owsp ? owsp + i0 : dummy);
-            }
-            j = jn;
+            for (int k = 0; k < 8; k++) over = gsm_umax(over, static_cast<uint32_t>(pv[k] - L));
+            sts_v4u32(a_w + c8 * 16, __byte_perm(pv[0], pv[1], 0x5410), __byte_perm(pv[2], pv[3], 0x5410),
+                      __byte_perm(pv[4], pv[5], 0x5410), __byte_perm(pv[6], pv[7], 0x5410));
         }
-        if ((n & 1) && tid == (nfull % BLOCK)) {   // odd last node
-            const int i = n - 1;
-            const uint32_t w = sh_w[i];
-            const int p = static_cast<int>(w & W::IDX);
-            gsm_fast_pass_b_checked<WANT_RATES>(fb, K, T, g_logfact, A, i, (w & W::DA) != 0, (w & W::PF) != 0, p == i, sh_h[i], sh_h[p],
-                                                sh_aux[i], sh_aux[p], __ldg(rate_row + i), __ldg(spike_row + i),
-                                                nst_row ? __ldg(nst_row + i) : 0, orate ? orate + i : dummy, owsp ? owsp + i : dummy);
-        }
+        if (bad || over >= nL) sh.bad = 1;
+        // the repack reads the landing zone of the parent row, which pass A overwrites with aux: workers only
+        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
     }
 
-    // ---- phase 4: reductions (fixed order) + epilogue ----
-    double v0 = warp_sum(A.tree), v1 = warp_sum(A.stub), v2 = warp_sum(A.spike), v3 = warp_sum(A.rate),
-           v4 = warp_sum(A.burst), v5 = warp_sum(A.dist);
-    int32_t c0 = __reduce_add_sync(0xffffffffu, A.n_extant), c1 = __reduce_add_sync(0xffffffffu, A.n_leaf),
-            c2 = __reduce_add_sync(0xffffffffu, A.n_da), c3 = __reduce_add_sync(0xffffffffu, A.n_extinct),
-            c4 = static_cast<int32_t>(__reduce_or_sync(0xffffffffu, static_cast<uint32_t>(A.bad)));
+    // ---- phase 2: pass A (workers) ----
+    GsmLeanC c;
+    gsm_lean_consts(K, c, n);
+    c.logtab = sh_blob->logtab;
+    c.exptab = sh_blob->exptab;
+    c.stubtab = sh_blob->stubtab;
+    c.mtab = sh_mtab;
+    c.logfact = g_logfact;
+    GsmLeanAccA SA;
+    gsm_lean_acc_a_zero(SA);
+    bool anyda = false;
+    if (!setup_warp && !sh.bad && sh.nroot == 1) {   // (a malformed tree is handed back right after the barrier)
+        if (c.leaf_term == 0) anyda = lean_pass_a<0, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
+        else if (c.leaf_term == 1) anyda = lean_pass_a<1, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
+        else anyda = lean_pass_a<2, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
+    }
+    const bool any = __syncthreads_or(anyda ? 1 : 0) != 0;
+    if (sh.bad || sh.nroot != 1) {
+        if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
+        return;
+    }
+    c.log_shape = sh.log_shape;
+    const int root = sh.root;
+    const bool general = any || root != n - 1;
+
+    // ---- phase 3: pass B ----
+    GsmLeanAccB SB;
+    gsm_lean_acc_b_zero(SB);
+    GsmLean6 s6;
+    if (general) {
+        lean_pass_b<true, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, out_rates, out_wspikes);
+    } else {
+        lean_pass_b<false, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, out_rates, out_wspikes);
+    }
+    // node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree): GENERAL flavour, own accumulator
+    GsmLeanAccB ST;
+    gsm_lean_acc_b_zero(ST);
+    if (tid == BLOCK - 1) {
+        const int i = n - 1;
+        const uint32_t w = sh_w[i];
+        const int p = static_cast<int>(w & 0x7fffu);
+        const int32_t nst = (b.stub_mode == GSM_STUBS_EXACT && b.nstubs) ? __ldg(b.nstubs + row + i) : 0;
+        double er, ew;
+        gsm_lean_b_node<true, WANT_RATES>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p], __ldg(b.rate + row + i),
+                                          __ldg(b.spike + row + i), nst, &er, &ew);
+        if (WANT_RATES) {
+            if (out_rates) out_rates[row + i] = er;
+            if (out_wspikes) out_wspikes[row + i] = ew;
+        }
+    }
+    if (general) {
+        SB.gam += ST.gam; SB.spk += ST.spk; SB.spk_el += ST.spk_el; SB.lr += ST.lr; SB.lr2 += ST.lr2; SB.stub += ST.stub;
+        SB.nlf += ST.nlf; SB.len += ST.len; SB.dA += ST.dA; SB.lenr += ST.lenr; SB.auxint += ST.auxint; SB.hint += ST.hint;
+        SB.auxfake += ST.auxfake; SB.hfake += ST.hfake;
+        gsm_lean_combine<true>(K, c, SA, SB, s6);
+    } else {
+        gsm_lean_combine<false>(K, c, SA, SB, s6);
+        GsmLean6 t6;
+        GsmLeanAccA SA0;
+        gsm_lean_acc_a_zero(SA0);
+        gsm_lean_combine<true>(K, c, SA0, ST, t6);
+        s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
+    }
+
+    // ---- phase 4: reductions (fixed order) ----
+    const double v0 = warp_sum(s6.tree), v1 = warp_sum(s6.stub), v2 = warp_sum(s6.spike), v3 = warp_sum(s6.rate),
+                 v4 = warp_sum(s6.burst), v5 = warp_sum(s6.dist);
+    const int32_t c0 = __reduce_add_sync(0xffffffffu, SB.n_nst + ST.n_nst), c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm),
+                  c2 = __reduce_add_sync(0xffffffffu, SA.n_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + ST.n_fake),
+                  c4 = __reduce_add_sync(0xffffffffu, SB.n_extant), c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct),
+                  c6 = __reduce_add_sync(0xffffffffu, SB.n_da);
+    const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk)),
+                   u1 = warp_max_u32(gsm_umax(SB.chk_n, ST.chk_n)), u2 = warp_max_u32(SB.chk_len), u3 = warp_max_u32(SA.hmax);
     if (lane == 0) {
-        sh_red[0][warp] = v0; sh_red[1][warp] = v1; sh_red[2][warp] = v2;
-        sh_red[3][warp] = v3; sh_red[4][warp] = v4; sh_red[5][warp] = v5;
-        sh_redi[0][warp] = c0; sh_redi[1][warp] = c1; sh_redi[2][warp] = c2; sh_redi[3][warp] = c3; sh_redi[4][warp] = c4;
+        sh.red[0][warp] = v0; sh.red[1][warp] = v1; sh.red[2][warp] = v2;
+        sh.red[3][warp] = v3; sh.red[4][warp] = v4; sh.red[5][warp] = v5;
+        sh.redi[0][warp] = c0; sh.redi[1][warp] = c1; sh.redi[2][warp] = c2; sh.redi[3][warp] = c3;
+        sh.redi[4][warp] = c4; sh.redi[5][warp] = c5; sh.redi[6][warp] = c6;
+        sh.redu[0][warp] = u0; sh.redu[1][warp] = u1; sh.redu[2][warp] = u2; sh.redu[3][warp] = u3;
     }
     __syncthreads();
-    if (tid == 0) {
-        GsmAcc R;
-        gsm_acc_zero(R);
+    if (warp == 0) {
+        // lanes 0..5 sum one double each over the warps (fixed order); lanes 8..14 the integers; lanes 16..19 the maxima
+        double dv = 0.0;
+        int32_t iv = 0;
+        uint32_t uv = 0u;
+        if (lane < 6) {
 #pragma unroll
-        for (int w = 0; w < NWARP; w++) {
-            R.tree += sh_red[0][w]; R.stub += sh_red[1][w]; R.spike += sh_red[2][w];
-            R.rate += sh_red[3][w]; R.burst += sh_red[4][w]; R.dist += sh_red[5][w];
-            R.n_extant += sh_redi[0][w]; R.n_leaf += sh_redi[1][w]; R.n_da += sh_redi[2][w];
-            R.n_extinct += sh_redi[3][w]; R.bad |= sh_redi[4][w];
+            for (int w = 0; w < NWARP; w++) dv += sh.red[lane][w];
+        } else if (lane >= 8 && lane < 15) {
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) iv += sh.redi[lane - 8][w];
+        } else if (lane >= 16 && lane < 20) {
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) uv = gsm_umax(uv, sh.redu[lane - 16][w]);
         }
-        const int32_t root = sh_root;
-        double res[GSM_NOUT];
-        if (root < 0) {
-#pragma unroll
-            for (int k = 0; k < GSM_NOUT; k++) res[k] = NAN;
+        const uint32_t chk = __shfl_sync(0xffffffffu, uv, 16), chk_n = __shfl_sync(0xffffffffu, uv, 17),
+                       chk_len = __shfl_sync(0xffffffffu, uv, 18), hmax = __shfl_sync(0xffffffffu, uv, 19);
+        bool bad = chk >= GSM_CHK_LIMIT || chk_n != 0u ||
+                   (!general && chk_len >= GSM_CHK_LIMIT) || hmax >= 0x7ff00000u;
+        if (!bad) bad = !(K.c1 * __hiloint2double(static_cast<int>(hmax) + 1, 0) < 700.0);   // exp(-c1 h) stays in range
+        if (bad) {
+            if (lane == 0) lean_redo(redo_count, redo_list, rows, t);
         } else {
-            gsm_fast_fix_acc(K, R, n);
-            gsm_finish_consts(K, sh_h[root]);
-            gsm_finalize(K, R, n, (sh_w[root] & W::FAKE) != 0, res);
+            GsmLeanRow* r = rows + t;
+            double* rd = reinterpret_cast<double*>(r);
+            int32_t* ri = reinterpret_cast<int32_t*>(rd + 7);
+            if (lane < 6) rd[lane] = dv;
+            else if (lane == 6) rd[6] = sh_h[root];
+            else if (lane >= 8 && lane < 15) {
+                // redi order: n_nst, n_leafterm, n_plain, n_fake, n_extant, n_extinct, n_da  == row order
+                ri[lane - 8] = iv;
+            } else if (lane == 15) {
+                ri[7] = (sh_w[root] & 0x8000u) ? 1 : 0;
+                ri[8] = 1;
+            }
         }
-#pragma unroll
-        for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
     }
 }
 
@@ -617,95 +824,147 @@ cudaError_t gsm_init_tables() {
         s += log(static_cast<double>(i));
         h[i] = s;
     }
-    return cudaMemcpyToSymbol(g_logfact, h, sizeof(h));
+    cudaError_t e = cudaMemcpyToSymbol(g_logfact, h, sizeof(h));
+    if (e != cudaSuccess) return e;
+    GsmLogEntry st[GSM_LEAN_MAX_NST + 1];
+    for (int i = 0; i <= GSM_LEAN_MAX_NST; i++) {
+        st[i].invc = static_cast<double>(i);
+        st[i].logc = -h[i];
+    }
+    return cudaMemcpyToSymbol(g_lean_blob, st, sizeof(st), offsetof(GsmLeanBlob, stubtab));
 }
 
-static size_t eval_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
+size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
+
+static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
+static size_t lean_smem_bytes(int64_t stride) {
+    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + GSM_LEAN_MTAB_N * sizeof(GsmLogEntry);
+}
+
+template <typename KERN>
+static cudaError_t prep(KERN kern, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_block(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
-    const size_t smem = eval_smem_bytes(b.stride);
+static cudaError_t launch_generic(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
+    const size_t smem = generic_smem_bytes(b.stride);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     cudaError_t e;
     if (r || w) {
         auto kern = gsm_eval_kernel<BLOCK, MINB, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     } else {
         auto kern = gsm_eval_kernel<BLOCK, MINB, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     }
     return cudaGetLastError();
 }
 
-template <typename WORD, int BLOCK, int MINB>
-static cudaError_t launch_fast(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(b.stride) * (16u + sizeof(WORD));
+template <int BLOCK, int MINB>
+static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
+    const size_t smem = lean_smem_bytes(b.stride);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
+    GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
+    int32_t* cnt = sc.redo + (sc.epoch & 1);
+    int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
+    int32_t* list = sc.redo + 4;
     cudaError_t e;
     if (r || w) {
-        auto kern = gsm_eval_fast_kernel<WORD, BLOCK, MINB, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        auto kern = gsm_lean_kernel<BLOCK, MINB, true>;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     } else {
-        auto kern = gsm_eval_fast_kernel<WORD, BLOCK, MINB, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        auto kern = gsm_lean_kernel<BLOCK, MINB, false>;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     }
     return cudaGetLastError();
 }
 
-// Launch configuration: one CTA per tree.  The shared-memory footprint per node (18-22 B) bounds the number of
-// resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in
+template <int BLOCK, int MINB>
+static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* o, double* r, double* w, int sm_count,
+                               cudaStream_t st) {
+    const size_t smem = generic_smem_bytes(b.stride);
+    int64_t g = (b.n_trees + BLOCK - 1) / BLOCK;
+    const int64_t cap = static_cast<int64_t>(sm_count) * MINB;
+    if (g < cap) g = b.n_trees < cap ? b.n_trees : cap;   // enough CTAs for the redo list when the batch is small
+    if (g > 4 * cap) g = 4 * cap;
+    if (g < 1) g = 1;
+    const dim3 grid(static_cast<unsigned>(g));
+    const GsmLeanRow* rows = reinterpret_cast<const GsmLeanRow*>(sc.rows);
+    const int32_t* cnt = sc.redo + (sc.epoch & 1);
+    const int32_t* list = sc.redo + 4;
+    cudaError_t e;
+    if (r || w) {
+        auto kern = gsm_post_kernel<BLOCK, MINB, true>;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, list, o, r, w);
+    } else {
+        auto kern = gsm_post_kernel<BLOCK, MINB, false>;
+        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, list, o, r, w);
+    }
+    return cudaGetLastError();
+}
+
+static int g_sm_count = 0;
+
+// Launch configuration: one CTA per tree.  The shared-memory footprint per node (18 B lean, 22 B generic) bounds
+// the number of resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in
 // profiles/.  GSM_BLOCK / GSM_MINB / GSM_GENERIC override the choice for tuning runs.
-int gsm_launch_eval(const GsmBatch& b, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
+int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                     cudaStream_t stream) {
     if (b.n_trees <= 0) return 0;
-    const bool fast = gsm_fast_path_ok(b.flags, b.stub_mode) && b.rate != nullptr && !getenv("GSM_GENERIC");
-    int block, minb;
-    if (fast) {
-        block = b.n_nodes <= 512 ? 128 : 256;
-        minb = b.n_nodes <= 512 ? 6 : 3;
-    } else {
-        block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
-        minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_sm_count = n > 0 ? n : 148;
     }
-    if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
-    if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(b.rate) | reinterpret_cast<uintptr_t>(b.spike) |
+                           reinterpret_cast<uintptr_t>(b.nstubs) | reinterpret_cast<uintptr_t>(b.height) |
+                           reinterpret_cast<uintptr_t>(b.parent)) & 15u) == 0 && (b.stride % 32) == 0;
+    const bool lean = gsm_lean_wiring_ok(b.flags, b.stub_mode) && b.rate != nullptr && sc.rows != nullptr && sc.redo != nullptr &&
+                      aligned && (b.stub_mode == GSM_STUBS_NOSTUB || b.nstubs != nullptr) && !getenv("GSM_GENERIC");
     cudaError_t e = cudaErrorInvalidConfiguration;
-    if (fast) {
-        const bool w16 = b.n_nodes <= 4096;
-#define GSM_CFG(B, M)                                                                                      \
-    if (block == B && minb == M)                                                                           \
-        e = w16 ? launch_fast<uint16_t, B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream)           \
-                : launch_fast<uint32_t, B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
-        GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
-        GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
-        GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
-#undef GSM_CFG
-    } else {
+    int launches = 0;
+    if (lean) {
+        int block = b.n_nodes <= 512 ? 128 : 256;
+        int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2800 ? 3 : 2);
+        if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
+        if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
 #define GSM_CFG(B, M) \
-    if (block == B && minb == M) e = launch_block<B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
+    if (block == B && minb == M) e = launch_lean<B, M>(b, sc, d_out_rates, d_out_wspikes, stream);
         GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
         GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
         GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
 #undef GSM_CFG
+        if (e != cudaSuccess) return -static_cast<int>(e);
+        if (b.n_nodes <= 2048) e = launch_post<256, 3>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);
+        else e = launch_post<384, 2>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);
+        if (e != cudaSuccess) return -static_cast<int>(e);
+        sc.epoch++;
+        launches = 2;
+    } else {
+        int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
+        int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
+        if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
+        if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
+#define GSM_CFG(B, M) \
+    if (block == B && minb == M) e = launch_generic<B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
+        GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
+        GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
+        GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
+#undef GSM_CFG
+        if (e != cudaSuccess) return -static_cast<int>(e);
+        launches = 1;
     }
-    if (e != cudaSuccess) return -static_cast<int>(e);
-    return 1;
+    return launches;
 }
 
 int gsm_launch_stub_cdf(const GsmBatch& b, int64_t tree, int32_t node, double* d_cdf, int32_t cap, int32_t* d_len,

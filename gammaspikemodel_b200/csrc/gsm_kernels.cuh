@@ -24,9 +24,22 @@ struct GsmBatch {
     int32_t stub_mode;
 };
 
+// Device scratch of the lean path, owned by whoever owns the stream the evaluation runs on (one per handle slot):
+//   rows  n_trees * gsm_scratch_row_bytes() bytes — per-tree sums handed from the lean kernel to the post kernel
+//   redo  (n_trees + 4) int32 — [0], [1]: ping-pong counters (zero-initialised once), [4..]: trees the lean kernel
+//         hands back to the generic path
+//   epoch evaluation counter (selects the live counter)
+struct GsmScratch {
+    void* rows = nullptr;
+    int32_t* redo = nullptr;
+    uint32_t epoch = 0;
+};
+size_t gsm_scratch_row_bytes();
+
 // Evaluate the whole batch: one result row per tree, optional per-branch rates / weighted spikes
 // (pitch = stride).  Returns the number of kernels launched (>=1) or a negative cudaError_t.
-int gsm_launch_eval(const GsmBatch& b, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
+// Without scratch (rows == nullptr) every wiring runs the generic kernel.
+int gsm_launch_eval(const GsmBatch& b, GsmScratch& scratch, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                     cudaStream_t stream);
 
 // Fills the device-side sum_{i=2..n} log(i) table of the current device (idempotent).

@@ -1,0 +1,377 @@
+// gsm_lean.cuh — the lean evaluation path: per-node bodies of gsm_lean_kernel (gsm_kernels.cu).
+//
+// The generic functions of gsm_node_math.cuh follow the Java statement by statement and handle every wiring and
+// every special value; they cost ~450 instructions per branch.  This file is the same arithmetic for the default
+// wiring family (rates wired, known-n spike prior, no noSpikeOnDatedTips: gsm_lean_wiring_ok) restructured so that
+// a branch costs ~150 instructions:
+//
+//   * BEAST's node numbering is used instead of rediscovered: leaves are nodes 0..L-1, L = (n+1)/2
+//     (beast.base.evolution.tree.Tree invariant; validated per tree: n odd, every parent index in [L, n)).
+//   * per-branch terms are accumulated as sums of their factors (sum log r, sum log^2 r, sum len, sum dA, ...)
+//     and combined with the per-tree constants once per thread, instead of one fused term per branch;
+//   * log / exp use 512-entry tables staged in shared memory (|r| <= 2^-10: degree-4 polynomials, 8-9 fp64
+//     instructions each, absolute error <= 3e-16);
+//   * no per-branch special-value branches: every value that feeds a log / table lookup is folded into two
+//     unsigned maxima per thread ("chk" words).  A tree whose maxima show anything but positive normal
+//     arguments, stub counts in 0..31, non-negative branch lengths ... is NOT finished here: it is appended to
+//     a redo list and evaluated by the generic kernel (gsm_eval_kernel) in a second launch.  So the reference's
+//     behaviour for -inf / NaN / invalid states is inherited from the generic path, never re-implemented.
+//   * two loop flavours: CLEAN (root is node n-1 and every other branch has positive length — an ordinary
+//     BDWS tree) and GENERAL (sampled ancestors / fake nodes / zero-length branches / root anywhere).
+//
+// Everything is GSM_HD so that tests/emu/gsm_emu.cpp can walk the same code on the host.
+#pragma once
+
+#include "gsm_node_math.cuh"
+
+#define GSM_LEAN_MAX_NST 31      // stub counts handled by the tables of the lean path (0..31)
+#define GSM_LEAN_MTAB_N 33       // m = 0..32 spikes on a branch
+#define GSM_LEAN_MAX_NODES 32767 // parent index is 15 bits of the packed word
+
+// one contiguous block of constant tables; the device copy is brought into shared memory by one TMA bulk copy per CTA
+struct __attribute__((aligned(16))) GsmLeanBlob {
+    GsmLogEntry logtab[GSM_LOG9_TAB_N];       // {invc, logc}
+    uint64_t exptab[GSM_EXP9_TAB_N];          // bits(2^(j/512)) - (j << 43)
+    GsmLogEntry stubtab[GSM_LEAN_MAX_NST + 1];// {(double)n, -sum_{i=2..n} log(i)}  (STP:567 / 633)
+};
+
+GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
+    const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
+    const bool known_n = !stubs_spike || stub_mode != GSM_STUBS_NOSTUB;          // BSP:77
+    return known_n && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
+}
+
+// fp64 constants that do not fit an instruction immediate live in constant memory on the device, so that the hot
+// loops use them as constant-bank operands instead of re-materialising them with moves
+enum { GSM_LK_LN2 = 0, GSM_LK_THIRD, GSM_LK_KBIAS, GSM_LK_INVLN2N, GSM_LK_NLN2HI, GSM_LK_NLN2LO, GSM_LK_SHIFT, GSM_LK_SIXTH,
+       GSM_LK_24TH, GSM_LK_LEAF_EPS, GSM_LK_COND_EPS, GSM_LK_N };
+#define GSM_LK_INIT {GSM_LN2, 1.0 / 3, 4503599627371520.0 /* 2^52 + 1024 */, GSM_EXP9_INVLN2N, GSM_EXP9_NEGLN2HIN, \
+                     GSM_EXP9_NEGLN2LON, 0x1.8p52, 1.0 / 6, 1.0 / 24, GSM_LEAF_EPS, 0.000000000005 /* STP:470 */}
+static const double gsm_lean_k_h[GSM_LK_N] = GSM_LK_INIT;
+#if defined(__CUDACC__)
+static __constant__ double gsm_lean_k_d[GSM_LK_N] = GSM_LK_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GSM_LK(i) gsm_lean_k_d[i]
+#else
+#define GSM_LK(i) gsm_lean_k_h[i]
+#endif
+
+// ---- table-driven log / exp on the 512-entry tables (arguments must be "regular": see the chk words) -------------
+GSM_HD double gsm_log9(double x, const GsmLogEntry* __restrict__ tab) {
+    const int32_t hi = gsm_hi32(x);
+    const int32_t tmp = hi - 0x3fe60000;
+    const int32_t i = (tmp >> 11) & (GSM_LOG9_TAB_N - 1);
+    const int32_t k = tmp >> 20;   // arithmetic
+    const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
+    const GsmLogEntry e = tab[i];
+    const double r = fma(z, e.invc, -1.0);
+    const double kd = gsm_hilo(0x43300000, k + 1024) - GSM_LK(GSM_LK_KBIAS);   // (double)k
+    const double hp = fma(kd, GSM_LK(GSM_LK_LN2), e.logc);
+    const double r2 = r * r;
+    double p = fma(-0.25, r, GSM_LK(GSM_LK_THIRD));
+    p = fma(p, r, -0.5);
+    const double y = fma(p, r2, r);     // log1p(r), |r| <= 2^-10
+    return hp + y;
+}
+
+GSM_HD double gsm_exp9(double x, const uint64_t* __restrict__ tab) {
+    double kd = fma(x, GSM_LK(GSM_LK_INVLN2N), GSM_LK(GSM_LK_SHIFT));
+    const int32_t ki = gsm_lo32(kd);
+    kd -= GSM_LK(GSM_LK_SHIFT);
+    double r = fma(kd, GSM_LK(GSM_LK_NLN2HI), x);
+    r = fma(kd, GSM_LK(GSM_LK_NLN2LO), r);
+    const uint64_t t = tab[ki & (GSM_EXP9_TAB_N - 1)];
+    const double scale = gsm_hilo((int32_t)(t >> 32) + (ki << 11), (int32_t)(t & 0xffffffffu));
+    const double r2 = r * r;
+    double q = fma(GSM_LK(GSM_LK_24TH), r, GSM_LK(GSM_LK_SIXTH));
+    q = fma(q, r, 0.5);
+    const double tmp = fma(q, r2, r);   // expm1(r), |r| <= ln2/1024
+    return fma(scale, tmp, scale);
+}
+
+// "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal finite double
+#define GSM_CHK_LIMIT 0x7fe00000u
+GSM_HD uint32_t gsm_chk_pos(double x) { return (uint32_t)(gsm_hi32(x) - 0x00100000); }
+GSM_HD uint32_t gsm_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// ---- per-tree constants held in registers -----------------------------------------------------------------------
+struct GsmLeanC {
+    // pass A
+    double neg_c1, omc2, opc2, kS, c1, rho;
+    // pass B
+    double kEh;        // (lambda + mu + psi - c1) / 2: E/2 = len * kEh + (aux - aux_parent)   (STP:749-769 via aux)
+    double shape, base, eff_mean;
+    double log_shape;          // only for branches with more than GSM_LEAN_MAX_NST stubs (gsm_lean_big_count)
+    const double* logfact;     // sum_{i=2..n} log(i), n < GSM_LOGFACT_N (same use)
+    const GsmLogEntry* logtab;
+    const uint64_t* exptab;
+    const GsmLogEntry* stubtab;
+    const GsmLogEntry* mtab;   // per tree: {shape*m - 1, log(shape) - logGamma(shape*m)}, m = 0..32
+    int32_t L;                 // leaves are nodes 0..L-1
+    int32_t leaf_term;         // 0: none, 1: psi > 0 (STP:337-343), 2: origin / root conditioned (STP:467-474)
+    bool use_counts;           // stub counts exist (COUNTS / EXACT); else getNStubsOnBranch == -1 (Stubs:348-350)
+    bool s2p, s2c;             // stubs wired to the spike prior (BSP:81) / the clock model (PRCM:192-195)
+    bool stub_term;            // STP:219 && count mode
+    bool use_rate;             // relaxed clock (PRCM:216)
+};
+
+// true when the per-tree constants allow the lean path at all (everything else goes to the generic kernel)
+GSM_HD bool gsm_lean_consts_ok(const GsmTreeConsts& K) {
+    if (K.stp_early || K.spike_invalid || K.rate_invalid) return false;
+    const bool fin = (K.c1 >= 0.0) && (K.c1 < INFINITY) && (K.opc2 > 1e-300) && (K.opc2 < INFINITY) && (K.omc2 > -INFINITY) &&
+                     (K.omc2 < INFINITY) && (K.opc2 + K.omc2 > 1e-300);
+    const bool par = (K.shape > 1e-300) && (K.shape < 1e300) && (K.sigma < 1e150) && (K.base == K.base) &&
+                     (K.spike_mean == K.spike_mean) && (fabs(K.kE) < INFINITY) && (fabs(K.kS) < INFINITY) &&
+                     (K.psi < 700.0);   // exp(psi) overflow makes STP -inf (STP:176-178): generic path
+    return fin && par;
+}
+
+GSM_HD void gsm_lean_consts(const GsmTreeConsts& K, GsmLeanC& c, int32_t n) {
+    c.neg_c1 = -K.c1; c.omc2 = K.omc2; c.opc2 = K.opc2; c.kS = K.kS; c.c1 = K.c1; c.rho = K.rho;
+    c.kEh = 0.5 * K.kE; c.shape = K.shape; c.base = K.base;
+    c.eff_mean = ((K.flags & GSM_F_HAS_INDICATOR) && !K.use_spike) ? 0.0 : K.spike_mean;   // PRCM:181-183
+    c.L = (n + 1) >> 1;
+    c.leaf_term = K.tree_variant == GSM_TV_PSI ? 1 : (K.tree_variant == GSM_TV_CONDITIONED ? 2 : 0);
+    c.use_counts = K.stub_mode != GSM_STUBS_NOSTUB;
+    c.s2p = (K.flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
+    c.s2c = (K.flags & GSM_F_STUBS_TO_CLOCK) != 0;
+    c.stub_term = K.stub_term && K.stub_counts;
+    c.use_rate = !(K.flags & GSM_F_RELAXED_FALSE);
+}
+
+// ---- pass A: aux(h) = log G(h) for every node; extinct-leaf terms of the psi > 0 densities -----------------------
+struct GsmLeanAccA {
+    double leafterm;      // sum over leaves that need it of  log(numer) + c1 h + aux
+    int32_t n_leafterm;   // ... their number (each adds t_leaf)
+    int32_t n_plain;      // origin/root-conditioned: leaves that add log(4 rho) instead (STP:473)
+    uint32_t chk;         // specialness of numer
+    uint32_t hmax;        // max of the high words of the heights (>= 0x7ff00000: negative / inf / NaN)
+};
+GSM_HD void gsm_lean_acc_a_zero(GsmLeanAccA& S) { S.leafterm = 0.0; S.n_leafterm = S.n_plain = 0; S.chk = 0u; S.hmax = 0u; }
+
+// aux of one node.  e_out / G_out feed the leaf term.
+GSM_HD double gsm_lean_aux(const GsmLeanC& c, GsmLeanAccA& S, double h, double& e_out, double& G_out) {
+    S.hmax = gsm_umax(S.hmax, (uint32_t)gsm_hi32(h));
+    const double e = gsm_exp9(c.neg_c1 * h, c.exptab);
+    const double G = fma(c.omc2, e, c.opc2);
+    e_out = e;
+    G_out = G;
+    return gsm_log9(G, c.logtab);
+}
+
+// LT = c.leaf_term (compile-time in the kernel's loops); leaf and not a direct ancestor is decided by the caller
+template <int LT>
+GSM_HD void gsm_lean_leaf_term(const GsmLeanC& c, GsmLeanAccA& S, bool leaf_not_da, double h, double aux, double e, double G) {
+    if (LT == 0) return;
+    bool need;
+    if (LT == 1) need = leaf_not_da && !(h <= GSM_LK(GSM_LK_LEAF_EPS));                       // STP:339
+    else need = leaf_not_da && (h > GSM_LK(GSM_LK_COND_EPS) || c.rho == 0.);                  // STP:470
+    const double numer = c.kS * G - c.c1 * (c.opc2 - e * c.omc2);                             // 2 lambda G p0(h), STP:506-507
+    const double arg = need ? numer : 1.0;
+    S.chk = gsm_umax(S.chk, gsm_chk_pos(arg));
+    const double ln = gsm_log9(arg, c.logtab);
+    if (need) {
+        S.leafterm += ln + fma(c.c1, h, aux);
+        S.n_leafterm++;
+    } else if (LT == 2 && leaf_not_da) {
+        S.n_plain++;
+    }
+}
+
+// ---- pass B -----------------------------------------------------------------------------------------------------
+// A branch with more stubs than the tables hold (rare: long branches near the root): the two table entries are
+// computed on the spot.  On the device the two transcendental parts are out-of-line calls that return their
+// value in registers (no local-memory traffic in the hot loop, which would share a scoreboard with the prefetch).
+#if defined(__CUDACC__)
+static __device__ __noinline__ double gsm_lean_big_lgc_d(double shape, double log_shape, int32_t m) {
+    return log_shape - gsm_log_gamma(shape * m);
+}
+static __device__ __noinline__ double gsm_lean_big_nlf_d(const double* __restrict__ logfact, int32_t nst) {
+    return -gsm_logfact(logfact, nst);
+}
+#endif
+GSM_HD void gsm_lean_big_count(double shape, double log_shape, int32_t m, int32_t nst, const double* __restrict__ logfact,
+                               GsmLogEntry& me, GsmLogEntry& se) {
+    me.invc = shape * m - 1;
+    se.invc = (double)nst;
+#if defined(__CUDA_ARCH__)
+    me.logc = gsm_lean_big_lgc_d(shape, log_shape, m);
+    se.logc = gsm_lean_big_nlf_d(logfact, nst);
+#else
+    me.logc = log_shape - gsm_log_gamma(shape * m);
+    se.logc = -gsm_logfact(logfact, nst);
+#endif
+}
+
+struct GsmLeanAccB {
+    double gam;        // sum  log(x shape) (shape m - 1) + log(shape) - logGamma(shape m)        (BSP:97-99 without - x shape)
+    double spk;        // sum of spikes                                                           (x shape term; burst in CLEAN)
+    double spk_el;     // GENERAL: sum of spikes that count as bursts of eligible branches        (SPL:53-54)
+    double lr, lr2;    // sum log r, sum log^2 r                                                  (BRP:171)
+    double stub;       // sum n_i log(E_i / 2)                                                    (STP:566)
+    double nlf;        // sum -log(n_i!)                                                          (STP:567)
+    double len, dA;    // sum len, sum (aux - aux_parent)
+    double lenr;       // sum len * r                                                             (SPL:44-49 / PRCM:233)
+    double auxint, hint;     // sums over internal nodes of aux, h
+    double auxfake, hfake;   // GENERAL: the same over fake internal nodes
+    int32_t n_nst;     // sum of stub counts
+    int32_t n_extant, n_extinct, n_da, n_fake;
+    uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
+    uint32_t chk_n;    // nonzero when a stub count is negative
+    uint32_t chk_len;  // CLEAN: specialness of len (zero / negative lengths -> rerun as GENERAL)
+};
+GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
+    S.gam = S.spk = S.spk_el = S.lr = S.lr2 = S.stub = S.nlf = S.len = S.dA = S.lenr = 0.0;
+    S.auxint = S.hint = S.auxfake = S.hfake = 0.0;
+    S.n_nst = S.n_extant = S.n_extinct = S.n_da = S.n_fake = 0;
+    S.chk = S.chk_n = S.chk_len = 0u;
+}
+
+// One node i < n-1.  w: own packed word (parent index | FAKE << 15), wp: the parent's word (GENERAL only).
+template <bool GENERAL, bool WANT_RATES>
+GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32_t w, uint32_t wp, double h, double hp,
+                            double aux, double auxp, double rate, double spike, int32_t nst_raw, double* out_rate,
+                            double* out_wspike) {
+    const double len = hp - h;                          // a root points to itself: 0
+    const double dA = aux - auxp;
+    const double E2 = fma(len, c.kEh, dA);              // half the expected stub count (STP:749-769)
+    const bool have_len = len > 0.0;                    // STP:558 / PRCM:229
+    const int32_t nst = c.use_counts ? nst_raw : -1;    // Stubs:344-370 (i < n-1 here)
+    const int32_t ns = c.s2p ? nst : 0;                 // BSP:81
+    const bool leaf = i < c.L;
+    int32_t m = ns + 1;                                 // BSP:197-213
+    bool da = false, pf = false, fake_self = false;
+    if (GENERAL) {
+        const bool root = (int32_t)(w & 0x7fffu) == i;
+        const bool zero = len == 0.0;
+        da = leaf && zero && !root;                                                     // Node.isDirectAncestor
+        pf = ((wp & 0x8000u) != 0) && !root;                                            // parent isFake
+        fake_self = (w & 0x8000u) != 0;
+        m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
+        if (!(have_len || zero)) S.chk = 0xffffffffu;                                   // negative / NaN length
+        if (m == 0 && spike != 0.0) S.chk = 0xffffffffu;                                // BSP:86-95 -> -inf
+        if (c.stub_term && !have_len && nst != 0) S.chk = 0xffffffffu;                  // STP:232-240, 558-561
+    } else {
+        S.chk_len = gsm_umax(S.chk_len, gsm_chk_pos(len));
+    }
+    // table entries of this branch's spike count m and stub count n
+    const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
+    const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
+    GsmLogEntry me = c.mtab[mi];                        // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
+    GsmLogEntry se = c.stubtab[ni];                     // {(double)n, -log(n!)}
+    if (c.use_counts && (uint32_t)nst > (uint32_t)GSM_LEAN_MAX_NST) {   // rare
+        if (nst < 0) S.chk_n = 1u;                      // not a count: generic path
+        else gsm_lean_big_count(c.shape, c.log_shape, m, nst, c.logfact, me, se);
+    }
+
+    // ---- BranchRatePrior BRP:43-60 ----
+    S.chk = gsm_umax(S.chk, gsm_chk_pos(rate));
+    const double lr = gsm_log9(rate, c.logtab);
+    S.lr += lr;
+    S.lr2 = fma(lr, lr, S.lr2);
+
+    // ---- BranchSpikePrior, known stub count: BSP:69-100 ----
+    const double xs = spike * c.shape;
+    const double arg_s = (GENERAL && m == 0) ? 1.0 : xs;
+    S.chk = gsm_umax(S.chk, gsm_chk_pos(arg_s));
+    const double lxs = gsm_log9(arg_s, c.logtab);
+    S.gam += fma(lxs, me.invc, me.logc);
+    S.spk += spike;
+
+    // ---- stub density, count mode: STP:555-571 / 621-637 ----
+    if (c.stub_term) {
+        const uint32_t chkE = gsm_chk_pos(E2);
+        S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
+        const double lE = gsm_log9(E2, c.logtab);       // finite garbage when E2 == 0 (len == 0): multiplied by n = 0
+        S.stub = fma(se.invc, lE, S.stub);
+        S.nlf += se.logc;
+        S.n_nst += nst;
+    }
+    S.len += len;
+    S.dA += dA;
+
+    // ---- clock model: SPL sums, optional per-branch outputs (PRCM:178-242, SPL:33-61) ----
+    const double r = c.use_rate ? rate : 1.0;           // PRCM:210-222
+    S.lenr = fma(len, r, S.lenr);                       // len == 0 for every ineligible branch
+    double bsp = spike;
+    if (GENERAL) {
+        if (pf && (!c.s2c || nst == 0)) bsp = 0.0;      // PRCM:192-202
+        S.spk_el += have_len ? bsp : 0.0;
+    }
+    if (WANT_RATES) {
+        const double burst = bsp * c.eff_mean;          // PRCM:204-206
+        double eff = c.base;
+        if (have_len) eff = (len * c.base * r + burst) / len;   // PRCM:233-236
+        *out_rate = eff;
+        *out_wspike = burst;
+    }
+
+    // ---- census of the leaves (STP:190-195, 291-312, 352-359) / sums over internal nodes ----
+    if (leaf) {
+        const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
+        const bool ext = !low && (len > GSM_LK(GSM_LK_LEAF_EPS));
+        if (GENERAL) {
+            S.n_da += da ? 1 : 0;
+            S.n_extant += (!da && low) ? 1 : 0;
+            S.n_extinct += (!da && ext) ? 1 : 0;
+        } else {
+            S.n_extant += low ? 1 : 0;
+            S.n_extinct += ext ? 1 : 0;
+        }
+    } else {
+        S.auxint += aux;
+        S.hint += h;
+        if (GENERAL && fake_self) {
+            S.auxfake += aux;
+            S.hfake += h;
+            S.n_fake++;
+        }
+    }
+}
+
+// per-thread combination of the factor sums into the six result sums (constants per node are added once per tree
+// by gsm_lean_finish).  spk_el: in CLEAN every main-loop node is eligible.
+struct GsmLean6 { double tree, stub, spike, rate, burst, dist; };
+
+template <bool GENERAL>
+GSM_HD void gsm_lean_combine(const GsmTreeConsts& K, const GsmLeanC& c, const GsmLeanAccA& SA, const GsmLeanAccB& S, GsmLean6& o) {
+    const double aux_nf = S.auxint - (GENERAL ? S.auxfake : 0.0), h_nf = S.hint - (GENERAL ? S.hfake : 0.0);
+    double tree = 0.0;
+    const int32_t variant = K.tree_variant;
+    if (variant == GSM_TV_COMPLETE_RHO) tree = (S.dA - K.lmm * S.len) - S.auxint;            // STP:387-393, 398-426
+    else if (variant == GSM_TV_NO_PSI) tree = -(K.lmm * h_nf) - 2 * aux_nf;                  // STP:371-377
+    else if (variant == GSM_TV_PSI || variant == GSM_TV_CONDITIONED) tree = -(K.c1 * h_nf) - 2 * aux_nf + SA.leafterm;
+    o.tree = tree;
+    o.stub = (S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);                                 // sum n log(E/2) - log n! - E
+    o.spike = S.gam - c.shape * S.spk;
+    o.rate = -K.inv_2s2 * (S.lr2 - 2 * K.m_ln * S.lr) - S.lr;                                // sum -(lr - m)^2/(2 s^2) - lr, without n m^2
+    o.burst = c.eff_mean * (GENERAL ? S.spk_el : S.spk);
+    o.dist = c.base * S.lenr;
+}
+
+// per-tree: add the per-node constants and the tail accumulator (node n-1, evaluated by the generic functions).
+// nb = number of nodes the main loops covered (n-1), of which nb - L internal.
+GSM_HD void gsm_lean_finish(const GsmTreeConsts& K, const GsmLeanC& c, const GsmLean6& r, int32_t n_nst, int32_t n_leafterm,
+                            int32_t n_plain, int32_t n_fake, int32_t nb, GsmAcc& A /* in: tail + census; out: totals */) {
+    const int32_t n_int = nb - c.L;
+    double tree = r.tree;
+    // count * constant, with 0 * (+-inf) = 0: a term that never occurs adds nothing (log psi, log 4 rho can be -inf)
+    auto times = [](int32_t cnt, double k) { return cnt != 0 ? cnt * k : 0.0; };
+    switch (K.tree_variant) {
+        case GSM_TV_COMPLETE_RHO: tree += times(n_int, K.t_internal); break;
+        case GSM_TV_NO_PSI: tree += times(n_int - n_fake, K.t_internal); break;
+        case GSM_TV_PSI: tree += times(n_int - n_fake, K.t_internal) + times(n_leafterm, K.t_leaf); break;
+        case GSM_TV_CONDITIONED:
+            tree += times(n_int - n_fake, K.t_internal) + times(n_leafterm, K.t_leaf) + times(n_plain, K.log_4rho) +
+                    times(n_fake, K.log_psi);
+            break;
+        default: tree = 0.0; break;
+    }
+    A.tree += tree;
+    if (c.stub_term) A.stub += r.stub + n_nst * 0.69314718055994530942;
+    A.spike += r.spike;
+    A.rate += r.rate - nb * (K.inv_2s2 * K.m_ln * K.m_ln + K.log_s_sqrt2pi);
+    A.burst += r.burst;
+    A.dist += r.dist + r.burst;
+}

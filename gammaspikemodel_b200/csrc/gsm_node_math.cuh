@@ -146,8 +146,13 @@ GSM_HD double gsm_gamma_logdens(const GsmTreeConsts& K, int32_t m, double x, dou
 }
 
 // ---- per-tree constants that do not depend on the tree's heights ----
-GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int32_t use_spike, uint32_t flags,
-                             int32_t stub_mode) {
+// Split in three so that the lean kernel can evaluate the transcendental functions on the lanes of one warp:
+//   gsm_setup_scalars  wiring + arithmetic-only constants
+//   gsm_setup_arg(j)   argument of the j-th logarithm (j < GSM_SETUP_NLOG)
+//   gsm_setup_finish   stores the logarithms and everything derived from them
+#define GSM_SETUP_NLOG 9
+GSM_HD void gsm_setup_scalars(GsmTreeConsts& K, const double* __restrict__ p, int32_t use_spike, uint32_t flags,
+                              int32_t stub_mode) {
     K.flags = flags;
     K.stub_mode = stub_mode;
     K.use_spike = use_spike;
@@ -164,7 +169,6 @@ GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int
 
     // BranchSpikePrior BSP:58-64
     K.spike_invalid = (K.shape <= 0) ? 1 : 0;
-    K.log_shape = gsm_log(K.shape);
     const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
     K.stub_counts = (stub_mode != GSM_STUBS_NOSTUB) ? 1 : 0;                 // Stubs:648-650
     K.spike_known_n = (!stubs_spike || K.stub_counts) ? 1 : 0;               // BSP:77
@@ -173,14 +177,12 @@ GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int
     K.rate_invalid = (K.sigma <= 0) ? 1 : 0;
     K.m_ln = 0.0 - (0.5 * K.sigma * K.sigma);                                // log(1) - 0.5 s^2
     K.inv_2s2 = 1.0 / (2 * K.sigma * K.sigma);
-    K.log_s_sqrt2pi = gsm_log(K.sigma * 2.50662827463100050242 /* sqrt(2*pi) */);
 
     // StumpedTreePrior dispatcher STP:150-214
     K.lmm = K.lambda - K.mu;
     K.stp_early = (K.lambda <= K.mu) ? 1 : 0;                                // STP:160-164
     K.tree_variant = GSM_TV_NONE;
     if (!(flags & GSM_F_IGNORE_TREE_PRIOR)) {
-        if (gsm_exp(K.psi) == INFINITY || gsm_exp(-K.psi) == 0) K.stp_early = 1;     // STP:176-178
         if (flags & (GSM_F_ORIGIN | GSM_F_COND_ROOT)) K.tree_variant = GSM_TV_CONDITIONED;
         else if (K.psi == 0 && K.rho == 1) K.tree_variant = GSM_TV_COMPLETE_RHO;
         else if (K.psi == 0) K.tree_variant = GSM_TV_NO_PSI;
@@ -197,14 +199,38 @@ GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int
     K.kE = K.kS - K.c1;
     K.omc2 = 1 - K.c2;
     K.opc2 = 1 + K.c2;
-    K.log_lambda = gsm_log(K.lambda);
-    K.log_psi = gsm_log(K.psi);
-    K.log_rho = gsm_log(K.rho);
-    K.log_lmm = gsm_log(K.lmm);
-    K.log_4rho = gsm_log(4 * K.rho);
-    K.log_2lambda = gsm_log(2 * K.lambda);
-    K.lb_shift = gsm_log(2.0 / K.lmm);
+    K.need_E = ((K.stub_term && K.stub_counts) || (!K.spike_known_n)) ? 1 : 0;   // Poisson mean of the stub count
+}
 
+GSM_HD double gsm_setup_arg(const GsmTreeConsts& K, int32_t j) {
+    switch (j) {
+        case 0: return K.shape;
+        case 1: return K.sigma * 2.50662827463100050242 /* sqrt(2*pi) */;
+        case 2: return K.lambda;
+        case 3: return K.psi;
+        case 4: return K.rho;
+        case 5: return K.lmm;
+        case 6: return 4 * K.rho;
+        case 7: return 2 * K.lambda;
+        case 8: return 2.0 / K.lmm;
+        default: return 1.0;
+    }
+}
+
+// lg[j] = log(gsm_setup_arg(K, j)); exp_psi = exp(psi), exp_npsi = exp(-psi)
+GSM_HD void gsm_setup_finish(GsmTreeConsts& K, const double* lg, double exp_psi, double exp_npsi) {
+    K.log_shape = lg[0];
+    K.log_s_sqrt2pi = lg[1];
+    K.log_lambda = lg[2];
+    K.log_psi = lg[3];
+    K.log_rho = lg[4];
+    K.log_lmm = lg[5];
+    K.log_4rho = lg[6];
+    K.log_2lambda = lg[7];
+    K.lb_shift = lg[8];
+    if (!(K.flags & GSM_F_IGNORE_TREE_PRIOR)) {
+        if (exp_psi == INFINITY || exp_npsi == 0) K.stp_early = 1;           // STP:176-178
+    }
     K.t_internal = 0.0;
     K.t_leaf = 0.0;
     switch (K.tree_variant) {
@@ -222,8 +248,15 @@ GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int
             break;
         default: break;
     }
-    K.need_E = ((K.stub_term && K.stub_counts) || (!K.spike_known_n)) ? 1 : 0;   // Poisson mean of the stub count
     K.need_aux = (K.need_E || (K.tree_variant != GSM_TV_NONE && !K.stp_early)) ? 1 : 0;
+}
+
+GSM_HD void gsm_setup_consts(GsmTreeConsts& K, const double* __restrict__ p, int32_t use_spike, uint32_t flags,
+                             int32_t stub_mode) {
+    gsm_setup_scalars(K, p, use_spike, flags, stub_mode);
+    double lg[GSM_SETUP_NLOG];
+    for (int32_t j = 0; j < GSM_SETUP_NLOG; j++) lg[j] = gsm_log(gsm_setup_arg(K, j));
+    gsm_setup_finish(K, lg, gsm_exp(K.psi), gsm_exp(-K.psi));
 }
 
 // one entry of the per-m tables (entries are independent: the kernel spreads m over the lanes of a warp)
@@ -533,305 +566,3 @@ GSM_HD void gsm_finalize(const GsmTreeConsts& K, const GsmAcc& A, int32_t n, boo
     (void)n;
 }
 
-// =================================================================================================================
-// Fast path: the default wiring family (rates wired, known-n spike prior, no noSpikeOnDatedTips), with every
-// per-tree quantity hoisted into registers and the remaining wiring choices turned into register booleans.
-// The generic functions above remain the reference implementation inside the product for every other wiring
-// (mixture mode, strict clock without rates, dated-tip rule) and are what the fast path is tested against.
-// =================================================================================================================
-
-// packed per-node word (gsm_eval_fast_kernel): parent index in the low bits (a root / detached node points to
-// itself) and four flag bits on top.  WORD = uint16_t for trees of <= 4096 nodes, uint32_t above.
-template <typename WORD> struct GsmWord;
-template <> struct GsmWord<uint16_t> { static constexpr uint32_t IDX = 0x0fffu, NL = 0x1000u, FAKE = 0x2000u, DA = 0x4000u, PF = 0x8000u; };
-template <> struct GsmWord<uint32_t> { static constexpr uint32_t IDX = 0x0fffffffu, NL = 0x10000000u, FAKE = 0x20000000u, DA = 0x40000000u, PF = 0x80000000u; };
-
-GSM_HD bool gsm_fast_path_ok(uint32_t flags, int32_t stub_mode) {
-    const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
-    const bool known_n = !stubs_spike || stub_mode != GSM_STUBS_NOSTUB;          // BSP:77
-    return known_n && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
-}
-
-struct GsmFastA {           // pass A registers
-    double neg_c1, omc2, opc2, t_internal, t_leaf, lmm, c1, kS, log_psi, log_4rho, rho;
-    int32_t variant;
-    bool safe;              // c1, c2 are such that G(h) is a positive normal number for every h >= 0
-};
-struct GsmFastB {           // pass B registers
-    double base, eff_mean, shape, m_ln, inv_2s2, kE, lmm;
-    int32_t n_cut;          // nodes i >= n_cut have no stub count (Stubs:354): n-1 in COUNTS mode, n in EXACT, 0 in NOSTUB
-    int32_t nst_default;    // -1 in NOSTUB mode (Stubs:348-350), else 0
-    bool use_rate;          // relaxed clock (PRCM:216)
-    bool burst_on;          // indicator absent or true (PRCM:181)
-    bool s2c;               // stubs wired to the clock model (PRCM:192-195)
-    bool s2p;               // stubs wired to the spike prior (BSP:81)
-    bool stub_term;         // STP:219 && count mode
-    bool complete_rho;      // psi == 0 && rho == 1 tree density needs the per-branch integral
-};
-
-GSM_HD void gsm_fast_consts(const GsmTreeConsts& K, GsmFastA& a, GsmFastB& b, int32_t n) {
-    a.neg_c1 = -K.c1; a.omc2 = K.omc2; a.opc2 = K.opc2; a.t_internal = K.t_internal; a.t_leaf = K.t_leaf;
-    a.lmm = K.lmm; a.c1 = K.c1; a.kS = K.kS; a.log_psi = K.log_psi; a.log_4rho = K.log_4rho; a.rho = K.rho;
-    a.variant = K.stp_early ? GSM_TV_NONE : K.tree_variant;
-    a.safe = (K.c1 >= 0.0) && (K.c1 < INFINITY) && (K.opc2 > 1e-300) && (K.opc2 < INFINITY) && (K.omc2 == K.omc2) &&
-             (K.omc2 > -INFINITY) && (K.omc2 < INFINITY) && (K.opc2 + K.omc2 > 1e-300);
-    b.base = K.base; b.eff_mean = K.spike_mean; b.shape = K.shape; b.m_ln = K.m_ln; b.inv_2s2 = K.inv_2s2;
-    b.kE = K.kE; b.lmm = K.lmm;
-    b.n_cut = K.stub_mode == GSM_STUBS_COUNTS ? n - 1 : (K.stub_mode == GSM_STUBS_EXACT ? n : 0);
-    b.nst_default = K.stub_mode == GSM_STUBS_NOSTUB ? -1 : 0;
-    b.use_rate = !(K.flags & GSM_F_RELAXED_FALSE);
-    b.burst_on = !((K.flags & GSM_F_HAS_INDICATOR) && !K.use_spike);
-    b.s2c = (K.flags & GSM_F_STUBS_TO_CLOCK) != 0;
-    b.s2p = (K.flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
-    b.stub_term = K.stub_term && K.stub_counts;
-    b.complete_rho = (a.variant == GSM_TV_COMPLETE_RHO);
-}
-
-// -------- checked single-node forms (any input; used for the odd tail node and whenever a warp votes that one of
-// its lanes holds a special value) --------------------------------------------------------------------------------
-template <int VARIANT>
-GSM_HD double gsm_fast_pass_a_checked(const GsmFastA& c, const GsmTabs& T, GsmAcc& A, bool leaf, bool fake_self, bool da,
-                                      bool root, double h, double hp) {
-    const double len = root ? 0.0 : hp - h;
-    if (leaf) {                                                              // STP:190-195, 291-312, 352-359
-        A.n_leaf++;
-        if (da) A.n_da++;
-        else if (h <= GSM_LEAF_EPS) A.n_extant++;
-        else if (len > GSM_LEAF_EPS) A.n_extinct++;
-    }
-    const double e_neg = gsm_exp_t(c.neg_c1 * h, T);
-    const double G = fma(c.omc2, e_neg, c.opc2);
-    const double aux = gsm_log_t(G, T);
-    if (VARIANT == GSM_TV_COMPLETE_RHO) {
-        if (!leaf) A.tree += c.t_internal - aux;
-    } else if (VARIANT == GSM_TV_NO_PSI) {
-        if (!leaf && !fake_self) A.tree += c.t_internal - c.lmm * h - 2 * aux;
-    } else if (VARIANT == GSM_TV_PSI) {
-        if (!leaf) {
-            if (!fake_self) A.tree += c.t_internal - c.c1 * h - 2 * aux;
-        } else if (!(h <= GSM_LEAF_EPS) && !da) {
-            const double numer = c.kS * G - c.c1 * (c.opc2 - e_neg * c.omc2);
-            A.tree += gsm_log_t(numer, T) + c.t_leaf + c.c1 * h + aux;
-        }
-    } else if (VARIANT == GSM_TV_CONDITIONED) {
-        if (leaf) {
-            if (!da) {
-                if (h > 0.000000000005 || c.rho == 0.) {
-                    const double numer = c.kS * G - c.c1 * (c.opc2 - e_neg * c.omc2);
-                    A.tree += gsm_log_t(numer, T) + c.t_leaf + c.c1 * h + aux;
-                } else {
-                    A.tree += c.log_4rho;
-                }
-            }
-        } else if (fake_self) {
-            A.tree += c.log_psi;
-        } else {
-            A.tree += c.t_internal - c.c1 * h - 2 * aux;
-        }
-    }
-    return aux;
-}
-
-// Accumulates into A.rate WITHOUT the per-entry constant log(sigma*sqrt(2 pi)) (added once per tree in
-// gsm_fast_fix_acc) — everything else is the arithmetic of gsm_node_pass_b.
-template <bool WANT_RATES>
-GSM_HD void gsm_fast_pass_b_checked(const GsmFastB& c, const GsmTreeConsts& K, const GsmTabs& T, const double* __restrict__ logfact,
-                                    GsmAcc& A, int32_t i, bool da, bool pf, bool root, double h, double hp, double aux,
-                                    double auxp, double rate, double spike, int32_t nst_raw, double* out_rate, double* out_wspike) {
-    const double len = root ? 0.0 : hp - h;
-    const int32_t nst = (i < c.n_cut) ? nst_raw : c.nst_default;             // Stubs:344-370
-    double burst = spike * c.eff_mean;                                       // PRCM:204-206
-    if (!c.burst_on || (pf && (!c.s2c || nst == 0))) burst = 0.0;            // PRCM:181-183, 192-202
-    const bool eligible = !(len <= 0 || da || root);                         // PRCM:229, SPL:41
-    const double r = c.use_rate ? rate : 1.0;                                // PRCM:210-222
-    if (WANT_RATES) {
-        double eff = c.base;
-        if (eligible) {
-            const double dist = len * c.base * r + burst;                    // PRCM:233
-            eff = dist / len;                                                // PRCM:236
-            A.dist += len * eff;
-            A.burst += burst;
-        }
-        *out_rate = eff;
-        *out_wspike = burst;
-    } else if (eligible) {
-        A.dist += len * c.base * r + burst;
-        A.burst += burst;
-    }
-    {   // BranchRatePrior BRP:43-60
-        if (rate < 0) A.bad |= GSM_BAD_NEG_RATE;
-        const double lr = gsm_log_t(rate, T);
-        const double x0 = lr - c.m_ln;
-        const double t = -(x0 * x0) * c.inv_2s2 - lr;
-        A.rate += (rate <= 0) ? gsm_neg_inf() : t;                           // BRP:168-171
-    }
-    {   // BranchSpikePrior, known-n: BSP:69-100
-        if (spike < 0) A.bad |= GSM_BAD_NEG_SPIKE;                           // BSP:72-75
-        const int32_t ns = c.s2p ? nst : 0;                                  // BSP:81
-        const int32_t m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));     // BSP:197-213
-        const double xs = spike * c.shape;
-        if (m == 0) {
-            if (spike != 0) A.spike += gsm_neg_inf();                        // BSP:86-95
-        } else {
-            A.spike += gsm_gamma_logdens(K, m, spike, xs, gsm_log_t(xs, T)); // BSP:97-99
-        }
-    }
-    const bool have_len = hp > h && !root;
-    if (c.stub_term) {   // stub density, count mode: STP:232-240, 555-571 / 621-637
-        if (da && nst > 0) A.bad |= GSM_BAD_SA_STUBS;
-        if (!root) {
-            if (!have_len) {
-                if (nst != 0) A.stub += gsm_neg_inf();                       // STP:558-561
-            } else {
-                const double E = fma(len, c.kE, 2 * (aux - auxp));           // STP:749-769 via aux
-                double lp = nst * gsm_log_t(E, T) - E;                       // STP:566
-                lp -= gsm_logfact(logfact, nst);                             // STP:567
-                A.stub += lp;
-            }
-        }
-    }
-    if (c.complete_rho && !root) A.tree += (aux - auxp) - c.lmm * len;       // STP:398-416
-}
-
-// -------- unchecked pair forms: two adjacent nodes, straight-line, no special-value handling -----------------------
-// Preconditions are established by gsm_fast_a_special / gsm_fast_b_special (voted per warp by the kernel).
-
-// pass A: exp argument in range, G a positive normal number
-GSM_HD bool gsm_fast_a_special(const GsmFastA& c, double h) {
-    const double x = c.neg_c1 * h;
-    return gsm_exp_special(x) || !(x <= 0.0);          // |c1 h| >= 704, NaN, or a negative height
-}
-
-template <int VARIANT>
-GSM_HD void gsm_fast_pass_a_pair(const GsmFastA& c, const GsmTabs& T, GsmAcc& A, const bool leaf[2], const bool fake_self[2],
-                                 const bool da[2], const bool root[2], const double h[2], const double hp[2], double aux_out[2]) {
-    double e[2], G[2], a[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) e[k] = gsm_exp_body(c.neg_c1 * h[k], T.exptab);
-#pragma unroll
-    for (int k = 0; k < 2; k++) G[k] = fma(c.omc2, e[k], c.opc2);           // in [min(1+c2, 2), max(1+c2, 2)]: positive, normal
-#pragma unroll
-    for (int k = 0; k < 2; k++) a[k] = gsm_log_body(G[k], T.logtab);
-    // extinct-leaf terms need log(numer) (psi > 0 and origin/root-conditioned variants): one more body, shared by the pair
-    double lnum[2] = {0.0, 0.0};
-    bool need_num[2] = {false, false};
-    if (VARIANT == GSM_TV_PSI || VARIANT == GSM_TV_CONDITIONED) {
-        double numer[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (VARIANT == GSM_TV_PSI) need_num[k] = leaf[k] && !(h[k] <= GSM_LEAF_EPS) && !da[k];
-            else need_num[k] = leaf[k] && !da[k] && (h[k] > 0.000000000005 || c.rho == 0.);
-            numer[k] = c.kS * G[k] - c.c1 * (c.opc2 - e[k] * c.omc2);
-        }
-        if (need_num[0] || need_num[1]) {
-#pragma unroll
-            for (int k = 0; k < 2; k++) lnum[k] = gsm_log_t(need_num[k] ? numer[k] : 1.0, T);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const double len = root[k] ? 0.0 : hp[k] - h[k];
-        if (leaf[k]) {                                                       // STP:190-195, 291-312, 352-359
-            A.n_leaf++;
-            if (da[k]) A.n_da++;
-            else if (h[k] <= GSM_LEAF_EPS) A.n_extant++;
-            else if (len > GSM_LEAF_EPS) A.n_extinct++;
-        }
-        if (VARIANT == GSM_TV_COMPLETE_RHO) {
-            if (!leaf[k]) A.tree += c.t_internal - a[k];
-        } else if (VARIANT == GSM_TV_NO_PSI) {
-            if (!leaf[k] && !fake_self[k]) A.tree += c.t_internal - c.lmm * h[k] - 2 * a[k];
-        } else if (VARIANT == GSM_TV_PSI) {
-            if (!leaf[k]) {
-                if (!fake_self[k]) A.tree += c.t_internal - c.c1 * h[k] - 2 * a[k];
-            } else if (need_num[k]) {
-                A.tree += lnum[k] + c.t_leaf + c.c1 * h[k] + a[k];
-            }
-        } else if (VARIANT == GSM_TV_CONDITIONED) {
-            if (leaf[k]) {
-                if (!da[k]) A.tree += need_num[k] ? lnum[k] + c.t_leaf + c.c1 * h[k] + a[k] : c.log_4rho;
-            } else if (fake_self[k]) {
-                A.tree += c.log_psi;
-            } else {
-                A.tree += c.t_internal - c.c1 * h[k] - 2 * a[k];
-            }
-        }
-        aux_out[k] = a[k];
-    }
-}
-
-// pass B: true when this branch needs the checked path
-GSM_HD bool gsm_fast_b_special(const GsmFastB& c, int32_t i, bool da, bool pf, bool root, double len, double E, double rate,
-                               double spike, int32_t nst_raw) {
-    const int32_t nst = (i < c.n_cut) ? nst_raw : c.nst_default;
-    const int32_t ns = c.s2p ? nst : 0;
-    const int32_t m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
-    bool sp = gsm_log_special(rate) || !(len >= 0.0);
-    sp = sp || (m == 0 ? (spike != 0) : (gsm_log_special(spike * c.shape) || m > GSM_LUT_M || m < 0));
-    if (c.stub_term) {
-        const bool have_len = len > 0.0;
-        sp = sp || (da && nst > 0) || (nst < 0) || (nst >= GSM_LOGFACT_N) || (!have_len && !root && nst != 0) ||
-             (have_len && gsm_log_special(E));
-    }
-    return sp;
-}
-
-template <bool WANT_RATES>
-GSM_HD void gsm_fast_pass_b_pair(const GsmFastB& c, const GsmTreeConsts& K, const GsmTabs& T, const double* __restrict__ logfact,
-                                 GsmAcc& A, int32_t i0, const bool da[2], const bool pf[2], const bool root[2], const double len[2],
-                                 const double E[2], const double dA[2], const double rate[2], const double spike[2],
-                                 const int32_t nst_raw[2], double* out_rate, double* out_wspike) {
-    double xs[2], lr[2], lxs[2], lE[2];
-    int32_t nst[2], m[2];
-    bool have_len[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        nst[k] = (i0 + k < c.n_cut) ? nst_raw[k] : c.nst_default;
-        const int32_t ns = c.s2p ? nst[k] : 0;
-        m[k] = root[k] ? ns + 1 : (da[k] ? 0 : (pf[k] ? ns : ns + 1));
-        xs[k] = spike[k] * c.shape;
-        have_len[k] = len[k] > 0.0;
-    }
-    // six independent log bodies (arguments of lanes that do not need a value are replaced by 1)
-#pragma unroll
-    for (int k = 0; k < 2; k++) lr[k] = gsm_log_body(rate[k], T.logtab);
-#pragma unroll
-    for (int k = 0; k < 2; k++) lxs[k] = gsm_log_body(m[k] == 0 ? 1.0 : xs[k], T.logtab);
-    if (c.stub_term) {
-#pragma unroll
-        for (int k = 0; k < 2; k++) lE[k] = gsm_log_body(have_len[k] ? E[k] : 1.0, T.logtab);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        double burst = spike[k] * c.eff_mean;                                // PRCM:204-206
-        if (!c.burst_on || (pf[k] && (!c.s2c || nst[k] == 0))) burst = 0.0;  // PRCM:181-183, 192-202
-        const bool eligible = have_len[k] && !da[k];                         // PRCM:229, SPL:41 (a root has len == 0)
-        const double r = c.use_rate ? rate[k] : 1.0;                         // PRCM:210-222
-        if (WANT_RATES) {
-            double eff = c.base;
-            if (eligible) {
-                const double dist = len[k] * c.base * r + burst;             // PRCM:233
-                eff = dist / len[k];                                         // PRCM:236
-                A.dist += len[k] * eff;
-                A.burst += burst;
-            }
-            out_rate[k] = eff;
-            out_wspike[k] = burst;
-        } else if (eligible) {
-            A.dist += len[k] * c.base * r + burst;
-            A.burst += burst;
-        }
-        const double x0 = lr[k] - c.m_ln;                                    // BRP:171
-        A.rate += -(x0 * x0) * c.inv_2s2 - lr[k];
-        if (m[k] != 0) A.spike += lxs[k] * K.am1[m[k]] - xs[k] + K.lgc[m[k]];   // BSP:97-99
-        if (c.stub_term && have_len[k]) {                                    // STP:566-567
-            double lp = nst[k] * lE[k] - E[k];
-            lp -= (nst[k] < 2) ? 0.0 : logfact[nst[k]];
-            A.stub += lp;
-        }
-        if (c.complete_rho && !root[k]) A.tree += dA[k] - c.lmm * len[k];    // STP:398-416
-    }
-}
-
-// add the per-entry constant of the rate prior that the fast pass B leaves out
-GSM_HD void gsm_fast_fix_acc(const GsmTreeConsts& K, GsmAcc& A, int32_t n) { A.rate -= n * K.log_s_sqrt2pi; }

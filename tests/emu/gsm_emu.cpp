@@ -1,5 +1,5 @@
 // gsm_emu.cpp — TEST INFRASTRUCTURE.  Compiles the product's per-node device math
-// (gammaspikemodel_b200/csrc/gsm_node_math.cuh, GSM_HD = plain inline under g++) and walks one tree at a
+// (gammaspikemodel_b200/csrc/gsm_node_math.cuh and gsm_lean.cuh, GSM_HD = plain inline under g++) and walks one tree at a
 // time through the same phases as gsm_eval_kernel, sequentially.  It lets the CPU-only test tier check the
 // algebra and the flag/epilogue logic of the kernel against the oracle without a GPU.  It is never loaded
 // by the product package and is not a fallback.
@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../gammaspikemodel_b200/csrc/gsm_node_math.cuh"
+#include "../../gammaspikemodel_b200/csrc/gsm_lean.cuh"
 
 static double g_logfact_host[GSM_LOGFACT_N];
 static bool g_init = false;
@@ -109,147 +110,169 @@ extern "C" int gsm_emu_eval_batch(uint32_t flags, int32_t stub_mode, int64_t n_t
     return 0;
 }
 
-// ---- the fast path of gsm_eval_fast_kernel, walked sequentially in node pairs (32-bit packed words).  A "warp" is
-// one pair here: the pair takes the checked path when either node is special, exactly as a voting warp would. ----
-template <int VARIANT>
-static void fast_a(const GsmFastA& fa, const GsmTabs& T, GsmAcc& A, int n, const double* h, double* aux, uint32_t* w) {
-    using W = GsmWord<uint32_t>;
-    std::vector<uint32_t> wnew(w, w + n);
-    auto flags = [&](int i, bool& leaf, bool& fake_self, bool& da, bool& root, bool& pf, double& hp) {
-        const int p = (int)(w[i] & W::IDX);
-        hp = h[p];
-        root = p == i;
-        leaf = !(w[i] & W::NL);
-        fake_self = (w[i] & W::FAKE) != 0;
-        da = leaf && !root && hp == h[i];
-        pf = !root && (w[p] & W::FAKE);
-    };
-    const int nfull = n >> 1;
-    for (int j = 0; j < nfull; j++) {
-        const int i0 = 2 * j;
-        bool leaf[2], fake_self[2], da[2], root[2], pf[2];
-        double hh[2] = {h[i0], h[i0 + 1]}, hp[2], a[2];
-        for (int k = 0; k < 2; k++) flags(i0 + k, leaf[k], fake_self[k], da[k], root[k], pf[k], hp[k]);
-        const bool sp = !fa.safe || gsm_fast_a_special(fa, hh[0]) || gsm_fast_a_special(fa, hh[1]);
-        if (sp) for (int k = 0; k < 2; k++) a[k] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf[k], fake_self[k], da[k], root[k], hh[k], hp[k]);
-        else gsm_fast_pass_a_pair<VARIANT>(fa, T, A, leaf, fake_self, da, root, hh, hp, a);
-        for (int k = 0; k < 2; k++) {
-            aux[i0 + k] = a[k];
-            wnew[i0 + k] = w[i0 + k] | (da[k] ? W::DA : 0u) | (pf[k] ? W::PF : 0u);
-        }
+// ---- the lean path (gsm_lean_kernel + gsm_post_kernel), walked sequentially by one "thread".  A tree the lean
+// path hands back (redo list on the device) is evaluated by the generic walk above, exactly as the post kernel does. ----
+static GsmLeanBlob g_blob;
+static bool g_blob_init = false;
+static void init_blob() {
+    if (g_blob_init) return;
+    static const GsmLogEntry lt[GSM_LOG9_TAB_N] = GSM_LOG9_TAB_INIT;
+    static const uint64_t et[GSM_EXP9_TAB_N] = GSM_EXP9_TAB_INIT;
+    memcpy(g_blob.logtab, lt, sizeof lt);
+    memcpy(g_blob.exptab, et, sizeof et);
+    init_tables();
+    for (int i = 0; i <= GSM_LEAN_MAX_NST; i++) {
+        g_blob.stubtab[i].invc = (double)i;
+        g_blob.stubtab[i].logc = -g_logfact_host[i];
     }
-    if (n & 1) {
-        const int i = n - 1;
-        bool leaf, fake_self, da, root, pf;
-        double hp;
-        flags(i, leaf, fake_self, da, root, pf, hp);
-        aux[i] = gsm_fast_pass_a_checked<VARIANT>(fa, T, A, leaf, fake_self, da, root, h[i], hp);
-        wnew[i] = w[i] | (da ? W::DA : 0u) | (pf ? W::PF : 0u);
-    }
-    for (int i = 0; i < n; i++) w[i] = wnew[i];
+    g_blob_init = true;
 }
 
+template <bool GENERAL, bool WANT>
+static void lean_b_all(const GsmLeanC& c, GsmLeanAccB& SB, int n, const double* h, const double* aux, const uint16_t* w,
+                       const double* rate, const double* spike, const int32_t* nstubs, double* out_rates, double* out_wsp) {
+    double dr, dw;
+    for (int i = 0; i < n - 1; i++) {
+        const int p = w[i] & 0x7fff;
+        gsm_lean_b_node<GENERAL, WANT>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], nstubs ? nstubs[i] : -1,
+                                       out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
+    }
+}
+
+// returns false when the tree is handed back to the generic path
 template <bool WANT>
-static void eval_tree_fast(uint32_t flags, int32_t stub_mode, int32_t n, const double* h, const int32_t* par_in,
+static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const double* h, const int32_t* par_in,
                            const double* rate, const double* spike, const int32_t* nstubs, const double* params,
                            int32_t use_spike, double* out, double* out_rates, double* out_wsp) {
-    using W = GsmWord<uint32_t>;
-    if (n <= 0) {
-        for (int k = 0; k < GSM_NOUT; k++) out[k] = NAN;
-        return;
-    }
+    if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) return false;
+    const int L = (n + 1) >> 1;
     GsmTreeConsts K;
-    gsm_setup_consts(K, params, use_spike, flags, stub_mode);
-    for (int m = 0; m <= GSM_LUT_M; m++) gsm_lut_entry(K, params[GSM_P_SPIKE_SHAPE], m);
-    GsmTabs T;
-    T.logtab = gsm_log_tab_h;
-    T.exptab = gsm_exp_tab_h;
-    std::vector<uint32_t> w(n);
-    std::vector<double> aux(n, 0.0);
-    int32_t root = -1;
-    bool anyzero = false;
-    for (int i = 0; i < n; i++) {
-        int32_t p = par_in[i];
-        if ((uint32_t)p >= (uint32_t)n) { if (p < 0) root = i; p = i; }
-        w[i] = (uint32_t)p;
+    memset(&K, 0, sizeof K);
+    gsm_setup_scalars(K, params, use_spike, flags, stub_mode);
+    GsmLogEntry mtab[GSM_LEAN_MTAB_N];
+    mtab[0].invc = -1.0;
+    mtab[0].logc = 0.0;
+    for (int m = 1; m < GSM_LEAN_MTAB_N; m++) {
+        mtab[m].invc = K.shape * m - 1;
+        mtab[m].logc = gsm_log(K.shape) - gsm_log_gamma(K.shape * m);
     }
+    if (!gsm_lean_consts_ok(K)) return false;
+    std::vector<uint16_t> w(n);
+    int root = -1, nroot = 0;
+    bool bad = false;
     for (int i = 0; i < n; i++) {
-        int p = (int)(w[i] & W::IDX);
-        if (p != i) { w[p] |= W::NL; if (h[p] == h[i]) anyzero = true; }
+        int p = par_in[i];
+        if (p < 0) { root = i; nroot++; p = i; bad = bad || (i < L); }
+        else bad = bad || p < L || p >= n;
+        w[i] = (uint16_t)(p & 0x7fff);
     }
-    if (anyzero)
-        for (int i = 0; i < n; i++) {
-            int p = (int)(w[i] & W::IDX);
-            if (!(w[i] & W::NL) && p != i && h[p] == h[i]) w[p] |= W::FAKE;
+    if (bad || nroot != 1) return false;
+    GsmLeanC c;
+    gsm_lean_consts(K, c, n);
+    c.logtab = g_blob.logtab; c.exptab = g_blob.exptab; c.stubtab = g_blob.stubtab; c.mtab = mtab;
+    c.log_shape = gsm_log(K.shape); c.logfact = g_logfact_host;
+    GsmLeanAccA SA;
+    gsm_lean_acc_a_zero(SA);
+    std::vector<double> aux(n);
+    bool anyda = false;
+    for (int i = 0; i < n; i++) {
+        double e, G;
+        aux[i] = gsm_lean_aux(c, SA, h[i], e, G);
+        if (i < L) {
+            const int p = w[i] & 0x7fff;
+            const bool da = h[p] == h[i];
+            if (da) { w[p] |= 0x8000; anyda = true; }
+            if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, SA, !da, h[i], aux[i], e, G);
+            else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, SA, !da, h[i], aux[i], e, G);
         }
+    }
+    const bool general = anyda || root != n - 1;
+    GsmLeanAccB SB, ST;
+    gsm_lean_acc_b_zero(SB);
+    gsm_lean_acc_b_zero(ST);
+    if (general) lean_b_all<true, WANT>(c, SB, n, h, aux.data(), w.data(), rate, spike, c.use_counts ? nstubs : nullptr, out_rates, out_wsp);
+    else lean_b_all<false, WANT>(c, SB, n, h, aux.data(), w.data(), rate, spike, c.use_counts ? nstubs : nullptr, out_rates, out_wsp);
+    {
+        const int i = n - 1, p = w[i] & 0x7fff;
+        const int32_t nst = (stub_mode == GSM_STUBS_EXACT && nstubs) ? nstubs[i] : 0;
+        double dr, dw;
+        gsm_lean_b_node<true, WANT>(c, ST, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], nst,
+                                    out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
+    }
+    GsmLean6 s6, t6;
+    GsmLeanAccA SA0;
+    gsm_lean_acc_a_zero(SA0);
+    if (general) gsm_lean_combine<true>(K, c, SA, SB, s6);
+    else gsm_lean_combine<false>(K, c, SA, SB, s6);
+    gsm_lean_combine<true>(K, c, SA0, ST, t6);
+    s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
+    const uint32_t chk = gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk), chk_n = gsm_umax(SB.chk_n, ST.chk_n);
+    bool redo = chk >= GSM_CHK_LIMIT || chk_n != 0u ||
+                (!general && SB.chk_len >= GSM_CHK_LIMIT) || SA.hmax >= 0x7ff00000u;
+    if (!redo) redo = !(K.c1 * gsm_hilo((int32_t)SA.hmax + 1, 0) < 700.0);
+    if (redo) return false;
+    // ---- gsm_post_kernel part 1 ----
+    GsmTreeConsts K2;
+    memset(&K2, 0, sizeof K2);
+    gsm_setup_consts(K2, params, use_spike, flags, stub_mode);
+    GsmLeanC c2;
+    gsm_lean_consts(K2, c2, n);
     GsmAcc A;
     gsm_acc_zero(A);
-    GsmFastA fa;
-    GsmFastB fb;
-    gsm_fast_consts(K, fa, fb, n);
-    switch (fa.variant) {
-        case GSM_TV_COMPLETE_RHO: fast_a<GSM_TV_COMPLETE_RHO>(fa, T, A, n, h, aux.data(), w.data()); break;
-        case GSM_TV_NO_PSI: fast_a<GSM_TV_NO_PSI>(fa, T, A, n, h, aux.data(), w.data()); break;
-        case GSM_TV_PSI: fast_a<GSM_TV_PSI>(fa, T, A, n, h, aux.data(), w.data()); break;
-        case GSM_TV_CONDITIONED: fast_a<GSM_TV_CONDITIONED>(fa, T, A, n, h, aux.data(), w.data()); break;
-        default: fast_a<GSM_TV_NONE>(fa, T, A, n, h, aux.data(), w.data()); break;
-    }
-    double dummy[2];
-    const int nfull = n >> 1;
-    for (int j = 0; j <= nfull; j++) {
-        const int i0 = 2 * j;
-        const int cnt = (j < nfull) ? 2 : (n & 1);
-        if (cnt == 0) break;
-        bool da[2], pf[2], rt[2], sp = false;
-        double hp[2], auxp[2], len[2], dA[2], E[2], rr[2], ss[2];
-        int32_t nr[2];
-        for (int k = 0; k < cnt; k++) {
-            const int i = i0 + k;
-            const int p = (int)(w[i] & W::IDX);
-            da[k] = (w[i] & W::DA) != 0; pf[k] = (w[i] & W::PF) != 0; rt[k] = p == i;
-            hp[k] = h[p]; auxp[k] = aux[p]; len[k] = hp[k] - h[i]; dA[k] = aux[i] - auxp[k];
-            E[k] = fma(len[k], fb.kE, 2 * dA[k]);
-            rr[k] = rate[i]; ss[k] = spike[i]; nr[k] = nstubs ? nstubs[i] : 0;
-            sp = sp || gsm_fast_b_special(fb, i, da[k], pf[k], rt[k], len[k], E[k], rr[k], ss[k], nr[k]);
-        }
-        if (sp || cnt == 1) {
-            for (int k = 0; k < cnt; k++)
-                gsm_fast_pass_b_checked<WANT>(fb, K, T, g_logfact_host, A, i0 + k, da[k], pf[k], rt[k], h[i0 + k], hp[k], aux[i0 + k],
-                                              auxp[k], rr[k], ss[k], nr[k], out_rates ? out_rates + i0 + k : dummy,
-                                              out_wsp ? out_wsp + i0 + k : dummy);
-        } else {
-            gsm_fast_pass_b_pair<WANT>(fb, K, T, g_logfact_host, A, i0, da, pf, rt, len, E, dA, rr, ss, nr,
-                                       out_rates ? out_rates + i0 : dummy, out_wsp ? out_wsp + i0 : dummy);
-        }
-    }
-    if (root < 0) {
-        for (int k = 0; k < GSM_NOUT; k++) out[k] = NAN;
-        return;
-    }
-    gsm_fast_fix_acc(K, A, n);
-    gsm_finish_consts(K, h[root]);
-    gsm_finalize(K, A, n, (w[root] & W::FAKE) != 0, out);
+    A.n_leaf = c2.L;
+    A.n_extant = SB.n_extant;
+    A.n_extinct = SB.n_extinct;
+    A.n_da = SB.n_da;
+    gsm_lean_finish(K2, c2, s6, SB.n_nst + ST.n_nst, SA.n_leafterm, SA.n_plain, SB.n_fake + ST.n_fake, n, A);
+    gsm_finish_consts(K2, h[root]);
+    gsm_finalize(K2, A, n, (w[root] & 0x8000) != 0, out);
+    return true;
 }
 
-// returns 1 when the wiring is outside the fast-path family (caller falls back to gsm_emu_eval_batch)
-extern "C" int gsm_emu_eval_batch_fast(uint32_t flags, int32_t stub_mode, int64_t n_trees, int32_t n_nodes, int64_t stride,
+// returns 1 when the wiring is outside the lean family (caller uses gsm_emu_eval_batch); *n_lean = trees finished
+// by the lean path (the rest went through the generic walk, as on the device)
+extern "C" int gsm_emu_eval_batch_lean(uint32_t flags, int32_t stub_mode, int64_t n_trees, int32_t n_nodes, int64_t stride,
                                        const double* height, const int32_t* parent, const double* rate, const double* spike,
                                        const int32_t* nstubs, const double* params, const uint8_t* use_spike,
-                                       const int32_t* node_count, double* out_tree, double* out_rates, double* out_wsp) {
-    init_tables();
-    if (!gsm_fast_path_ok(flags, stub_mode) || !rate) return 1;
+                                       const int32_t* node_count, double* out_tree, double* out_rates, double* out_wsp,
+                                       int64_t* n_lean) {
+    init_blob();
+    if (n_lean) *n_lean = 0;
+    if (!gsm_lean_wiring_ok(flags, stub_mode) || !rate) return 1;
     for (int64_t t = 0; t < n_trees; t++) {
         int32_t n = node_count ? node_count[t] : n_nodes;
         const int64_t r = t * stride;
-        if (out_rates || out_wsp)
-            eval_tree_fast<true>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
-                                 params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT,
-                                 out_rates ? out_rates + r : nullptr, out_wsp ? out_wsp + r : nullptr);
+        const bool want = out_rates || out_wsp;
+        bool ok;
+        if (want)
+            ok = eval_tree_lean<true>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
+                                      params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT,
+                                      out_rates ? out_rates + r : nullptr, out_wsp ? out_wsp + r : nullptr);
         else
-            eval_tree_fast<false>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
-                                  params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT, nullptr, nullptr);
+            ok = eval_tree_lean<false>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
+                                       params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT, nullptr, nullptr);
+        if (ok) {
+            if (n_lean) ++*n_lean;
+            continue;
+        }
+        if (want)
+            eval_tree<true>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
+                            params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT,
+                            out_rates ? out_rates + r : nullptr, out_wsp ? out_wsp + r : nullptr);
+        else
+            eval_tree<false>(flags, stub_mode, n, height + r, parent + r, rate + r, spike + r, nstubs ? nstubs + r : nullptr,
+                             params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1, out_tree + t * GSM_NOUT, nullptr, nullptr);
     }
     return 0;
+}
+
+extern "C" void gsm_emu_log9_vec(const double* x, double* y, int64_t n) {
+    init_blob();
+    for (int64_t i = 0; i < n; i++) y[i] = gsm_log9(x[i], g_blob.logtab);
+}
+extern "C" void gsm_emu_exp9_vec(const double* x, double* y, int64_t n) {
+    init_blob();
+    for (int64_t i = 0; i < n; i++) y[i] = gsm_exp9(x[i], g_blob.exptab);
 }
 
 // ---- table-driven log / exp of the kernels, exposed for accuracy tests ----

@@ -20,8 +20,8 @@ def emu():
         _emu = C.CDLL(os.path.join(ROOT, "tests", "_emu", "libgsm_emu.so"))
         _emu.gsm_emu_eval_batch.argtypes = [C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 11
         _emu.gsm_emu_eval_batch.restype = C.c_int
-        _emu.gsm_emu_eval_batch_fast.argtypes = _emu.gsm_emu_eval_batch.argtypes
-        _emu.gsm_emu_eval_batch_fast.restype = C.c_int
+        _emu.gsm_emu_eval_batch_lean.argtypes = _emu.gsm_emu_eval_batch.argtypes + [C.c_void_p]
+        _emu.gsm_emu_eval_batch_lean.restype = C.c_int
     return _emu
 
 
@@ -52,18 +52,21 @@ def run_emu(a, flags, mode, node_count=None, rates=True):
     return {"out": out, "rates": r, "wspikes": w}
 
 
-def run_emu_fast(a, flags, mode, node_count=None, rates=True):
-    """host build of the fast-path math (gsm_eval_fast_kernel); returns None when the wiring is outside its family"""
+def run_emu_lean(a, flags, mode, node_count=None, rates=True):
+    """host build of the lean path (gsm_lean_kernel + gsm_post_kernel; trees it hands back go through the generic walk, as on
+    the device).  Returns None when the wiring is outside its family; else the results plus "n_lean" = trees it finished."""
     T, N = a["height"].shape
     out = np.empty((T, abi.NOUT))
     r = np.full((T, N), np.nan) if rates else None
     w = np.full((T, N), np.nan) if rates else None
     nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
-    rc = emu().gsm_emu_eval_batch_fast(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
-                                       _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w))
+    n_lean = np.zeros(1, np.int64)
+    rc = emu().gsm_emu_eval_batch_lean(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
+                                       _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w),
+                                       _p(n_lean))
     if rc != 0:
         return None
-    return {"out": out, "rates": r, "wspikes": w}
+    return {"out": out, "rates": r, "wspikes": w, "n_lean": int(n_lean[0])}
 
 
 def run_capi(a, flags, mode, node_count=None, rates=True, engine=None):

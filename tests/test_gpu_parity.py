@@ -115,7 +115,7 @@ def test_device_resident_path_equals_host_path():
     st.synchronize()
     assert np.array_equal(out.cpu().numpy(), host["out"], equal_nan=True)
     assert np.array_equal(rates[:, : b.n_nodes].cpu().numpy(), host["rates"])
-    assert eng.launch_count == 1
+    assert eng.launch_count in (1, 2)   # generic: one kernel; lean path: lean + post kernel
     eng.close()
 
 

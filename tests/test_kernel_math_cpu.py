@@ -7,7 +7,7 @@ import pytest
 
 from gammaspikemodel_b200 import abi
 from cases import build_cases
-from helpers import assert_results_match, run_emu, run_emu_fast, run_oracle
+from helpers import assert_results_match, run_emu, run_emu_lean, run_oracle
 
 CASES = build_cases()
 
@@ -31,10 +31,23 @@ def test_logp_only_variant_equals_rates_variant():
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_emulated_fast_path_matches_oracle(case):
-    """the register-hoisted fast path (gsm_eval_fast_kernel's math) on every case of its wiring family"""
+def test_emulated_lean_path_matches_oracle(case):
+    """the lean path (gsm_lean_kernel's math + redo hand-back) on every case of its wiring family"""
     name, a, flags, mode, nc = case
-    got = run_emu_fast(a, flags, mode, node_count=nc)
+    got = run_emu_lean(a, flags, mode, node_count=nc)
     if got is None:
-        pytest.skip("wiring outside the fast-path family (generic kernel handles it)")
+        pytest.skip("wiring outside the lean family (generic kernel handles it)")
     assert_results_match(got, run_oracle(a, flags, mode, node_count=nc), node_count=nc, what=name)
+
+
+# cases whose trees must all be finished by the lean path itself (no hand-back): ordinary valid states
+LEAN_FULL = {"c2-default", "c3-default", "c4-default", "c3-exact-counts", "c3-strict-clock", "c3-no-indicator", "c3-ignore-tree-prior", "c3-ignore-stub-prior",
+             "c3-origin", "c3-origin-cond-sampling", "c3-origin-cond-rho", "c3-root-cond-sampling", "c3-root-cond-rho",
+             "c2-psi0-rho-lt1", "c3-psi0-rho1-dated", "c3-psi0-rho-lt1-dated", "c2-psi-on-ultrametric", "ragged-node-counts"}
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in LEAN_FULL], ids=[c[0] for c in CASES if c[0] in LEAN_FULL])
+def test_lean_path_covers_ordinary_states(case):
+    name, a, flags, mode, nc = case
+    got = run_emu_lean(a, flags, mode, node_count=nc)
+    assert got is not None and got["n_lean"] == a["height"].shape[0], (name, got and got["n_lean"])
