@@ -118,6 +118,24 @@ static __device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y)
 static __device__ __forceinline__ void sts_v4u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// per-thread asynchronous global -> shared copies (LDGSTS): the prefetch of pass B.  They complete in groups
+// (commit / wait_group), not through register scoreboards, so an in-flight prefetch never stalls an unrelated load.
+static __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+static __device__ __forceinline__ int2 lds_v2s32(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 static __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(v)) : "memory");
 }
@@ -405,7 +423,6 @@ struct GsmLeanShared {
     GsmTreeConsts K;
     uint64_t mbar;
     int32_t root, nroot, bad;
-    double log_shape;
     double red[6][NWARP];
     int32_t redi[7][NWARP];
     uint32_t redu[4][NWARP];
@@ -471,9 +488,11 @@ static __device__ __forceinline__ bool lean_pass_a(const GsmLeanC& c, GsmLeanAcc
     return anyda;
 }
 
+// a_ring: two stages of BLOCK * 40 bytes: per stage [rate pairs: BLOCK x 16 B][spike pairs: BLOCK x 16 B][stub-count
+// pairs: BLOCK x 8 B]; every thread copies and reads only its own slots, so no barrier is involved.
 template <bool GENERAL, bool WANT_RATES, int BLOCK>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, const GsmBatch& b, int64_t row, int n,
-                                                   int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
+                                                   int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w, uint32_t a_ring,
                                                    double* __restrict__ out_rates, double* __restrict__ out_wspikes) {
     const double2* rate2 = reinterpret_cast<const double2*>(b.rate + row);
     const double2* spike2 = reinterpret_cast<const double2*>(b.spike + row);
@@ -481,8 +500,29 @@ static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAcc
     double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const int npairs = (n - 1) >> 1;   // main loop: nodes 0 .. n-2 (n is odd)
+    constexpr uint32_t STAGE = BLOCK * 40u;
+    const uint32_t slot = a_ring + tid * 16u;   // rate; spike at + BLOCK*16; counts at + BLOCK*32 - tid*8
 
-    auto body = [&](int j, const double2& rr, const double2& ss, const int2& kk) {
+    auto fetch = [&](int j, uint32_t st) {
+        if (j < npairs) {
+            cp_async_16(slot + st, rate2 + j);
+            cp_async_16(slot + st + BLOCK * 16u, spike2 + j);
+            if (nst2) cp_async_8(slot + st + BLOCK * 32u - tid * 8u, nst2 + j);
+        }
+        cp_async_commit();
+    };
+    uint32_t st = 0u;
+    int j = tid;
+    fetch(j, st);
+#pragma unroll 1
+    for (; j < npairs; j += BLOCK) {
+        fetch(j + BLOCK, st ^ STAGE);   // the strip after this one
+        cp_async_wait<1>();             // this strip has landed
+        const double2 rr = lds_v2f64(slot + st);
+        const double2 ss = lds_v2f64(slot + st + BLOCK * 16u);
+        int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
+        if (nst2) kk = lds_v2s32(slot + st + BLOCK * 32u - tid * 8u);
+        st ^= STAGE;
         const double2 h2 = lds_v2f64(a_h + j * 16);
         const double2 a2 = lds_v2f64(a_aux + j * 16);
         const uint32_t w2 = lds_u32(a_w + j * 4);
@@ -502,29 +542,8 @@ static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAcc
             if (orate2) orate2[j] = make_double2(er[0], er[1]);
             if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
         }
-    };
-    auto fetch = [&](int j, double2& rr, double2& ss, int2& kk) {
-        if (j < npairs) {
-            rr = ld_stream(rate2 + j);
-            ss = ld_stream(spike2 + j);
-            if (nst2) kk = ld_stream(nst2 + j);
-        }
-    };
-    // two register sets in ping-pong: the strip after the current one is always in flight
-    double2 rA = make_double2(1.0, 1.0), sA = rA, rB = rA, sB = rA;
-    int2 kA = make_int2(-1, -1), kB = kA;   // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
-    int j = tid;
-    fetch(j, rA, sA, kA);
-#pragma unroll 1
-    while (j < npairs) {
-        fetch(j + BLOCK, rB, sB, kB);
-        body(j, rA, sA, kA);
-        j += BLOCK;
-        if (j >= npairs) break;
-        fetch(j + BLOCK, rA, sA, kA);
-        body(j, rB, sB, kB);
-        j += BLOCK;
     }
+    cp_async_wait<0>();
 }
 
 template <int BLOCK, int MINB, bool WANT_RATES>
@@ -542,6 +561,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     uint16_t* sh_w = reinterpret_cast<uint16_t*>(sh_aux + S);
     GsmLeanBlob* sh_blob = reinterpret_cast<GsmLeanBlob*>(smem_raw + static_cast<size_t>(S) * 18u);
     GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_blob + 1);
+    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_mtab + GSM_LEAN_MTAB_N + 1);   // 16-byte aligned
     GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
@@ -587,17 +607,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
-    const uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w);
+    const uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w), a_ring = smem_u32(sh_ring);
     if (setup_warp) {
         // {shape m - 1, log shape - logGamma(shape m)}, m = lane + 1 (BSP:97-99 with the Lanczos logGamma of commons-math)
         const double shape = K.shape;
         const double lsh = log(shape);
-        if (lane == 1) sh.log_shape = lsh;
-        const int m = lane + 1;
         GsmLogEntry e;
-        e.invc = shape * m - 1;
-        e.logc = lsh - lean_log_gamma(shape * m);
-        sh_mtab[m] = e;
+#pragma unroll 1
+        for (int m = lane + 1; m < GSM_LEAN_MTAB_N; m += 32) {
+            e.invc = shape * m - 1;
+            e.logc = lsh - lean_log_gamma(shape * m);
+            sh_mtab[m] = e;
+        }
         if (lane == 0) {
             e.invc = -1.0;
             e.logc = 0.0;
@@ -642,7 +663,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     c.exptab = sh_blob->exptab;
     c.stubtab = sh_blob->stubtab;
     c.mtab = sh_mtab;
-    c.logfact = g_logfact;
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     bool anyda = false;
@@ -656,7 +676,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
-    c.log_shape = sh.log_shape;
     const int root = sh.root;
     const bool general = any || root != n - 1;
 
@@ -665,9 +684,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     gsm_lean_acc_b_zero(SB);
     GsmLean6 s6;
     if (general) {
-        lean_pass_b<true, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, out_rates, out_wspikes);
+        lean_pass_b<true, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, a_ring, out_rates, out_wspikes);
     } else {
-        lean_pass_b<false, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, out_rates, out_wspikes);
+        lean_pass_b<false, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, a_ring, out_rates, out_wspikes);
     }
     // node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree): GENERAL flavour, own accumulator
     GsmLeanAccB ST;
@@ -733,7 +752,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         }
         const uint32_t chk = __shfl_sync(0xffffffffu, uv, 16), chk_n = __shfl_sync(0xffffffffu, uv, 17),
                        chk_len = __shfl_sync(0xffffffffu, uv, 18), hmax = __shfl_sync(0xffffffffu, uv, 19);
-        bool bad = chk >= GSM_CHK_LIMIT || chk_n != 0u ||
+        bool bad = chk >= GSM_CHK_LIMIT || (c.use_counts && chk_n > static_cast<uint32_t>(GSM_LEAN_MAX_NST)) ||
                    (!general && chk_len >= GSM_CHK_LIMIT) || hmax >= 0x7ff00000u;
         if (!bad) bad = !(K.c1 * __hiloint2double(static_cast<int>(hmax) + 1, 0) < 700.0);   // exp(-c1 h) stays in range
         if (bad) {
@@ -837,8 +856,9 @@ cudaError_t gsm_init_tables() {
 size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
-static size_t lean_smem_bytes(int64_t stride) {
-    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + GSM_LEAN_MTAB_N * sizeof(GsmLogEntry);
+static size_t lean_smem_bytes(int64_t stride, int block) {
+    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + (GSM_LEAN_MTAB_N + 1) * sizeof(GsmLogEntry) +
+           static_cast<size_t>(block) * 80u;   // + two prefetch stages of 40 bytes per thread
 }
 
 template <typename KERN>
@@ -867,7 +887,7 @@ static cudaError_t launch_generic(const GsmBatch& b, double* o, double* r, doubl
 
 template <int BLOCK, int MINB>
 static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
-    const size_t smem = lean_smem_bytes(b.stride);
+    const size_t smem = lean_smem_bytes(b.stride, BLOCK);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
     int32_t* cnt = sc.redo + (sc.epoch & 1);

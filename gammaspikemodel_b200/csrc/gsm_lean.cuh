@@ -24,8 +24,8 @@
 
 #include "gsm_node_math.cuh"
 
-#define GSM_LEAN_MAX_NST 31      // stub counts handled by the tables of the lean path (0..31)
-#define GSM_LEAN_MTAB_N 33       // m = 0..32 spikes on a branch
+#define GSM_LEAN_MAX_NST 63      // stub counts handled by the tables of the lean path (0..63); beyond: generic path
+#define GSM_LEAN_MTAB_N 65       // m = 0..64 spikes on a branch
 #define GSM_LEAN_MAX_NODES 32767 // parent index is 15 bits of the packed word
 
 // one contiguous block of constant tables; the device copy is brought into shared memory by one TMA bulk copy per CTA
@@ -102,12 +102,10 @@ struct GsmLeanC {
     // pass B
     double kEh;        // (lambda + mu + psi - c1) / 2: E/2 = len * kEh + (aux - aux_parent)   (STP:749-769 via aux)
     double shape, base, eff_mean;
-    double log_shape;          // only for branches with more than GSM_LEAN_MAX_NST stubs (gsm_lean_big_count)
-    const double* logfact;     // sum_{i=2..n} log(i), n < GSM_LOGFACT_N (same use)
     const GsmLogEntry* logtab;
     const uint64_t* exptab;
     const GsmLogEntry* stubtab;
-    const GsmLogEntry* mtab;   // per tree: {shape*m - 1, log(shape) - logGamma(shape*m)}, m = 0..32
+    const GsmLogEntry* mtab;   // per tree: {shape*m - 1, log(shape) - logGamma(shape*m)}, m = 0..64
     int32_t L;                 // leaves are nodes 0..L-1
     int32_t leaf_term;         // 0: none, 1: psi > 0 (STP:337-343), 2: origin / root conditioned (STP:467-474)
     bool use_counts;           // stub counts exist (COUNTS / EXACT); else getNStubsOnBranch == -1 (Stubs:348-350)
@@ -180,30 +178,6 @@ GSM_HD void gsm_lean_leaf_term(const GsmLeanC& c, GsmLeanAccA& S, bool leaf_not_
 }
 
 // ---- pass B -----------------------------------------------------------------------------------------------------
-// A branch with more stubs than the tables hold (rare: long branches near the root): the two table entries are
-// computed on the spot.  On the device the two transcendental parts are out-of-line calls that return their
-// value in registers (no local-memory traffic in the hot loop, which would share a scoreboard with the prefetch).
-#if defined(__CUDACC__)
-static __device__ __noinline__ double gsm_lean_big_lgc_d(double shape, double log_shape, int32_t m) {
-    return log_shape - gsm_log_gamma(shape * m);
-}
-static __device__ __noinline__ double gsm_lean_big_nlf_d(const double* __restrict__ logfact, int32_t nst) {
-    return -gsm_logfact(logfact, nst);
-}
-#endif
-GSM_HD void gsm_lean_big_count(double shape, double log_shape, int32_t m, int32_t nst, const double* __restrict__ logfact,
-                               GsmLogEntry& me, GsmLogEntry& se) {
-    me.invc = shape * m - 1;
-    se.invc = (double)nst;
-#if defined(__CUDA_ARCH__)
-    me.logc = gsm_lean_big_lgc_d(shape, log_shape, m);
-    se.logc = gsm_lean_big_nlf_d(logfact, nst);
-#else
-    me.logc = log_shape - gsm_log_gamma(shape * m);
-    se.logc = -gsm_logfact(logfact, nst);
-#endif
-}
-
 struct GsmLeanAccB {
     double gam;        // sum  log(x shape) (shape m - 1) + log(shape) - logGamma(shape m)        (BSP:97-99 without - x shape)
     double spk;        // sum of spikes                                                           (x shape term; burst in CLEAN)
@@ -218,7 +192,7 @@ struct GsmLeanAccB {
     int32_t n_nst;     // sum of stub counts
     int32_t n_extant, n_extinct, n_da, n_fake;
     uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
-    uint32_t chk_n;    // nonzero when a stub count is negative
+    uint32_t chk_n;    // max stub count as unsigned (negative counts become huge)
     uint32_t chk_len;  // CLEAN: specialness of len (zero / negative lengths -> rerun as GENERAL)
 };
 GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
@@ -258,12 +232,9 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
     // table entries of this branch's spike count m and stub count n
     const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
     const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
-    GsmLogEntry me = c.mtab[mi];                        // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
-    GsmLogEntry se = c.stubtab[ni];                     // {(double)n, -log(n!)}
-    if (c.use_counts && (uint32_t)nst > (uint32_t)GSM_LEAN_MAX_NST) {   // rare
-        if (nst < 0) S.chk_n = 1u;                      // not a count: generic path
-        else gsm_lean_big_count(c.shape, c.log_shape, m, nst, c.logfact, me, se);
-    }
+    const GsmLogEntry me = c.mtab[mi];                  // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
+    const GsmLogEntry se = c.stubtab[ni];               // {(double)n, -log(n!)}
+    if (c.use_counts) S.chk_n = gsm_umax(S.chk_n, (uint32_t)nst);   // above GSM_LEAN_MAX_NST: tree goes to the generic path
 
     // ---- BranchRatePrior BRP:43-60 ----
     S.chk = gsm_umax(S.chk, gsm_chk_pos(rate));

@@ -170,7 +170,6 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
     c.logtab = g_blob.logtab; c.exptab = g_blob.exptab; c.stubtab = g_blob.stubtab; c.mtab = mtab;
-    c.log_shape = gsm_log(K.shape); c.logfact = g_logfact_host;
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     std::vector<double> aux(n);
@@ -207,7 +206,7 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     gsm_lean_combine<true>(K, c, SA0, ST, t6);
     s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
     const uint32_t chk = gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk), chk_n = gsm_umax(SB.chk_n, ST.chk_n);
-    bool redo = chk >= GSM_CHK_LIMIT || chk_n != 0u ||
+    bool redo = chk >= GSM_CHK_LIMIT || (c.use_counts && chk_n > (uint32_t)GSM_LEAN_MAX_NST) ||
                 (!general && SB.chk_len >= GSM_CHK_LIMIT) || SA.hmax >= 0x7ff00000u;
     if (!redo) redo = !(K.c1 * gsm_hilo((int32_t)SA.hmax + 1, 0) < 700.0);
     if (redo) return false;
