@@ -118,19 +118,6 @@ static __device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y)
 static __device__ __forceinline__ void sts_v4u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-// per-thread asynchronous global -> shared copies (LDGSTS): the prefetch of pass B.  They complete in groups
-// (commit / wait_group), not through register scoreboards, so an in-flight prefetch never stalls an unrelated load.
-static __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-static __device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-static __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 static __device__ __forceinline__ int2 lds_v2s32(uint32_t a) {
     int2 v;
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -488,41 +475,61 @@ static __device__ __forceinline__ bool lean_pass_a(const GsmLeanC& c, GsmLeanAcc
     return anyda;
 }
 
-// a_ring: two stages of BLOCK * 40 bytes: per stage [rate pairs: BLOCK x 16 B][spike pairs: BLOCK x 16 B][stub-count
-// pairs: BLOCK x 8 B]; every thread copies and reads only its own slots, so no barrier is involved.
-template <bool GENERAL, bool WANT_RATES, int BLOCK>
-static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, const GsmBatch& b, int64_t row, int n,
-                                                   int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w, uint32_t a_ring,
-                                                   double* __restrict__ out_rates, double* __restrict__ out_wspikes) {
-    const double2* rate2 = reinterpret_cast<const double2*>(b.rate + row);
-    const double2* spike2 = reinterpret_cast<const double2*>(b.spike + row);
-    const int2* nst2 = c.use_counts ? reinterpret_cast<const int2*>(b.nstubs + row) : nullptr;
-    double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
-    double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
-    const int npairs = (n - 1) >> 1;   // main loop: nodes 0 .. n-2 (n is odd)
-    constexpr uint32_t STAGE = BLOCK * 40u;
-    const uint32_t slot = a_ring + tid * 16u;   // rate; spike at + BLOCK*16; counts at + BLOCK*32 - tid*8
+// ---- pass B: the branch rows (rate, spike, stub count) are prefetched one strip ahead with per-thread asynchronous
+// copies (LDGSTS) into a two-stage ring: every thread copies and later reads only its own slots, so no barrier is
+// involved, and completion goes through async groups, not through register scoreboards (an in-flight register
+// prefetch would stall unrelated shared-memory loads that happen to share its scoreboard).
+// Stage layout: [rate pairs: BLOCK x 16 B][spike pairs: BLOCK x 16 B][stub-count pairs: BLOCK x 8 B].
+static __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
-    auto fetch = [&](int j, uint32_t st) {
-        if (j < npairs) {
-            cp_async_16(slot + st, rate2 + j);
-            cp_async_16(slot + st + BLOCK * 16u, spike2 + j);
-            if (nst2) cp_async_8(slot + st + BLOCK * 32u - tid * 8u, nst2 + j);
-        }
-        cp_async_commit();
-    };
-    uint32_t st = 0u;
-    int j = tid;
-    fetch(j, st);
+struct LeanRing {
+    uint32_t slot;       // shared-window address of this thread's rate slot in stage 0
+    uint32_t st;         // byte offset of the current stage (0 or STAGE)
+    const double2* rate; // row pointers (pairs)
+    const double2* spike;
+    const int2* nst;     // nullptr: no stub counts
+};
+struct LeanSpan { int first, end; };   // pairs [first, end)
+
+template <bool STDW, int BLOCK>
+static __device__ __forceinline__ void ring_fetch(const LeanRing& rg, uint32_t st, int j, bool on, int tid) {
+    if (on) {
+        cp_async_16(rg.slot + st, rg.rate + j);
+        cp_async_16(rg.slot + st + BLOCK * 16u, rg.spike + j);
+        if (STDW || rg.nst) cp_async_8(rg.slot + st + BLOCK * 32u - tid * 8u, rg.nst + j);
+    }
+    cp_async_commit();
+}
+
+// one span (all leaf pairs or all internal pairs) of the main loop.  On entry this thread's first pair of the span
+// is in flight in stage rg.st; `next`: the span whose first pair is prefetched during this span's last strip.
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int BLOCK>
+static __device__ __forceinline__ void lean_pass_b_span(const GsmLeanC& c, GsmLeanAccB& SB, LeanRing& rg, const LeanSpan sp,
+                                                        const LeanSpan* next, int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
+                                                        double2* __restrict__ orate2, double2* __restrict__ owsp2) {
+    constexpr uint32_t STAGE = BLOCK * 40u;
 #pragma unroll 1
-    for (; j < npairs; j += BLOCK) {
-        fetch(j + BLOCK, st ^ STAGE);   // the strip after this one
+    for (int j = sp.first + tid; j < sp.end; j += BLOCK) {
+        const int jn = j + BLOCK;
+        if (jn < sp.end || !next) ring_fetch<STDW, BLOCK>(rg, rg.st ^ STAGE, jn, jn < sp.end, tid);
+        else ring_fetch<STDW, BLOCK>(rg, rg.st ^ STAGE, next->first + tid, next->first + tid < next->end, tid);
         cp_async_wait<1>();             // this strip has landed
-        const double2 rr = lds_v2f64(slot + st);
-        const double2 ss = lds_v2f64(slot + st + BLOCK * 16u);
+        const uint32_t slot = rg.slot + rg.st;
+        const double2 rr = lds_v2f64(slot);
+        const double2 ss = lds_v2f64(slot + BLOCK * 16u);
         int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
-        if (nst2) kk = lds_v2s32(slot + st + BLOCK * 32u - tid * 8u);
-        st ^= STAGE;
+        if (STDW || rg.nst) kk = lds_v2s32(slot + BLOCK * 32u - tid * 8u);
+        rg.st ^= STAGE;
         const double2 h2 = lds_v2f64(a_h + j * 16);
         const double2 a2 = lds_v2f64(a_aux + j * 16);
         const uint32_t w2 = lds_u32(a_w + j * 4);
@@ -536,13 +543,35 @@ static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAcc
             wp1 = lds_u16(a_w + p1 * 2);
         }
         double er[2], ew[2];
-        gsm_lean_b_node<GENERAL, WANT_RATES>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
-        gsm_lean_b_node<GENERAL, WANT_RATES>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1], &ew[1]);
+        gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0],
+                                                         &ew[0]);
+        gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y,
+                                                         &er[1], &ew[1]);
         if (WANT_RATES) {
             if (orate2) orate2[j] = make_double2(er[0], er[1]);
             if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
         }
     }
+}
+
+// main loop of pass B: leaf pairs [0, L/2), then internal pairs [(L+1)/2, (n-1)/2).  A pair that straddles L and
+// node n-1 are the tail (see the kernel).
+template <bool GENERAL, bool WANT_RATES, bool STDW, int BLOCK>
+static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, LeanRing& rg, int n, int tid, uint32_t a_h,
+                                                   uint32_t a_aux, uint32_t a_w, double2* __restrict__ orate2,
+                                                   double2* __restrict__ owsp2) {
+    const int L = c.L;
+    LeanSpan leaf, inner;
+    leaf.first = 0;
+    leaf.end = L >> 1;
+    inner.first = (L + 1) >> 1;
+    inner.end = (n - 1) >> 1;
+    rg.st = 0u;
+    if (leaf.end > 0) ring_fetch<STDW, BLOCK>(rg, 0u, tid, tid < leaf.end, tid);
+    else ring_fetch<STDW, BLOCK>(rg, 0u, inner.first + tid, inner.first + tid < inner.end, tid);
+    if (leaf.end > 0)
+        lean_pass_b_span<GENERAL, WANT_RATES, 1, STDW, BLOCK>(c, SB, rg, leaf, &inner, tid, a_h, a_aux, a_w, orate2, owsp2);
+    lean_pass_b_span<GENERAL, WANT_RATES, 0, STDW, BLOCK>(c, SB, rg, inner, nullptr, tid, a_h, a_aux, a_w, orate2, owsp2);
     cp_async_wait<0>();
 }
 
@@ -607,7 +636,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
-    const uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w), a_ring = smem_u32(sh_ring);
+    // shared-window base addresses, made opaque so that they stay in registers instead of being re-derived in the loops
+    uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w), a_ring = smem_u32(sh_ring);
+    asm volatile("" : "+r"(a_h), "+r"(a_aux), "+r"(a_w), "+r"(a_ring));
     if (setup_warp) {
         // {shape m - 1, log shape - logGamma(shape m)}, m = lane + 1 (BSP:97-99 with the Lanczos logGamma of commons-math)
         const double shape = K.shape;
@@ -682,35 +713,53 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     // ---- phase 3: pass B ----
     GsmLeanAccB SB;
     gsm_lean_acc_b_zero(SB);
-    GsmLean6 s6;
+    LeanRing rg;
+    rg.slot = a_ring + tid * 16u;
+    rg.st = 0u;
+    rg.rate = reinterpret_cast<const double2*>(b.rate + row);
+    rg.spike = reinterpret_cast<const double2*>(b.spike + row);
+    rg.nst = c.use_counts ? reinterpret_cast<const int2*>(b.nstubs + row) : nullptr;
+    double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
+    double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
+    const bool stdw = gsm_lean_std_wiring(c);
     if (general) {
-        lean_pass_b<true, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, a_ring, out_rates, out_wspikes);
+        if (stdw) lean_pass_b<true, WANT_RATES, true, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
+        else lean_pass_b<true, WANT_RATES, false, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
     } else {
-        lean_pass_b<false, WANT_RATES, BLOCK>(c, SB, b, row, n, tid, a_h, a_aux, a_w, a_ring, out_rates, out_wspikes);
+        if (stdw) lean_pass_b<false, WANT_RATES, true, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
+        else lean_pass_b<false, WANT_RATES, false, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
     }
-    // node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree): GENERAL flavour, own accumulator
+    // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree), the pair that
+    // straddles L: GENERAL flavour, own accumulator, two lanes of the last warp ----
     GsmLeanAccB ST;
     gsm_lean_acc_b_zero(ST);
-    if (tid == BLOCK - 1) {
-        const int i = n - 1;
-        const uint32_t w = sh_w[i];
-        const int p = static_cast<int>(w & 0x7fffu);
-        const int32_t nst = (b.stub_mode == GSM_STUBS_EXACT && b.nstubs) ? __ldg(b.nstubs + row + i) : 0;
-        double er, ew;
-        gsm_lean_b_node<true, WANT_RATES>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p], __ldg(b.rate + row + i),
-                                          __ldg(b.spike + row + i), nst, &er, &ew);
-        if (WANT_RATES) {
-            if (out_rates) out_rates[row + i] = er;
-            if (out_wspikes) out_wspikes[row + i] = ew;
+    if (warp == NWARP - 1 && lane >= 30) {
+        int i0 = 0, cnt = 0;
+        if (lane == 31) { i0 = n - 1; cnt = 1; }
+        else if (L & 1) { i0 = L - 1; cnt = 2; }
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const int i = i0 + k;
+            const uint32_t w = sh_w[i];
+            const int p = static_cast<int>(w & 0x7fffu);
+            int32_t nst = -1;
+            if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? __ldg(b.nstubs + row + i) : 0;
+            double er, ew;
+            gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p],
+                                                        __ldg(b.rate + row + i), __ldg(b.spike + row + i), nst, &er, &ew);
+            if (WANT_RATES) {
+                if (out_rates) out_rates[row + i] = er;
+                if (out_wspikes) out_wspikes[row + i] = ew;
+            }
         }
     }
+    GsmLean6 s6;
     if (general) {
-        SB.gam += ST.gam; SB.spk += ST.spk; SB.spk_el += ST.spk_el; SB.lr += ST.lr; SB.lr2 += ST.lr2; SB.stub += ST.stub;
-        SB.nlf += ST.nlf; SB.len += ST.len; SB.dA += ST.dA; SB.lenr += ST.lenr; SB.auxint += ST.auxint; SB.hint += ST.hint;
-        SB.auxfake += ST.auxfake; SB.hfake += ST.hfake;
         gsm_lean_combine<true>(K, c, SA, SB, s6);
     } else {
         gsm_lean_combine<false>(K, c, SA, SB, s6);
+    }
+    if (warp == NWARP - 1 && lane >= 30) {
         GsmLean6 t6;
         GsmLeanAccA SA0;
         gsm_lean_acc_a_zero(SA0);
@@ -721,10 +770,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     // ---- phase 4: reductions (fixed order) ----
     const double v0 = warp_sum(s6.tree), v1 = warp_sum(s6.stub), v2 = warp_sum(s6.spike), v3 = warp_sum(s6.rate),
                  v4 = warp_sum(s6.burst), v5 = warp_sum(s6.dist);
-    const int32_t c0 = __reduce_add_sync(0xffffffffu, SB.n_nst + ST.n_nst), c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm),
+    const int32_t c0 = 0, c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm),
                   c2 = __reduce_add_sync(0xffffffffu, SA.n_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + ST.n_fake),
-                  c4 = __reduce_add_sync(0xffffffffu, SB.n_extant), c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct),
-                  c6 = __reduce_add_sync(0xffffffffu, SB.n_da);
+                  c4 = __reduce_add_sync(0xffffffffu, SB.n_extant + ST.n_extant),
+                  c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct + ST.n_extinct), c6 = __reduce_add_sync(0xffffffffu, SB.n_da + ST.n_da);
     const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk)),
                    u1 = warp_max_u32(gsm_umax(SB.chk_n, ST.chk_n)), u2 = warp_max_u32(SB.chk_len), u3 = warp_max_u32(SA.hmax);
     if (lane == 0) {
@@ -960,9 +1009,7 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
         if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
 #define GSM_CFG(B, M) \
     if (block == B && minb == M) e = launch_lean<B, M>(b, sc, d_out_rates, d_out_wspikes, stream);
-        GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
-        GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
-        GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
+        GSM_CFG(128, 6) GSM_CFG(128, 4) GSM_CFG(256, 3) GSM_CFG(256, 2) GSM_CFG(288, 2) GSM_CFG(384, 2) GSM_CFG(512, 1)
 #undef GSM_CFG
         if (e != cudaSuccess) return -static_cast<int>(e);
         if (b.n_nodes <= 2048) e = launch_post<256, 3>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);

@@ -75,6 +75,22 @@ GSM_HD double gsm_log9(double x, const GsmLogEntry* __restrict__ tab) {
     return hp + y;
 }
 
+// log(x) = lz + k ln2 with the k ln2 part left to the caller (sums of logs collect k in integer accumulators)
+GSM_HD double gsm_log9_split(double x, const GsmLogEntry* __restrict__ tab, int32_t& k) {
+    const int32_t hi = gsm_hi32(x);
+    const int32_t tmp = hi - 0x3fe60000;
+    const int32_t i = (tmp >> 11) & (GSM_LOG9_TAB_N - 1);
+    k = tmp >> 20;   // arithmetic
+    const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
+    const GsmLogEntry e = tab[i];
+    const double r = fma(z, e.invc, -1.0);
+    const double r2 = r * r;
+    double p = fma(-0.25, r, GSM_LK(GSM_LK_THIRD));
+    p = fma(p, r, -0.5);
+    const double y = fma(p, r2, r);
+    return e.logc + y;
+}
+
 GSM_HD double gsm_exp9(double x, const uint64_t* __restrict__ tab) {
     double kd = fma(x, GSM_LK(GSM_LK_INVLN2N), GSM_LK(GSM_LK_SHIFT));
     const int32_t ki = gsm_lo32(kd);
@@ -189,7 +205,8 @@ struct GsmLeanAccB {
     double lenr;       // sum len * r                                                             (SPL:44-49 / PRCM:233)
     double auxint, hint;     // sums over internal nodes of aux, h
     double auxfake, hfake;   // GENERAL: the same over fake internal nodes
-    int32_t n_nst;     // sum of stub counts
+    int32_t k_mk, k_k; // sum m_i k_i, sum k_i with k_i the binary exponent of x_i shape: ln2 (shape k_mk - k_k) belongs to gam
+    int32_t k_nk;      // sum n_i (k_i + 1) with k_i the binary exponent of E_i / 2: ln2 k_nk belongs to stub
     int32_t n_extant, n_extinct, n_da, n_fake;
     uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
     uint32_t chk_n;    // max stub count as unsigned (negative counts become huge)
@@ -198,22 +215,28 @@ struct GsmLeanAccB {
 GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
     S.gam = S.spk = S.spk_el = S.lr = S.lr2 = S.stub = S.nlf = S.len = S.dA = S.lenr = 0.0;
     S.auxint = S.hint = S.auxfake = S.hfake = 0.0;
-    S.n_nst = S.n_extant = S.n_extinct = S.n_da = S.n_fake = 0;
+    S.k_mk = S.k_k = S.k_nk = S.n_extant = S.n_extinct = S.n_da = S.n_fake = 0;
     S.chk = S.chk_n = S.chk_len = 0u;
 }
 
-// One node i < n-1.  w: own packed word (parent index | FAKE << 15), wp: the parent's word (GENERAL only).
-template <bool GENERAL, bool WANT_RATES>
+// One node i.  w: own packed word (parent index | FAKE << 15), wp: the parent's word (GENERAL only).
+//   GENERAL  false: ordinary tree (no zero-length branch in the main loop); true: any tree
+//   LEAF     1: i < L, 0: i >= L (compile-time for the split loops), 2: decided here
+//   STDW     the default wiring (stub counts wired to clock model, spike prior and tree prior; relaxed clock) is
+//            compiled in; false: the wiring is read from c
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
 GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32_t w, uint32_t wp, double h, double hp,
                             double aux, double auxp, double rate, double spike, int32_t nst_raw, double* out_rate,
                             double* out_wspike) {
+    const bool use_counts = STDW || c.use_counts, s2p = STDW || c.s2p, s2c = STDW || c.s2c, stub_term = STDW || c.stub_term,
+               use_rate = STDW || c.use_rate;
     const double len = hp - h;                          // a root points to itself: 0
     const double dA = aux - auxp;
     const double E2 = fma(len, c.kEh, dA);              // half the expected stub count (STP:749-769)
     const bool have_len = len > 0.0;                    // STP:558 / PRCM:229
-    const int32_t nst = c.use_counts ? nst_raw : -1;    // Stubs:344-370 (i < n-1 here)
-    const int32_t ns = c.s2p ? nst : 0;                 // BSP:81
-    const bool leaf = i < c.L;
+    const int32_t nst = use_counts ? nst_raw : -1;      // Stubs:344-370
+    const int32_t ns = s2p ? nst : 0;                   // BSP:81
+    const bool leaf = LEAF == 2 ? (i < c.L) : (LEAF == 1);
     int32_t m = ns + 1;                                 // BSP:197-213
     bool da = false, pf = false, fake_self = false;
     if (GENERAL) {
@@ -225,16 +248,14 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
         m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
         if (!(have_len || zero)) S.chk = 0xffffffffu;                                   // negative / NaN length
         if (m == 0 && spike != 0.0) S.chk = 0xffffffffu;                                // BSP:86-95 -> -inf
-        if (c.stub_term && !have_len && nst != 0) S.chk = 0xffffffffu;                  // STP:232-240, 558-561
+        if (stub_term && !have_len && nst != 0) S.chk = 0xffffffffu;                    // STP:232-240, 558-561
     } else {
         S.chk_len = gsm_umax(S.chk_len, gsm_chk_pos(len));
     }
     // table entries of this branch's spike count m and stub count n
     const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
-    const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
     const GsmLogEntry me = c.mtab[mi];                  // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
-    const GsmLogEntry se = c.stubtab[ni];               // {(double)n, -log(n!)}
-    if (c.use_counts) S.chk_n = gsm_umax(S.chk_n, (uint32_t)nst);   // above GSM_LEAN_MAX_NST: tree goes to the generic path
+    if (use_counts) S.chk_n = gsm_umax(S.chk_n, (uint32_t)nst);   // above GSM_LEAN_MAX_NST: tree goes to the generic path
 
     // ---- BranchRatePrior BRP:43-60 ----
     S.chk = gsm_umax(S.chk, gsm_chk_pos(rate));
@@ -246,28 +267,34 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
     const double xs = spike * c.shape;
     const double arg_s = (GENERAL && m == 0) ? 1.0 : xs;
     S.chk = gsm_umax(S.chk, gsm_chk_pos(arg_s));
-    const double lxs = gsm_log9(arg_s, c.logtab);
-    S.gam += fma(lxs, me.invc, me.logc);
+    int32_t ks;
+    const double lzs = gsm_log9_split(arg_s, c.logtab, ks);
+    S.gam += fma(lzs, me.invc, me.logc);
+    S.k_mk += m * ks;
+    S.k_k += ks;
     S.spk += spike;
 
     // ---- stub density, count mode: STP:555-571 / 621-637 ----
-    if (c.stub_term) {
+    if (stub_term) {
+        const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
+        const GsmLogEntry se = c.stubtab[ni];           // {(double)n, -log(n!)}
         const uint32_t chkE = gsm_chk_pos(E2);
         S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
-        const double lE = gsm_log9(E2, c.logtab);       // finite garbage when E2 == 0 (len == 0): multiplied by n = 0
-        S.stub = fma(se.invc, lE, S.stub);
+        int32_t ke;
+        const double lzE = gsm_log9_split(E2, c.logtab, ke);   // finite garbage when E2 == 0 (len == 0): multiplied by n = 0
+        S.stub = fma(se.invc, lzE, S.stub);
         S.nlf += se.logc;
-        S.n_nst += nst;
+        S.k_nk += nst * (ke + 1);
     }
     S.len += len;
     S.dA += dA;
 
     // ---- clock model: SPL sums, optional per-branch outputs (PRCM:178-242, SPL:33-61) ----
-    const double r = c.use_rate ? rate : 1.0;           // PRCM:210-222
+    const double r = use_rate ? rate : 1.0;             // PRCM:210-222
     S.lenr = fma(len, r, S.lenr);                       // len == 0 for every ineligible branch
     double bsp = spike;
     if (GENERAL) {
-        if (pf && (!c.s2c || nst == 0)) bsp = 0.0;      // PRCM:192-202
+        if (pf && (!s2c || nst == 0)) bsp = 0.0;        // PRCM:192-202
         S.spk_el += have_len ? bsp : 0.0;
     }
     if (WANT_RATES) {
@@ -280,15 +307,27 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
 
     // ---- census of the leaves (STP:190-195, 291-312, 352-359) / sums over internal nodes ----
     if (leaf) {
-        const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
-        const bool ext = !low && (len > GSM_LK(GSM_LK_LEAF_EPS));
         if (GENERAL) {
+            const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
+            const bool ext = !low && (len > GSM_LK(GSM_LK_LEAF_EPS));
             S.n_da += da ? 1 : 0;
             S.n_extant += (!da && low) ? 1 : 0;
             S.n_extinct += (!da && ext) ? 1 : 0;
         } else {
-            S.n_extant += low ? 1 : 0;
-            S.n_extinct += ext ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+            // two compares, two predicated increments
+            asm("{\n\t.reg .pred lo, ex;\n\t"
+                "setp.le.f64 lo, %2, %4;\n\t"
+                "setp.gt.and.f64 ex, %3, %4, !lo;\n\t"
+                "@lo add.s32 %0, %0, 1;\n\t"
+                "@ex add.s32 %1, %1, 1;\n\t}"
+                : "+r"(S.n_extant), "+r"(S.n_extinct)
+                : "d"(h), "d"(len), "d"(GSM_LK(GSM_LK_LEAF_EPS)));
+#else
+            const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
+            if (low) S.n_extant++;
+            else if (len > GSM_LK(GSM_LK_LEAF_EPS)) S.n_extinct++;
+#endif
         }
     } else {
         S.auxint += aux;
@@ -300,6 +339,8 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
         }
     }
 }
+
+GSM_HD bool gsm_lean_std_wiring(const GsmLeanC& c) { return c.use_counts && c.s2p && c.s2c && c.stub_term && c.use_rate; }
 
 // per-thread combination of the factor sums into the six result sums (constants per node are added once per tree
 // by gsm_lean_finish).  spk_el: in CLEAN every main-loop node is eligible.
@@ -314,8 +355,9 @@ GSM_HD void gsm_lean_combine(const GsmTreeConsts& K, const GsmLeanC& c, const Gs
     else if (variant == GSM_TV_NO_PSI) tree = -(K.lmm * h_nf) - 2 * aux_nf;                  // STP:371-377
     else if (variant == GSM_TV_PSI || variant == GSM_TV_CONDITIONED) tree = -(K.c1 * h_nf) - 2 * aux_nf + SA.leafterm;
     o.tree = tree;
-    o.stub = (S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);                                 // sum n log(E/2) - log n! - E
-    o.spike = S.gam - c.shape * S.spk;
+    const double ln2 = 0.69314718055994530942;
+    o.stub = fma(ln2, (double)S.k_nk, S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);         // sum n log E - log n! - E
+    o.spike = fma(ln2, fma(c.shape, (double)S.k_mk, -(double)S.k_k), S.gam) - c.shape * S.spk;
     o.rate = -K.inv_2s2 * (S.lr2 - 2 * K.m_ln * S.lr) - S.lr;                                // sum -(lr - m)^2/(2 s^2) - lr, without n m^2
     o.burst = c.eff_mean * (GENERAL ? S.spk_el : S.spk);
     o.dist = c.base * S.lenr;
@@ -340,7 +382,8 @@ GSM_HD void gsm_lean_finish(const GsmTreeConsts& K, const GsmLeanC& c, const Gsm
         default: tree = 0.0; break;
     }
     A.tree += tree;
-    if (c.stub_term) A.stub += r.stub + n_nst * 0.69314718055994530942;
+    (void)n_nst;
+    if (c.stub_term) A.stub += r.stub;
     A.spike += r.spike;
     A.rate += r.rate - nb * (K.inv_2s2 * K.m_ln * K.m_ln + K.log_s_sqrt2pi);
     A.burst += r.burst;

@@ -128,14 +128,34 @@ static void init_blob() {
     g_blob_init = true;
 }
 
-template <bool GENERAL, bool WANT>
-static void lean_b_all(const GsmLeanC& c, GsmLeanAccB& SB, int n, const double* h, const double* aux, const uint16_t* w,
-                       const double* rate, const double* spike, const int32_t* nstubs, double* out_rates, double* out_wsp) {
+// main loop of pass B as the kernel splits it: leaf pairs, internal pairs (first pair even), the rest is the tail
+template <bool GENERAL, bool WANT, bool STDW>
+static void lean_b_all(const GsmLeanC& c, GsmLeanAccB& SB, GsmLeanAccB& ST, int n, int32_t stub_mode, const double* h,
+                       const double* aux, const uint16_t* w, const double* rate, const double* spike, const int32_t* nstubs,
+                       double* out_rates, double* out_wsp) {
     double dr, dw;
-    for (int i = 0; i < n - 1; i++) {
+    const int L = c.L;
+    std::vector<char> done(n, 0);
+    auto node = [&](int i, int leaf) {
         const int p = w[i] & 0x7fff;
-        gsm_lean_b_node<GENERAL, WANT>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], nstubs ? nstubs[i] : -1,
-                                       out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
+        const int32_t k = nstubs ? nstubs[i] : -1;
+        double* o_r = out_rates ? out_rates + i : &dr;
+        double* o_w = out_wsp ? out_wsp + i : &dw;
+        if (leaf == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
+        else gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
+        done[i] = 1;
+    };
+    for (int j = 0; j < (L >> 1); j++) { node(2 * j, 1); node(2 * j + 1, 1); }
+    const int first = (L + 1) >> 1;
+    for (int j = first; j < ((n - 1) >> 1); j++) { node(2 * j, 0); node(2 * j + 1, 0); }
+    // tail (GENERAL flavour, runtime leaf test and wiring): everything the two loops left out
+    for (int i = 0; i < n; i++) {
+        if (done[i]) continue;
+        const int p = w[i] & 0x7fff;
+        int32_t k = -1;
+        if (c.use_counts) k = (i < n - 1 || stub_mode == GSM_STUBS_EXACT) ? (nstubs ? nstubs[i] : 0) : 0;
+        gsm_lean_b_node<true, WANT, 2, false>(c, ST, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k,
+                                              out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
     }
 }
 
@@ -189,14 +209,14 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmLeanAccB SB, ST;
     gsm_lean_acc_b_zero(SB);
     gsm_lean_acc_b_zero(ST);
-    if (general) lean_b_all<true, WANT>(c, SB, n, h, aux.data(), w.data(), rate, spike, c.use_counts ? nstubs : nullptr, out_rates, out_wsp);
-    else lean_b_all<false, WANT>(c, SB, n, h, aux.data(), w.data(), rate, spike, c.use_counts ? nstubs : nullptr, out_rates, out_wsp);
-    {
-        const int i = n - 1, p = w[i] & 0x7fff;
-        const int32_t nst = (stub_mode == GSM_STUBS_EXACT && nstubs) ? nstubs[i] : 0;
-        double dr, dw;
-        gsm_lean_b_node<true, WANT>(c, ST, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], nst,
-                                    out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
+    const int32_t* ns = c.use_counts ? nstubs : nullptr;
+    const bool stdw = gsm_lean_std_wiring(c);
+    if (general) {
+        if (stdw) lean_b_all<true, WANT, true>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
+        else lean_b_all<true, WANT, false>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
+    } else {
+        if (stdw) lean_b_all<false, WANT, true>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
+        else lean_b_all<false, WANT, false>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
     }
     GsmLean6 s6, t6;
     GsmLeanAccA SA0;
@@ -219,10 +239,10 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmAcc A;
     gsm_acc_zero(A);
     A.n_leaf = c2.L;
-    A.n_extant = SB.n_extant;
-    A.n_extinct = SB.n_extinct;
-    A.n_da = SB.n_da;
-    gsm_lean_finish(K2, c2, s6, SB.n_nst + ST.n_nst, SA.n_leafterm, SA.n_plain, SB.n_fake + ST.n_fake, n, A);
+    A.n_extant = SB.n_extant + ST.n_extant;
+    A.n_extinct = SB.n_extinct + ST.n_extinct;
+    A.n_da = SB.n_da + ST.n_da;
+    gsm_lean_finish(K2, c2, s6, 0, SA.n_leafterm, SA.n_plain, SB.n_fake + ST.n_fake, n, A);
     gsm_finish_consts(K2, h[root]);
     gsm_finalize(K2, A, n, (w[root] & 0x8000) != 0, out);
     return true;

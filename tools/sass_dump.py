@@ -7,6 +7,6 @@ cur = None
 for l in txt.splitlines():
     m = re.match(r"\s*Function : (\S+)", l)
     if m: cur = m.group(1); continue
-    m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
+    m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
     if m and cur and pat in cur and lo <= int(m.group(1), 16) <= hi:
         print(m.group(1), m.group(2))

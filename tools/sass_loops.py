@@ -8,7 +8,7 @@ cur = None; funcs = collections.OrderedDict()
 for l in txt.splitlines():
     m = re.match(r"\s*Function : (\S+)", l)
     if m: cur = m.group(1); funcs[cur] = []; continue
-    m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
+    m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
     if m and cur: funcs[cur].append((int(m.group(1), 16), m.group(2).strip()))
 for fn, ins in funcs.items():
     if pat not in fn: continue
