@@ -21,7 +21,7 @@
 
 __device__ double g_logfact[GSM_LOGFACT_N];
 // constant tables of the lean path (stubtab is filled by gsm_init_tables)
-__device__ GsmLeanBlob g_lean_blob = {GSM_LOG9_TAB_INIT, GSM_EXP9_TAB_INIT, {}};
+__device__ GsmLeanBlob g_lean_blob;   // replicated log / exp tables, filled by gsm_init_tables
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared::cluster, completion on an mbarrier)
@@ -395,20 +395,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 // ---------------------------------------------------------------------------------------------------------
 // lean kernel: default wiring family (gsm_lean_wiring_ok), one CTA per tree.  See gsm_lean.cuh.
 //   shared memory: height row 8 B/node (TMA) + aux row 8 B/node (first used as the TMA landing zone of the
-//   parent row) + packed word 2 B/node (parent index, FAKE bit) + 12.8 KB of log/exp/stub tables (TMA)
-//   + the per-tree Gamma table.
-//   phase 0  one thread issues three TMA bulk copies; one warp computes the arithmetic-only per-tree
-//            constants and, one m per lane, the table {shape m - 1, log shape - logGamma(shape m)}
+//   parent row) + packed word 2 B/node (parent index, FAKE bit) + 16 KB of replicated log / exp tables (TMA)
+//   + the per-tree Gamma tables + a two-stage ring of branch-row chunks (TMA).
+//   phase 0  one thread issues the TMA bulk copies of the tree rows, the tables and the first two chunks of the
+//            branch rows; one warp computes the arithmetic-only per-tree constants and, one m per lane, the
+//            tables {shape m - 1, log shape - logGamma(shape m)}
 //   phase 1  parents int32 -> packed 16-bit words, validation of BEAST's numbering (eight nodes per step)
 //   phase 2  pass A: aux = log G(h) for node pairs; leaves detect sampled ancestors and mark fake parents
-//   phase 3  pass B: node pairs, 128-bit global / shared loads, one-strip register prefetch;
-//            CLEAN or GENERAL flavour per tree
+//   phase 3  pass B: chunks of 2 BLOCK nodes (one node pair per thread) arrive through the ring: rate / spike /
+//            stub-count rows by TMA into shared memory, full / empty mbarriers, the chunk after next is requested
+//            as soon as every warp has taken its pairs of the previous one; CLEAN or GENERAL flavour per tree
 //   phase 4  per-thread combination to six sums, warp-shuffle + cross-warp reduction, 128-byte scratch row
 // ---------------------------------------------------------------------------------------------------------
 template <int NWARP>
 struct GsmLeanShared {
     GsmTreeConsts K;
-    uint64_t mbar;
+    uint64_t mbar;       // tree rows + tables
+    uint64_t full[2];    // ring: chunk landed
+    uint64_t empty[2];   // ring: every warp has read its pairs of the chunk
     int32_t root, nroot, bad;
     double red[6][NWARP];
     int32_t redi[7][NWARP];
@@ -475,104 +479,120 @@ static __device__ __forceinline__ bool lean_pass_a(const GsmLeanC& c, GsmLeanAcc
     return anyda;
 }
 
-// ---- pass B: the branch rows (rate, spike, stub count) are prefetched one strip ahead with per-thread asynchronous
-// copies (LDGSTS) into a two-stage ring: every thread copies and later reads only its own slots, so no barrier is
-// involved, and completion goes through async groups, not through register scoreboards (an in-flight register
-// prefetch would stall unrelated shared-memory loads that happen to share its scoreboard).
-// Stage layout: [rate pairs: BLOCK x 16 B][spike pairs: BLOCK x 16 B][stub-count pairs: BLOCK x 8 B].
-static __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-static __device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-static __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
+// ---- pass B: the branch rows (rate, spike, stub count) come through a two-stage ring of chunks of 2 BLOCK nodes,
+// filled by TMA bulk copies (full mbarrier: arrive.expect_tx by the producer, complete_tx by the copies) and handed
+// back by one arrive per warp on the empty mbarrier once the warp holds its pairs in registers.
+// Stage layout: [rate: 2 BLOCK x 8 B][spike: 2 BLOCK x 8 B][stub counts: 2 BLOCK x 4 B].
 struct LeanRing {
-    uint32_t slot;       // shared-window address of this thread's rate slot in stage 0
-    uint32_t st;         // byte offset of the current stage (0 or STAGE)
-    const double2* rate; // row pointers (pairs)
-    const double2* spike;
-    const int2* nst;     // nullptr: no stub counts
+    uint32_t a_ring;     // shared-window address of stage 0
+    uint32_t a_full, a_empty;   // ... of full[0], empty[0]
+    const double* rate;  // row pointers
+    const double* spike;
+    const int32_t* nst;  // nullptr: no stub counts
+    int S;               // row pitch in nodes: the last chunk is copied up to the pitch (multiples of 16 bytes)
 };
-struct LeanSpan { int first, end; };   // pairs [first, end)
 
-template <bool STDW, int BLOCK>
-static __device__ __forceinline__ void ring_fetch(const LeanRing& rg, uint32_t st, int j, bool on, int tid) {
-    if (on) {
-        cp_async_16(rg.slot + st, rg.rate + j);
-        cp_async_16(rg.slot + st + BLOCK * 16u, rg.spike + j);
-        if (STDW || rg.nst) cp_async_8(rg.slot + st + BLOCK * 32u - tid * 8u, rg.nst + j);
-    }
-    cp_async_commit();
+static __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GSM_WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GSM_DONEA_%=;\n"
+        "bra GSM_WAITA_%=;\n"
+        "GSM_DONEA_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+static __device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src_gmem),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
-// one span (all leaf pairs or all internal pairs) of the main loop.  On entry this thread's first pair of the span
-// is in flight in stage rg.st; `next`: the span whose first pair is prefetched during this span's last strip.
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int BLOCK>
-static __device__ __forceinline__ void lean_pass_b_span(const GsmLeanC& c, GsmLeanAccB& SB, LeanRing& rg, const LeanSpan sp,
-                                                        const LeanSpan* next, int tid, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
-                                                        double2* __restrict__ orate2, double2* __restrict__ owsp2) {
+// one thread: request chunk ch into stage s
+template <int BLOCK>
+static __device__ __forceinline__ void ring_issue(const LeanRing& rg, int ch, uint32_t s) {
     constexpr uint32_t STAGE = BLOCK * 40u;
-#pragma unroll 1
-    for (int j = sp.first + tid; j < sp.end; j += BLOCK) {
-        const int jn = j + BLOCK;
-        if (jn < sp.end || !next) ring_fetch<STDW, BLOCK>(rg, rg.st ^ STAGE, jn, jn < sp.end, tid);
-        else ring_fetch<STDW, BLOCK>(rg, rg.st ^ STAGE, next->first + tid, next->first + tid < next->end, tid);
-        cp_async_wait<1>();             // this strip has landed
-        const uint32_t slot = rg.slot + rg.st;
-        const double2 rr = lds_v2f64(slot);
-        const double2 ss = lds_v2f64(slot + BLOCK * 16u);
-        int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
-        if (STDW || rg.nst) kk = lds_v2s32(slot + BLOCK * 32u - tid * 8u);
-        rg.st ^= STAGE;
-        const double2 h2 = lds_v2f64(a_h + j * 16);
-        const double2 a2 = lds_v2f64(a_aux + j * 16);
-        const uint32_t w2 = lds_u32(a_w + j * 4);
-        const uint32_t w0 = w2 & 0xffffu, w1 = w2 >> 16;
-        const uint32_t p0 = w0 & 0x7fffu, p1 = w1 & 0x7fffu;
-        const double hp0 = lds_f64(a_h + p0 * 8), hp1 = lds_f64(a_h + p1 * 8);
-        const double ap0 = lds_f64(a_aux + p0 * 8), ap1 = lds_f64(a_aux + p1 * 8);
-        uint32_t wp0 = 0u, wp1 = 0u;
-        if (GENERAL) {
-            wp0 = lds_u16(a_w + p0 * 2);
-            wp1 = lds_u16(a_w + p1 * 2);
-        }
-        double er[2], ew[2];
-        gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0],
-                                                         &ew[0]);
-        gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y,
-                                                         &er[1], &ew[1]);
-        if (WANT_RATES) {
-            if (orate2) orate2[j] = make_double2(er[0], er[1]);
-            if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
-        }
+    const int o = ch * 2 * BLOCK;
+    int cnt = rg.S - o;
+    if (cnt > 2 * BLOCK) cnt = 2 * BLOCK;
+    const uint32_t b8 = static_cast<uint32_t>(cnt) * 8u, b4 = static_cast<uint32_t>(cnt) * 4u;
+    const uint32_t bar = rg.a_full + s * 8u, st = rg.a_ring + s * STAGE;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * b8 + (rg.nst ? b4 : 0u)) : "memory");
+    tma_bulk_g2s_a(st, rg.rate + o, b8, bar);
+    tma_bulk_g2s_a(st + BLOCK * 16u, rg.spike + o, b8, bar);
+    if (rg.nst) tma_bulk_g2s_a(st + BLOCK * 32u, rg.nst + o, b4, bar);
+}
+
+// pairs [0, (n-1)/2) in chunks of BLOCK pairs
+static __device__ __forceinline__ int lean_chunks(int n, int block) { return (((n - 1) >> 1) + block - 1) / block; }
+
+// one node pair j of the main loop
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
+static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccB& SB, int j, const double2 rr, const double2 ss,
+                                                   const int2 kk, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
+                                                   double2* __restrict__ orate2, double2* __restrict__ owsp2) {
+    const double2 h2 = lds_v2f64(a_h + j * 16);
+    const double2 a2 = lds_v2f64(a_aux + j * 16);
+    const uint32_t w2 = lds_u32(a_w + j * 4);
+    const uint32_t w0 = w2 & 0xffffu, w1 = w2 >> 16;
+    const uint32_t p0 = w0 & 0x7fffu, p1 = w1 & 0x7fffu;
+    const double hp0 = lds_f64(a_h + p0 * 8), hp1 = lds_f64(a_h + p1 * 8);
+    const double ap0 = lds_f64(a_aux + p0 * 8), ap1 = lds_f64(a_aux + p1 * 8);
+    uint32_t wp0 = 0u, wp1 = 0u;
+    if (GENERAL) {
+        wp0 = lds_u16(a_w + p0 * 2);
+        wp1 = lds_u16(a_w + p1 * 2);
+    }
+    double er[2], ew[2];
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1],
+                                                     &ew[1]);
+    if (WANT_RATES) {
+        if (orate2) orate2[j] = make_double2(er[0], er[1]);
+        if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
     }
 }
 
-// main loop of pass B: leaf pairs [0, L/2), then internal pairs [(L+1)/2, (n-1)/2).  A pair that straddles L and
-// node n-1 are the tail (see the kernel).
+// main loop of pass B.  Chunks 0 and 1 were requested in phase 0.
 template <bool GENERAL, bool WANT_RATES, bool STDW, int BLOCK>
-static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, LeanRing& rg, int n, int tid, uint32_t a_h,
-                                                   uint32_t a_aux, uint32_t a_w, double2* __restrict__ orate2,
+static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, const LeanRing& rg, int n, int tid,
+                                                   uint32_t a_h, uint32_t a_aux, uint32_t a_w, double2* __restrict__ orate2,
                                                    double2* __restrict__ owsp2) {
+    constexpr uint32_t STAGE = BLOCK * 40u;
     const int L = c.L;
-    LeanSpan leaf, inner;
-    leaf.first = 0;
-    leaf.end = L >> 1;
-    inner.first = (L + 1) >> 1;
-    inner.end = (n - 1) >> 1;
-    rg.st = 0u;
-    if (leaf.end > 0) ring_fetch<STDW, BLOCK>(rg, 0u, tid, tid < leaf.end, tid);
-    else ring_fetch<STDW, BLOCK>(rg, 0u, inner.first + tid, inner.first + tid < inner.end, tid);
-    if (leaf.end > 0)
-        lean_pass_b_span<GENERAL, WANT_RATES, 1, STDW, BLOCK>(c, SB, rg, leaf, &inner, tid, a_h, a_aux, a_w, orate2, owsp2);
-    lean_pass_b_span<GENERAL, WANT_RATES, 0, STDW, BLOCK>(c, SB, rg, inner, nullptr, tid, a_h, a_aux, a_w, orate2, owsp2);
-    cp_async_wait<0>();
+    const int npairs = (n - 1) >> 1;
+    const int nch = lean_chunks(n, BLOCK);
+    const bool counts = STDW || rg.nst != nullptr;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+        const uint32_t s = static_cast<uint32_t>(ch) & 1u;
+        if (tid == 0 && ch >= 1 && ch + 1 < nch) {
+            // stage s ^ 1 held chunk ch - 1: every warp has taken its pairs -> request chunk ch + 1 into it
+            mbar_wait_a(rg.a_empty + (s ^ 1u) * 8u, static_cast<uint32_t>(((ch + 1) >> 1) - 1) & 1u);
+            ring_issue<BLOCK>(rg, ch + 1, s ^ 1u);
+        }
+        mbar_wait_a(rg.a_full + s * 8u, static_cast<uint32_t>(ch >> 1) & 1u);
+        const uint32_t st = rg.a_ring + s * STAGE + tid * 16u;
+        const double2 rr = lds_v2f64(st);
+        const double2 ss = lds_v2f64(st + BLOCK * 16u);
+        int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
+        if (counts) kk = lds_v2s32(st + BLOCK * 32u - tid * 8u);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_a(rg.a_empty + s * 8u);
+        const int j = ch * BLOCK + tid;
+        if (j < npairs) {
+            const int o = ch * 2 * BLOCK;
+            if (o + 2 * BLOCK <= L) lean_b_pair<GENERAL, WANT_RATES, 1, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
+            else if (o >= L) lean_b_pair<GENERAL, WANT_RATES, 0, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
+            else lean_b_pair<GENERAL, WANT_RATES, 2, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
+        }
+    }
 }
 
 template <int BLOCK, int MINB, bool WANT_RATES>
@@ -588,9 +608,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double* sh_h = reinterpret_cast<double*>(smem_raw);
     double* sh_aux = sh_h + S;
     uint16_t* sh_w = reinterpret_cast<uint16_t*>(sh_aux + S);
-    GsmLeanBlob* sh_blob = reinterpret_cast<GsmLeanBlob*>(smem_raw + static_cast<size_t>(S) * 18u);
+    GsmLeanBlob* sh_blob = reinterpret_cast<GsmLeanBlob*>(smem_raw + static_cast<size_t>(S) * 18u);   // S % 32 == 0: 64-byte aligned
     GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_blob + 1);
-    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_mtab + GSM_LEAN_MTAB_N + 1);   // 16-byte aligned
+    GsmLogEntry* sh_ntab = sh_mtab + (GSM_LEAN_MTAB_N + 1);
+    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_ntab + (GSM_LEAN_MAX_NST + 1));   // 16-byte aligned
     GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
@@ -606,10 +627,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     const int64_t row = t * S;
     const int L = (n + 1) >> 1;
+    const int nch = lean_chunks(n, BLOCK);
+
+    LeanRing rg;
+    rg.a_ring = smem_u32(sh_ring);
+    rg.a_full = smem_u32(&sh.full[0]);
+    rg.a_empty = smem_u32(&sh.empty[0]);
+    rg.rate = b.rate + row;
+    rg.spike = b.spike + row;
+    rg.nst = b.stub_mode != GSM_STUBS_NOSTUB ? b.nstubs + row : nullptr;
+    rg.S = S;
 
     // ---- phase 0 ----
     if (tid == 0) {
         mbar_init(&sh.mbar, 1);
+        mbar_init(&sh.full[0], 1);
+        mbar_init(&sh.full[1], 1);
+        mbar_init(&sh.empty[0], NWARP);
+        mbar_init(&sh.empty[1], NWARP);
         fence_mbar_init();
         sh.root = -1;
         sh.nroot = 0;
@@ -623,32 +658,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         tma_bulk_g2s(sh_h, b.height + row, bytes_h, &sh.mbar);
         tma_bulk_g2s(sh_aux, b.parent + row, bytes_p, &sh.mbar);   // landing zone; repacked in phase 1
         tma_bulk_g2s(sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
+        if (nch > 0) ring_issue<BLOCK>(rg, 0, 0u);
+        if (nch > 1) ring_issue<BLOCK>(rg, 1, 1u);
     }
-    // The last warp is the setup warp: per-tree constants now, the Gamma table while the others repack and run pass A.
+    // before any exit from here on: the bulk copies target this CTA's shared memory and must have landed
+    auto drain = [&]() {
+        if (nch > 0) mbar_wait_a(rg.a_full, 0u);
+        if (nch > 1) mbar_wait_a(rg.a_full + 8u, 0u);
+    };
+    // The last warp is the setup warp: per-tree constants now, the Gamma tables while the others repack and run pass A.
     constexpr int NWORK = BLOCK - 32;
     const bool setup_warp = warp == NWARP - 1;
     const double* prm = b.params + t * GSM_NPARAM;
     if (setup_warp && lane == 0)
         gsm_setup_scalars(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
     __syncthreads();
-    mbar_wait(&sh.mbar, 0);   // also before any early exit: the bulk copies target this CTA's shared memory
+    mbar_wait(&sh.mbar, 0);
     if (!gsm_lean_consts_ok(K)) {   // invalid state (lambda <= mu, shape <= 0, ...): the generic path reproduces the reference
+        drain();
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
     // shared-window base addresses, made opaque so that they stay in registers instead of being re-derived in the loops
-    uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w), a_ring = smem_u32(sh_ring);
-    asm volatile("" : "+r"(a_h), "+r"(a_aux), "+r"(a_w), "+r"(a_ring));
+    uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w);
+    asm volatile("" : "+r"(a_h), "+r"(a_aux), "+r"(a_w));
     if (setup_warp) {
-        // {shape m - 1, log shape - logGamma(shape m)}, m = lane + 1 (BSP:97-99 with the Lanczos logGamma of commons-math)
+        // mtab[m] = {shape m - 1, log shape - logGamma(shape m)}, ntab[m - 1] = {log shape - logGamma(shape m), -log((m - 1)!)}
+        // (BSP:97-99 with the Lanczos logGamma of commons-math; STP:567)
         const double shape = K.shape;
         const double lsh = log(shape);
-        GsmLogEntry e;
+        GsmLogEntry e, f;
 #pragma unroll 1
         for (int m = lane + 1; m < GSM_LEAN_MTAB_N; m += 32) {
             e.invc = shape * m - 1;
             e.logc = lsh - lean_log_gamma(shape * m);
             sh_mtab[m] = e;
+            f.invc = e.logc;
+            f.logc = -g_logfact[m - 1];
+            sh_ntab[m - 1] = f;
         }
         if (lane == 0) {
             e.invc = -1.0;
@@ -690,10 +737,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     // ---- phase 2: pass A (workers) ----
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
-    c.logtab = sh_blob->logtab;
-    c.exptab = sh_blob->exptab;
-    c.stubtab = sh_blob->stubtab;
+    c.t6.log_a = smem_u32(sh_blob->logtab);
+    c.t6.exp_a = smem_u32(sh_blob->exptab);
+    c.t6.rep = static_cast<uint32_t>(lane & 15) * 8u;
     c.mtab = sh_mtab;
+    c.ntab = sh_ntab;
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     bool anyda = false;
@@ -704,6 +752,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     const bool any = __syncthreads_or(anyda ? 1 : 0) != 0;
     if (sh.bad || sh.nroot != 1) {
+        drain();
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
@@ -713,12 +762,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     // ---- phase 3: pass B ----
     GsmLeanAccB SB;
     gsm_lean_acc_b_zero(SB);
-    LeanRing rg;
-    rg.slot = a_ring + tid * 16u;
-    rg.st = 0u;
-    rg.rate = reinterpret_cast<const double2*>(b.rate + row);
-    rg.spike = reinterpret_cast<const double2*>(b.spike + row);
-    rg.nst = c.use_counts ? reinterpret_cast<const int2*>(b.nstubs + row) : nullptr;
     double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
@@ -729,28 +772,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         if (stdw) lean_pass_b<false, WANT_RATES, true, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
         else lean_pass_b<false, WANT_RATES, false, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
     }
-    // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree), the pair that
-    // straddles L: GENERAL flavour, own accumulator, two lanes of the last warp ----
+    // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree): GENERAL flavour,
+    // own accumulator, one lane of the last warp ----
     GsmLeanAccB ST;
     gsm_lean_acc_b_zero(ST);
-    if (warp == NWARP - 1 && lane >= 30) {
-        int i0 = 0, cnt = 0;
-        if (lane == 31) { i0 = n - 1; cnt = 1; }
-        else if (L & 1) { i0 = L - 1; cnt = 2; }
-#pragma unroll 1
-        for (int k = 0; k < cnt; k++) {
-            const int i = i0 + k;
-            const uint32_t w = sh_w[i];
-            const int p = static_cast<int>(w & 0x7fffu);
-            int32_t nst = -1;
-            if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? __ldg(b.nstubs + row + i) : 0;
-            double er, ew;
-            gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p],
-                                                        __ldg(b.rate + row + i), __ldg(b.spike + row + i), nst, &er, &ew);
-            if (WANT_RATES) {
-                if (out_rates) out_rates[row + i] = er;
-                if (out_wspikes) out_wspikes[row + i] = ew;
-            }
+    const bool tail_lane = warp == NWARP - 1 && lane == 31;
+    if (tail_lane) {
+        const int i = n - 1;
+        const uint32_t w = sh_w[i];
+        const int p = static_cast<int>(w & 0x7fffu);
+        int32_t nst = -1;
+        if (c.use_counts) nst = b.stub_mode == GSM_STUBS_EXACT ? __ldg(b.nstubs + row + i) : 0;
+        double er, ew;
+        gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p],
+                                                    __ldg(b.rate + row + i), __ldg(b.spike + row + i), nst, &er, &ew);
+        if (WANT_RATES) {
+            if (out_rates) out_rates[row + i] = er;
+            if (out_wspikes) out_wspikes[row + i] = ew;
         }
     }
     GsmLean6 s6;
@@ -759,7 +797,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     } else {
         gsm_lean_combine<false>(K, c, SA, SB, s6);
     }
-    if (warp == NWARP - 1 && lane >= 30) {
+    if (tail_lane) {
         GsmLean6 t6;
         GsmLeanAccA SA0;
         gsm_lean_acc_a_zero(SA0);
@@ -894,20 +932,17 @@ cudaError_t gsm_init_tables() {
     }
     cudaError_t e = cudaMemcpyToSymbol(g_logfact, h, sizeof(h));
     if (e != cudaSuccess) return e;
-    GsmLogEntry st[GSM_LEAN_MAX_NST + 1];
-    for (int i = 0; i <= GSM_LEAN_MAX_NST; i++) {
-        st[i].invc = static_cast<double>(i);
-        st[i].logc = -h[i];
-    }
-    return cudaMemcpyToSymbol(g_lean_blob, st, sizeof(st), offsetof(GsmLeanBlob, stubtab));
+    static GsmLeanBlob blob;
+    gsm_lean_blob_fill(blob);
+    return cudaMemcpyToSymbol(g_lean_blob, &blob, sizeof(blob));
 }
 
 size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
 static size_t lean_smem_bytes(int64_t stride, int block) {
-    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + (GSM_LEAN_MTAB_N + 1) * sizeof(GsmLogEntry) +
-           static_cast<size_t>(block) * 80u;   // + two prefetch stages of 40 bytes per thread
+    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
+           static_cast<size_t>(block) * 80u;   // + two ring stages of 2 BLOCK nodes x 20 bytes
 }
 
 template <typename KERN>

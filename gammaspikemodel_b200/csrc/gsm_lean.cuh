@@ -28,12 +28,35 @@
 #define GSM_LEAN_MTAB_N 65       // m = 0..64 spikes on a branch
 #define GSM_LEAN_MAX_NODES 32767 // parent index is 15 bits of the packed word
 
-// one contiguous block of constant tables; the device copy is brought into shared memory by one TMA bulk copy per CTA
-struct __attribute__((aligned(16))) GsmLeanBlob {
-    GsmLogEntry logtab[GSM_LOG9_TAB_N];       // {invc, logc}
-    uint64_t exptab[GSM_EXP9_TAB_N];          // bits(2^(j/512)) - (j << 43)
-    GsmLogEntry stubtab[GSM_LEAN_MAX_NST + 1];// {(double)n, -sum_{i=2..n} log(i)}  (STP:567 / 633)
+// ---- constant tables of log / exp: 64 entries of 8 bytes, read from 16-fold replicated copies ------------------
+// A table lookup with a data-dependent index is the most expensive instruction of this path when it goes to shared
+// memory as it is: 32 lanes asking for 32 random 16-byte entries cost ~10 shared-memory wavefronts
+// (profiles/r01_v5_lean_ncu_summary.txt: 77 % of the L1/shared pipe, the top unit).  Here every lane of a half-warp
+// owns a replica of the table that lives in its own pair of banks: entry j of replica q is at byte (j * 16 + q) * 8, so
+// an LDS.64 is two wavefronts whatever the indices are.
+//   log: x = 2^k z with z in [c0, 2 c0), c0 ~ 2^(-1/128); entry j (64 linear sub-intervals of z) is invc_j ~ 2^(-i_j/64)
+//        with i_j = round(64 log2(centre_j)) kept in the low 6 bits of the entry itself.  Then
+//            log(x) = (64 k + i_j) ln2/64 + log1p(r),  r = z invc_j - 1,  |r| <= 0.01218,
+//        i.e. no second table for log(c_j), and sums of logs collect the integer part in integer registers.
+//   exp: 2^(j/64); |r| <= ln2/128.
+#define GSM_T6_N 64
+#define GSM_T6_REP 16
+#define GSM_T6_WORDS (GSM_T6_N * GSM_T6_REP)   // uint64 words per replicated table (8 KB)
+
+// device image of both replicated tables (one TMA bulk copy per CTA); filled by gsm_init_tables / the emulator
+struct __attribute__((aligned(128))) GsmLeanBlob {
+    uint64_t logtab[GSM_T6_WORDS];
+    uint64_t exptab[GSM_T6_WORDS];
 };
+static const uint64_t gsm_log6_tab_h[GSM_LOG6_TAB_N] = GSM_LOG6_TAB_INIT;
+static const uint64_t gsm_exp6_tab_h[GSM_EXP6_TAB_N] = GSM_EXP6_TAB_INIT;
+inline void gsm_lean_blob_fill(GsmLeanBlob& b) {
+    for (int j = 0; j < GSM_T6_N; j++)
+        for (int q = 0; q < GSM_T6_REP; q++) {
+            b.logtab[j * GSM_T6_REP + q] = gsm_log6_tab_h[j];
+            b.exptab[j * GSM_T6_REP + q] = gsm_exp6_tab_h[j];
+        }
+}
 
 GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
     const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
@@ -43,10 +66,11 @@ GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
 
 // fp64 constants that do not fit an instruction immediate live in constant memory on the device, so that the hot
 // loops use them as constant-bank operands instead of re-materialising them with moves
-enum { GSM_LK_LN2 = 0, GSM_LK_THIRD, GSM_LK_KBIAS, GSM_LK_INVLN2N, GSM_LK_NLN2HI, GSM_LK_NLN2LO, GSM_LK_SHIFT, GSM_LK_SIXTH,
-       GSM_LK_24TH, GSM_LK_LEAF_EPS, GSM_LK_COND_EPS, GSM_LK_N };
-#define GSM_LK_INIT {GSM_LN2, 1.0 / 3, 4503599627371520.0 /* 2^52 + 1024 */, GSM_EXP9_INVLN2N, GSM_EXP9_NEGLN2HIN, \
-                     GSM_EXP9_NEGLN2LON, 0x1.8p52, 1.0 / 6, 1.0 / 24, GSM_LEAF_EPS, 0.000000000005 /* STP:470 */}
+enum { GSM_LK_LN2_64 = 0, GSM_LK_KBIAS, GSM_LK_INVLN2N, GSM_LK_NLN2N, GSM_LK_SHIFT, GSM_LK_TWO52, GSM_LK_LEAF_EPS, GSM_LK_COND_EPS,
+       GSM_LK_Q3, GSM_LK_Q4 = GSM_LK_Q3 + 4, GSM_LK_E2 = GSM_LK_Q4 + 5, GSM_LK_N = GSM_LK_E2 + 3 };
+#define GSM_LK_INIT {GSM_LN2_64, 4503599628419072.0 /* 2^52 + 2^20 */, GSM_EXP6_INVLN2N, GSM_EXP6_NEGLN2N, 0x1.8p52, 0x1p52, \
+                     GSM_LEAF_EPS, 0.000000000005 /* STP:470 */, \
+                     GSM_LOG6_Q3, GSM_LOG6_Q4, GSM_EXP6_Q2}
 static const double gsm_lean_k_h[GSM_LK_N] = GSM_LK_INIT;
 #if defined(__CUDACC__)
 static __constant__ double gsm_lean_k_d[GSM_LK_N] = GSM_LK_INIT;
@@ -57,53 +81,100 @@ static __constant__ double gsm_lean_k_d[GSM_LK_N] = GSM_LK_INIT;
 #define GSM_LK(i) gsm_lean_k_h[i]
 #endif
 
-// ---- table-driven log / exp on the 512-entry tables (arguments must be "regular": see the chk words) -------------
-GSM_HD double gsm_log9(double x, const GsmLogEntry* __restrict__ tab) {
-    const int32_t hi = gsm_hi32(x);
-    const int32_t tmp = hi - 0x3fe60000;
-    const int32_t i = (tmp >> 11) & (GSM_LOG9_TAB_N - 1);
-    const int32_t k = tmp >> 20;   // arithmetic
-    const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
-    const GsmLogEntry e = tab[i];
-    const double r = fma(z, e.invc, -1.0);
-    const double kd = gsm_hilo(0x43300000, k + 1024) - GSM_LK(GSM_LK_KBIAS);   // (double)k
-    const double hp = fma(kd, GSM_LK(GSM_LK_LN2), e.logc);
-    const double r2 = r * r;
-    double p = fma(-0.25, r, GSM_LK(GSM_LK_THIRD));
-    p = fma(p, r, -0.5);
-    const double y = fma(p, r2, r);     // log1p(r), |r| <= 2^-10
-    return hp + y;
+// one thread's view of the two replicated tables
+struct GsmT6 {
+#if defined(__CUDACC__)
+    uint32_t log_a, exp_a;   // device: shared-window byte addresses of the tables (CTA-uniform)
+    uint32_t rep;            // this lane's replica offset in bytes: (lane & 15) * 8
+#else
+    const uint64_t* log_t;   // host (CPU-side logic tests): replica 0
+    const uint64_t* exp_t;
+#endif
+};
+// entry at byte offset `off` (a multiple of 128) of a table
+GSM_HD uint64_t gsm_t6_log_ld(const GsmT6& t, uint32_t off) {
+#if defined(__CUDA_ARCH__)
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.log_a + (off | t.rep)));
+    return v;
+#elif defined(__CUDACC__)
+    (void)t; (void)off;
+    return 0;
+#else
+    return t.log_t[off >> 3];
+#endif
+}
+GSM_HD uint64_t gsm_t6_exp_ld(const GsmT6& t, uint32_t off) {
+#if defined(__CUDA_ARCH__)
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.exp_a + (off | t.rep)));
+    return v;
+#elif defined(__CUDACC__)
+    (void)t; (void)off;
+    return 0;
+#else
+    return t.exp_t[off >> 3];
+#endif
 }
 
-// log(x) = lz + k ln2 with the k ln2 part left to the caller (sums of logs collect k in integer accumulators)
-GSM_HD double gsm_log9_split(double x, const GsmLogEntry* __restrict__ tab, int32_t& k) {
+// ---- table-driven log / exp (arguments must be "regular": see the chk words) ------------------------------------
+// r = z invc - 1 and K = 64 k + i of a positive normal x: log(x) = K ln2/64 + log1p(r)
+GSM_HD double gsm_log6_r(const GsmT6& t, double x, int32_t& K) {
     const int32_t hi = gsm_hi32(x);
-    const int32_t tmp = hi - 0x3fe60000;
-    const int32_t i = (tmp >> 11) & (GSM_LOG9_TAB_N - 1);
-    k = tmp >> 20;   // arithmetic
+    const int32_t tmp = hi - (int32_t)GSM_LOG6_OFFHI;
+    const uint64_t e = gsm_t6_log_ld(t, ((uint32_t)tmp >> 7) & 0x1f80u);
+    const int32_t elo = (int32_t)(uint32_t)(e & 0xffffffffu);
     const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
-    const GsmLogEntry e = tab[i];
-    const double r = fma(z, e.invc, -1.0);
+    K = (tmp >> 20) * 64 + (elo & 63);   // arithmetic shift
+    return fma(z, gsm_hilo((int32_t)(uint32_t)(e >> 32), elo), -1.0);
+}
+// log1p(r), |r| <= 0.01218: degree 5, absolute error <= 7e-14 (the per-branch sums)
+GSM_HD double gsm_log6_y3(double r) {
     const double r2 = r * r;
-    double p = fma(-0.25, r, GSM_LK(GSM_LK_THIRD));
-    p = fma(p, r, -0.5);
-    const double y = fma(p, r2, r);
-    return e.logc + y;
+    double q = fma(GSM_LK(GSM_LK_Q3 + 3), r, GSM_LK(GSM_LK_Q3 + 2));
+    q = fma(q, r, GSM_LK(GSM_LK_Q3 + 1));
+    q = fma(q, r, GSM_LK(GSM_LK_Q3 + 0));
+    return fma(q, r2, r);
+}
+// ... degree 6, absolute error <= 4e-16 (aux, which feeds differences)
+GSM_HD double gsm_log6_y4(double r) {
+    const double r2 = r * r;
+    double q = fma(GSM_LK(GSM_LK_Q4 + 4), r, GSM_LK(GSM_LK_Q4 + 3));
+    q = fma(q, r, GSM_LK(GSM_LK_Q4 + 2));
+    q = fma(q, r, GSM_LK(GSM_LK_Q4 + 1));
+    q = fma(q, r, -0.5);
+    return fma(q, r2, r);
+}
+// (double)K for |K| < 2^20 without a conversion instruction
+GSM_HD double gsm_k2d(int32_t K) { return gsm_hilo(0x43300000, K + (1 << 20)) - GSM_LK(GSM_LK_KBIAS); }
+// (double)n for 0 <= n < 2^31
+GSM_HD double gsm_u2d(int32_t n) { return gsm_hilo(0x43300000, n) - GSM_LK(GSM_LK_TWO52); }
+
+GSM_HD double gsm_log6(const GsmT6& t, double x) {   // degree 5
+    int32_t K;
+    const double r = gsm_log6_r(t, x, K);
+    return fma(gsm_k2d(K), GSM_LK(GSM_LK_LN2_64), gsm_log6_y3(r));
+}
+GSM_HD double gsm_log6_hi(const GsmT6& t, double x) {   // degree 6
+    int32_t K;
+    const double r = gsm_log6_r(t, x, K);
+    return fma(gsm_k2d(K), GSM_LK(GSM_LK_LN2_64), gsm_log6_y4(r));
 }
 
-GSM_HD double gsm_exp9(double x, const uint64_t* __restrict__ tab) {
+// exp(x), |x| < 700.  One-step argument reduction: its error, |x| 1e-16 relative, only matters where exp(x) does
+// (x = -c1 h <= 0 here: G = (1 + c2) + (1 - c2) e^x).  Relative error <= 1e-14.
+GSM_HD double gsm_exp6(const GsmT6& t, double x) {
     double kd = fma(x, GSM_LK(GSM_LK_INVLN2N), GSM_LK(GSM_LK_SHIFT));
     const int32_t ki = gsm_lo32(kd);
     kd -= GSM_LK(GSM_LK_SHIFT);
-    double r = fma(kd, GSM_LK(GSM_LK_NLN2HI), x);
-    r = fma(kd, GSM_LK(GSM_LK_NLN2LO), r);
-    const uint64_t t = tab[ki & (GSM_EXP9_TAB_N - 1)];
-    const double scale = gsm_hilo((int32_t)(t >> 32) + (ki << 11), (int32_t)(t & 0xffffffffu));
+    const double r = fma(kd, GSM_LK(GSM_LK_NLN2N), x);
+    const uint64_t e = gsm_t6_exp_ld(t, ((uint32_t)ki & 63u) << 7);
+    const double scale = gsm_hilo((int32_t)((uint32_t)(e >> 32) + ((uint32_t)ki << 14)), (int32_t)(uint32_t)(e & 0xffffffffu));
     const double r2 = r * r;
-    double q = fma(GSM_LK(GSM_LK_24TH), r, GSM_LK(GSM_LK_SIXTH));
+    double q = fma(GSM_LK(GSM_LK_E2 + 2), r, GSM_LK(GSM_LK_E2 + 1));
     q = fma(q, r, 0.5);
-    const double tmp = fma(q, r2, r);   // expm1(r), |r| <= ln2/1024
-    return fma(scale, tmp, scale);
+    const double em1 = fma(q, r2, r);   // expm1(r), |r| <= ln2/128
+    return fma(scale, em1, scale);
 }
 
 // "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal finite double
@@ -112,16 +183,18 @@ GSM_HD uint32_t gsm_chk_pos(double x) { return (uint32_t)(gsm_hi32(x) - 0x001000
 GSM_HD uint32_t gsm_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // ---- per-tree constants held in registers -----------------------------------------------------------------------
+// per-tree tables in shared memory (built by the setup warp):
+//   mtab[m]  = {shape m - 1, log(shape) - logGamma(shape m)}, m = 0..64; mtab[0] = {-1, 0}            (BSP:97-99)
+//   ntab[n]  = {log(shape) - logGamma(shape (n + 1)), -sum_{i=2..n} log i}, n = 0..63                 (BSP:97-99, STP:567)
 struct GsmLeanC {
     // pass A
     double neg_c1, omc2, opc2, kS, c1, rho;
     // pass B
     double kEh;        // (lambda + mu + psi - c1) / 2: E/2 = len * kEh + (aux - aux_parent)   (STP:749-769 via aux)
     double shape, base, eff_mean;
-    const GsmLogEntry* logtab;
-    const uint64_t* exptab;
-    const GsmLogEntry* stubtab;
-    const GsmLogEntry* mtab;   // per tree: {shape*m - 1, log(shape) - logGamma(shape*m)}, m = 0..64
+    GsmT6 t6;
+    const GsmLogEntry* mtab;
+    const GsmLogEntry* ntab;
     int32_t L;                 // leaves are nodes 0..L-1
     int32_t leaf_term;         // 0: none, 1: psi > 0 (STP:337-343), 2: origin / root conditioned (STP:467-474)
     bool use_counts;           // stub counts exist (COUNTS / EXACT); else getNStubsOnBranch == -1 (Stubs:348-350)
@@ -167,11 +240,11 @@ GSM_HD void gsm_lean_acc_a_zero(GsmLeanAccA& S) { S.leafterm = 0.0; S.n_leafterm
 // aux of one node.  e_out / G_out feed the leaf term.
 GSM_HD double gsm_lean_aux(const GsmLeanC& c, GsmLeanAccA& S, double h, double& e_out, double& G_out) {
     S.hmax = gsm_umax(S.hmax, (uint32_t)gsm_hi32(h));
-    const double e = gsm_exp9(c.neg_c1 * h, c.exptab);
+    const double e = gsm_exp6(c.t6, c.neg_c1 * h);
     const double G = fma(c.omc2, e, c.opc2);
     e_out = e;
     G_out = G;
-    return gsm_log9(G, c.logtab);
+    return gsm_log6_hi(c.t6, G);
 }
 
 // LT = c.leaf_term (compile-time in the kernel's loops); leaf and not a direct ancestor is decided by the caller
@@ -184,7 +257,7 @@ GSM_HD void gsm_lean_leaf_term(const GsmLeanC& c, GsmLeanAccA& S, bool leaf_not_
     const double numer = c.kS * G - c.c1 * (c.opc2 - e * c.omc2);                             // 2 lambda G p0(h), STP:506-507
     const double arg = need ? numer : 1.0;
     S.chk = gsm_umax(S.chk, gsm_chk_pos(arg));
-    const double ln = gsm_log9(arg, c.logtab);
+    const double ln = gsm_log6_hi(c.t6, arg);
     if (need) {
         S.leafterm += ln + fma(c.c1, h, aux);
         S.n_leafterm++;
@@ -194,26 +267,29 @@ GSM_HD void gsm_lean_leaf_term(const GsmLeanC& c, GsmLeanAccA& S, bool leaf_not_
 }
 
 // ---- pass B -----------------------------------------------------------------------------------------------------
+// Logs enter the sums as log(x) = K ln2/64 + y: the y parts are summed in fp64, the K parts (times their integer
+// weights) in integer registers.
 struct GsmLeanAccB {
-    double gam;        // sum  log(x shape) (shape m - 1) + log(shape) - logGamma(shape m)        (BSP:97-99 without - x shape)
+    double gam;        // sum y(x shape) (shape m - 1)                                           (BSP:97-99, the log term)
+    double gamc;       // sum log(shape) - logGamma(shape m)
     double spk;        // sum of spikes                                                           (x shape term; burst in CLEAN)
     double spk_el;     // GENERAL: sum of spikes that count as bursts of eligible branches        (SPL:53-54)
     double lr, lr2;    // sum log r, sum log^2 r                                                  (BRP:171)
-    double stub;       // sum n_i log(E_i / 2)                                                    (STP:566)
+    double stub;       // sum n_i y(E_i / 2)                                                      (STP:566)
     double nlf;        // sum -log(n_i!)                                                          (STP:567)
     double len, dA;    // sum len, sum (aux - aux_parent)
     double lenr;       // sum len * r                                                             (SPL:44-49 / PRCM:233)
     double auxint, hint;     // sums over internal nodes of aux, h
     double auxfake, hfake;   // GENERAL: the same over fake internal nodes
-    int32_t k_mk, k_k; // sum m_i k_i, sum k_i with k_i the binary exponent of x_i shape: ln2 (shape k_mk - k_k) belongs to gam
-    int32_t k_nk;      // sum n_i (k_i + 1) with k_i the binary exponent of E_i / 2: ln2 k_nk belongs to stub
+    int32_t k_mk, k_k; // sum m_i K_i, sum K_i of x_i shape: ln2/64 (shape k_mk - k_k) belongs to gam
+    int32_t k_nk;      // sum n_i (K_i + 64) of E_i / 2: ln2/64 k_nk belongs to stub
     int32_t n_extant, n_extinct, n_da, n_fake;
     uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
     uint32_t chk_n;    // max stub count as unsigned (negative counts become huge)
     uint32_t chk_len;  // CLEAN: specialness of len (zero / negative lengths -> rerun as GENERAL)
 };
 GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
-    S.gam = S.spk = S.spk_el = S.lr = S.lr2 = S.stub = S.nlf = S.len = S.dA = S.lenr = 0.0;
+    S.gam = S.gamc = S.spk = S.spk_el = S.lr = S.lr2 = S.stub = S.nlf = S.len = S.dA = S.lenr = 0.0;
     S.auxint = S.hint = S.auxfake = S.hfake = 0.0;
     S.k_mk = S.k_k = S.k_nk = S.n_extant = S.n_extinct = S.n_da = S.n_fake = 0;
     S.chk = S.chk_n = S.chk_len = 0u;
@@ -221,7 +297,7 @@ GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
 
 // One node i.  w: own packed word (parent index | FAKE << 15), wp: the parent's word (GENERAL only).
 //   GENERAL  false: ordinary tree (no zero-length branch in the main loop); true: any tree
-//   LEAF     1: i < L, 0: i >= L (compile-time for the split loops), 2: decided here
+//   LEAF     1: i < L, 0: i >= L (compile-time for chunks on one side of L), 2: decided here
 //   STDW     the default wiring (stub counts wired to clock model, spike prior and tree prior; relaxed clock) is
 //            compiled in; false: the wiring is read from c
 template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
@@ -252,14 +328,12 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
     } else {
         S.chk_len = gsm_umax(S.chk_len, gsm_chk_pos(len));
     }
-    // table entries of this branch's spike count m and stub count n
-    const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
-    const GsmLogEntry me = c.mtab[mi];                  // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
     if (use_counts) S.chk_n = gsm_umax(S.chk_n, (uint32_t)nst);   // above GSM_LEAN_MAX_NST: tree goes to the generic path
+    const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
 
     // ---- BranchRatePrior BRP:43-60 ----
     S.chk = gsm_umax(S.chk, gsm_chk_pos(rate));
-    const double lr = gsm_log9(rate, c.logtab);
+    const double lr = gsm_log6(c.t6, rate);
     S.lr += lr;
     S.lr2 = fma(lr, lr, S.lr2);
 
@@ -268,23 +342,39 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
     const double arg_s = (GENERAL && m == 0) ? 1.0 : xs;
     S.chk = gsm_umax(S.chk, gsm_chk_pos(arg_s));
     int32_t ks;
-    const double lzs = gsm_log9_split(arg_s, c.logtab, ks);
-    S.gam += fma(lzs, me.invc, me.logc);
-    S.k_mk += m * ks;
+    const double ys = gsm_log6_y3(gsm_log6_r(c.t6, arg_s, ks));
     S.k_k += ks;
     S.spk += spike;
-
-    // ---- stub density, count mode: STP:555-571 / 621-637 ----
-    if (stub_term) {
-        const uint32_t ni = (uint32_t)nst < (uint32_t)GSM_LEAN_MAX_NST ? (uint32_t)nst : (uint32_t)GSM_LEAN_MAX_NST;
-        const GsmLogEntry se = c.stubtab[ni];           // {(double)n, -log(n!)}
-        const uint32_t chkE = gsm_chk_pos(E2);
-        S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
+    if (!GENERAL && STDW) {
+        // m = n + 1: one 16-byte entry carries the Gamma constant of the spike prior and -log(n!) of the stub prior
+        const GsmLogEntry ne = c.ntab[ni];
+        const double nd = gsm_u2d((int32_t)ni);
+        const double md = nd + 1.0;
+        S.gam = fma(ys, fma(c.shape, md, -1.0), S.gam);
+        S.gamc += ne.invc;
+        S.k_mk += ((int32_t)ni + 1) * ks;
+        // ---- stub density, count mode: STP:555-571 / 621-637 ----
+        S.chk = gsm_umax(S.chk, gsm_chk_pos(E2));
         int32_t ke;
-        const double lzE = gsm_log9_split(E2, c.logtab, ke);   // finite garbage when E2 == 0 (len == 0): multiplied by n = 0
-        S.stub = fma(se.invc, lzE, S.stub);
-        S.nlf += se.logc;
-        S.k_nk += nst * (ke + 1);
+        const double yE = gsm_log6_y3(gsm_log6_r(c.t6, E2, ke));
+        S.stub = fma(nd, yE, S.stub);
+        S.nlf += ne.logc;
+        S.k_nk += (int32_t)ni * (ke + 64);
+    } else {
+        const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
+        const GsmLogEntry me = c.mtab[mi];              // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
+        S.gam = fma(ys, me.invc, S.gam);
+        S.gamc += me.logc;
+        S.k_mk += (int32_t)mi * ks;
+        if (stub_term) {
+            const uint32_t chkE = gsm_chk_pos(E2);
+            S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
+            int32_t ke;
+            const double yE = gsm_log6_y3(gsm_log6_r(c.t6, E2, ke));   // finite garbage when E2 == 0 (len == 0): times n = 0
+            S.stub = fma(gsm_u2d((int32_t)ni), yE, S.stub);
+            S.nlf += c.ntab[ni].logc;
+            S.k_nk += (int32_t)ni * (ke + 64);
+        }
     }
     S.len += len;
     S.dA += dA;
@@ -314,20 +404,10 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
             S.n_extant += (!da && low) ? 1 : 0;
             S.n_extinct += (!da && ext) ? 1 : 0;
         } else {
-#if defined(__CUDA_ARCH__)
-            // two compares, two predicated increments
-            asm("{\n\t.reg .pred lo, ex;\n\t"
-                "setp.le.f64 lo, %2, %4;\n\t"
-                "setp.gt.and.f64 ex, %3, %4, !lo;\n\t"
-                "@lo add.s32 %0, %0, 1;\n\t"
-                "@ex add.s32 %1, %1, 1;\n\t}"
-                : "+r"(S.n_extant), "+r"(S.n_extinct)
-                : "d"(h), "d"(len), "d"(GSM_LK(GSM_LK_LEAF_EPS)));
-#else
             const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
-            if (low) S.n_extant++;
-            else if (len > GSM_LK(GSM_LK_LEAF_EPS)) S.n_extinct++;
-#endif
+            const bool ext = !low && (len > GSM_LK(GSM_LK_LEAF_EPS));
+            S.n_extant += low ? 1 : 0;
+            S.n_extinct += ext ? 1 : 0;
         }
     } else {
         S.auxint += aux;
@@ -355,9 +435,9 @@ GSM_HD void gsm_lean_combine(const GsmTreeConsts& K, const GsmLeanC& c, const Gs
     else if (variant == GSM_TV_NO_PSI) tree = -(K.lmm * h_nf) - 2 * aux_nf;                  // STP:371-377
     else if (variant == GSM_TV_PSI || variant == GSM_TV_CONDITIONED) tree = -(K.c1 * h_nf) - 2 * aux_nf + SA.leafterm;
     o.tree = tree;
-    const double ln2 = 0.69314718055994530942;
-    o.stub = fma(ln2, (double)S.k_nk, S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);         // sum n log E - log n! - E
-    o.spike = fma(ln2, fma(c.shape, (double)S.k_mk, -(double)S.k_k), S.gam) - c.shape * S.spk;
+    const double l64 = GSM_LN2_64;
+    o.stub = fma(l64, (double)S.k_nk, S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);         // sum n log E - log n! - E
+    o.spike = fma(l64, fma(c.shape, (double)S.k_mk, -(double)S.k_k), S.gam + S.gamc) - c.shape * S.spk;
     o.rate = -K.inv_2s2 * (S.lr2 - 2 * K.m_ln * S.lr) - S.lr;                                // sum -(lr - m)^2/(2 s^2) - lr, without n m^2
     o.burst = c.eff_mean * (GENERAL ? S.spk_el : S.spk);
     o.dist = c.base * S.lenr;

@@ -116,44 +116,41 @@ static GsmLeanBlob g_blob;
 static bool g_blob_init = false;
 static void init_blob() {
     if (g_blob_init) return;
-    static const GsmLogEntry lt[GSM_LOG9_TAB_N] = GSM_LOG9_TAB_INIT;
-    static const uint64_t et[GSM_EXP9_TAB_N] = GSM_EXP9_TAB_INIT;
-    memcpy(g_blob.logtab, lt, sizeof lt);
-    memcpy(g_blob.exptab, et, sizeof et);
+    gsm_lean_blob_fill(g_blob);
     init_tables();
-    for (int i = 0; i <= GSM_LEAN_MAX_NST; i++) {
-        g_blob.stubtab[i].invc = (double)i;
-        g_blob.stubtab[i].logc = -g_logfact_host[i];
-    }
     g_blob_init = true;
 }
 
-// main loop of pass B as the kernel splits it: leaf pairs, internal pairs (first pair even), the rest is the tail
+// main loop of pass B as the kernel splits it: chunks of 2 BLOCK nodes, each all-leaf, all-internal or mixed; node n-1
+// is the tail
 template <bool GENERAL, bool WANT, bool STDW>
 static void lean_b_all(const GsmLeanC& c, GsmLeanAccB& SB, GsmLeanAccB& ST, int n, int32_t stub_mode, const double* h,
                        const double* aux, const uint16_t* w, const double* rate, const double* spike, const int32_t* nstubs,
                        double* out_rates, double* out_wsp) {
     double dr, dw;
     const int L = c.L;
-    std::vector<char> done(n, 0);
+    const int BLOCK = n <= 512 ? 128 : 256;
+    const int npairs = (n - 1) >> 1;
     auto node = [&](int i, int leaf) {
         const int p = w[i] & 0x7fff;
         const int32_t k = nstubs ? nstubs[i] : -1;
         double* o_r = out_rates ? out_rates + i : &dr;
         double* o_w = out_wsp ? out_wsp + i : &dw;
         if (leaf == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
-        else gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
-        done[i] = 1;
+        else if (leaf == 0) gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
+        else gsm_lean_b_node<GENERAL, WANT, 2, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
     };
-    for (int j = 0; j < (L >> 1); j++) { node(2 * j, 1); node(2 * j + 1, 1); }
-    const int first = (L + 1) >> 1;
-    for (int j = first; j < ((n - 1) >> 1); j++) { node(2 * j, 0); node(2 * j + 1, 0); }
-    // tail (GENERAL flavour, runtime leaf test and wiring): everything the two loops left out
-    for (int i = 0; i < n; i++) {
-        if (done[i]) continue;
+    for (int j = 0; j < npairs; j++) {
+        const int o = (j / BLOCK) * 2 * BLOCK;
+        const int leaf = (o + 2 * BLOCK <= L) ? 1 : (o >= L ? 0 : 2);
+        node(2 * j, leaf);
+        node(2 * j + 1, leaf);
+    }
+    {   // tail (GENERAL flavour, runtime leaf test and wiring): node n-1
+        const int i = n - 1;
         const int p = w[i] & 0x7fff;
         int32_t k = -1;
-        if (c.use_counts) k = (i < n - 1 || stub_mode == GSM_STUBS_EXACT) ? (nstubs ? nstubs[i] : 0) : 0;
+        if (c.use_counts) k = stub_mode == GSM_STUBS_EXACT ? (nstubs ? nstubs[i] : 0) : 0;
         gsm_lean_b_node<true, WANT, 2, false>(c, ST, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k,
                                               out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
     }
@@ -169,12 +166,14 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmTreeConsts K;
     memset(&K, 0, sizeof K);
     gsm_setup_scalars(K, params, use_spike, flags, stub_mode);
-    GsmLogEntry mtab[GSM_LEAN_MTAB_N];
+    GsmLogEntry mtab[GSM_LEAN_MTAB_N], ntab[GSM_LEAN_MAX_NST + 1];
     mtab[0].invc = -1.0;
     mtab[0].logc = 0.0;
     for (int m = 1; m < GSM_LEAN_MTAB_N; m++) {
         mtab[m].invc = K.shape * m - 1;
         mtab[m].logc = gsm_log(K.shape) - gsm_log_gamma(K.shape * m);
+        ntab[m - 1].invc = mtab[m].logc;
+        ntab[m - 1].logc = -g_logfact_host[m - 1];
     }
     if (!gsm_lean_consts_ok(K)) return false;
     std::vector<uint16_t> w(n);
@@ -189,7 +188,7 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     if (bad || nroot != 1) return false;
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
-    c.logtab = g_blob.logtab; c.exptab = g_blob.exptab; c.stubtab = g_blob.stubtab; c.mtab = mtab;
+    c.t6.log_t = g_blob.logtab; c.t6.exp_t = g_blob.exptab; c.mtab = mtab; c.ntab = ntab;
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     std::vector<double> aux(n);
@@ -285,13 +284,18 @@ extern "C" int gsm_emu_eval_batch_lean(uint32_t flags, int32_t stub_mode, int64_
     return 0;
 }
 
-extern "C" void gsm_emu_log9_vec(const double* x, double* y, int64_t n) {
+// which: 0 degree-5 log (per-branch sums), 1 degree-6 log (aux)
+extern "C" void gsm_emu_log6_vec(const double* x, double* y, int64_t n, int32_t which) {
     init_blob();
-    for (int64_t i = 0; i < n; i++) y[i] = gsm_log9(x[i], g_blob.logtab);
+    GsmT6 t;
+    t.log_t = g_blob.logtab; t.exp_t = g_blob.exptab;
+    for (int64_t i = 0; i < n; i++) y[i] = which ? gsm_log6_hi(t, x[i]) : gsm_log6(t, x[i]);
 }
-extern "C" void gsm_emu_exp9_vec(const double* x, double* y, int64_t n) {
+extern "C" void gsm_emu_exp6_vec(const double* x, double* y, int64_t n) {
     init_blob();
-    for (int64_t i = 0; i < n; i++) y[i] = gsm_exp9(x[i], g_blob.exptab);
+    GsmT6 t;
+    t.log_t = g_blob.logtab; t.exp_t = g_blob.exptab;
+    for (int64_t i = 0; i < n; i++) y[i] = gsm_exp6(t, x[i]);
 }
 
 // ---- table-driven log / exp of the kernels, exposed for accuracy tests ----

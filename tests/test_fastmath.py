@@ -38,3 +38,26 @@ def test_exp_accuracy_and_special_values():
     sp = np.array([0.0, -0.0, 709.0, 710.0, -745.0, -746.0, -708.5, np.inf, -np.inf, np.nan, 704.0, -704.0, 1e-320])
     with np.errstate(all="ignore"):
         assert np.array_equal(_call(emu().gsm_emu_exp_vec, sp), np.exp(sp), equal_nan=True)
+
+
+def test_lean_log6_exp6_accuracy():
+    """The lean kernel's 64-entry-table log / exp (gsm_lean.cuh): absolute error budgets of its header comments."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 300_000)), rng.uniform(0.4, 2.5, 400_000),
+                        1 + rng.uniform(-1e-3, 1e-3, 100_000), np.array([1.0, 0.9945993423461914, 0.5, 2.0])])
+    ref = np.log(x.astype(np.longdouble))
+    for which, tol in ((0, 1.0e-13), (1, 1.2e-14)):
+        y = np.empty_like(x)
+        emu().gsm_emu_log6_vec(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_int64(x.size), C.c_int32(which))
+        err = np.abs(y.astype(np.longdouble) - ref).astype(np.float64)
+        # K ln2/64 is one rounded product: allow its rounding on top of the polynomial's budget
+        assert np.all(err <= tol + 4e-16 * np.abs(ref.astype(np.float64))), (which, err.max())
+    y1 = np.empty(1)
+    one = np.array([1.0])
+    emu().gsm_emu_log6_vec(one.ctypes.data_as(C.c_void_p), y1.ctypes.data_as(C.c_void_p), C.c_int64(1), C.c_int32(0))
+    assert y1[0] == 0.0
+    x = np.concatenate([rng.uniform(-699, 0, 400_000), rng.uniform(-1, 1, 200_000), rng.uniform(-1e-5, 1e-5, 50_000)])
+    y = _call(emu().gsm_emu_exp6_vec, x)
+    ref = np.exp(x.astype(np.longdouble))
+    rel = np.abs((y.astype(np.longdouble) - ref) / ref).astype(np.float64)
+    assert np.all(rel <= 1.2e-14 + 1.2e-16 * np.abs(x)), rel.max()
