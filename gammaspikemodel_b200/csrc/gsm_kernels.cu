@@ -20,6 +20,30 @@
 #include <cstdlib>
 
 __device__ double g_logfact[GSM_LOGFACT_N];
+#ifdef GSM_PHASE_TIMING
+// debug builds (tools/build_dbg.sh): cycles spent by thread 0 of every CTA of the lean kernel between phase boundaries
+__device__ unsigned long long g_phase_cycles[8];
+extern "C" int gsm_debug_phase_cycles(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+    }
+    return static_cast<int>(e);
+}
+#define GSM_PHASE_MARK(k)                                                          \
+    do {                                                                           \
+        if (threadIdx.x == 0) {                                                    \
+            const long long now_ = clock64();                                      \
+            atomicAdd(&g_phase_cycles[k], static_cast<unsigned long long>(now_ - t_mark_)); \
+            t_mark_ = now_;                                                        \
+        }                                                                          \
+    } while (0)
+#define GSM_PHASE_START() long long t_mark_ = clock64()
+#else
+#define GSM_PHASE_MARK(k) do { } while (0)
+#define GSM_PHASE_START() do { } while (0)
+#endif
 // constant tables of the lean path (stubtab is filled by gsm_init_tables)
 __device__ GsmLeanBlob g_lean_blob;   // replicated log / exp tables, filled by gsm_init_tables
 
@@ -105,6 +129,11 @@ static __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 static __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 static __device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
@@ -394,29 +423,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 
 // ---------------------------------------------------------------------------------------------------------
 // lean kernel: default wiring family (gsm_lean_wiring_ok), one CTA per tree.  See gsm_lean.cuh.
-//   shared memory: height row 8 B/node (TMA) + aux row 8 B/node (first used as the TMA landing zone of the
-//   parent row) + packed word 2 B/node (parent index, FAKE bit) + 16 KB of replicated log / exp tables (TMA)
-//   + the per-tree Gamma tables + a two-stage ring of branch-row chunks (TMA).
-//   phase 0  one thread issues the TMA bulk copies of the tree rows, the tables and the first two chunks of the
-//            branch rows; one warp computes the arithmetic-only per-tree constants and, one m per lane, the
-//            tables {shape m - 1, log shape - logGamma(shape m)}
-//   phase 1  parents int32 -> packed 16-bit words, validation of BEAST's numbering (eight nodes per step)
-//   phase 2  pass A: aux = log G(h) for node pairs; leaves detect sampled ancestors and mark fake parents
-//   phase 3  pass B: chunks of 2 BLOCK nodes (one node pair per thread) arrive through the ring: rate / spike /
-//            stub-count rows by TMA into shared memory, full / empty mbarriers, the chunk after next is requested
-//            as soon as every warp has taken its pairs of the previous one; CLEAN or GENERAL flavour per tree
+//
+// What stays in shared memory is only what is gathered at random: the heights and aux = log G(h) of the INTERNAL
+// nodes (a leaf is nobody's parent), 16 bytes per internal node.  Everything else is read once, in node order, and
+// comes through a three-stage ring of chunks of 2 BLOCK nodes filled by TMA bulk copies: rate, spike, stub count
+// and parent index of every node, and the heights of the leaves.
+//   phase 0  one thread requests the internal heights, the replicated log / exp tables and the first three chunks;
+//            one lane computes the arithmetic-only per-tree constants
+//   phase 1  64 lanes compute the Gamma tables {log shape - logGamma(shape m)} (commons-math Lanczos with fast
+//            reciprocals); trees that may hold sampled ancestors (psi > 0) are scanned for them (leaf height ==
+//            parent height -> the parent is fake)
+//   phase 2  pass A: aux = log G(h) of the internal nodes (pairs)
+//   phase 3  pass B: leaf chunks (aux of a leaf is computed on the spot; a warp whose 64 heights are all zero uses
+//            the constant), then internal chunks; one node pair per thread and chunk; CLEAN or GENERAL flavour
 //   phase 4  per-thread combination to six sums, warp-shuffle + cross-warp reduction, 128-byte scratch row
+// BEAST's numbering (leaves 0..L-1, every parent in [L, n), one root) is validated on the fly (chk_p).
 // ---------------------------------------------------------------------------------------------------------
+#define GSM_RING_STAGES 3
 template <int NWARP>
 struct GsmLeanShared {
     GsmTreeConsts K;
-    uint64_t mbar;       // tree rows + tables
-    uint64_t full[2];    // ring: chunk landed
-    uint64_t empty[2];   // ring: every warp has read its pairs of the chunk
-    int32_t root, nroot, bad;
+    uint64_t mbar;                     // internal heights + tables
+    uint64_t full[GSM_RING_STAGES];    // ring: chunk landed
+    uint64_t empty[GSM_RING_STAGES];   // ring: every warp holds its pairs of the chunk in registers
+    int32_t root, nroot, bad, root_last;
     double red[6][NWARP];
     int32_t redi[7][NWARP];
-    uint32_t redu[4][NWARP];
+    uint32_t redu[5][NWARP];
 };
 
 static __device__ __forceinline__ void lean_redo(int32_t* __restrict__ redo_count, int32_t* __restrict__ redo_list,
@@ -426,70 +459,34 @@ static __device__ __forceinline__ void lean_redo(int32_t* __restrict__ redo_coun
     rows[t].status = 0;
 }
 
-// commons-math Lanczos logGamma with the 14 quotients evaluated independently (same summation order as
-// gsm_log_gamma / the Java loop, so the same value; the divisions overlap instead of forming one chain)
-static __device__ double lean_log_gamma(double x) {
-    if (!(x > 0.0)) return NAN;
-    double q[15];
-#pragma unroll
-    for (int i = 14; i > 0; --i) q[i] = gsm_lanczos_d[i] / (x + i);
+// commons-math Lanczos logGamma (same terms, same summation order as gsm_log_gamma / the Java loop) with reciprocals
+// instead of divisions and the kernel's table-driven logarithm: agrees with the Java value to ~1e-15 relative.
+static __device__ __forceinline__ double lean_log_gamma(const GsmT6& t6, double x) {
     double sum = 0.0;
 #pragma unroll
-    for (int i = 14; i > 0; --i) sum = sum + q[i];
+    for (int i = 14; i > 0; --i) sum = sum + gsm_lanczos_d[i] * __drcp_rn(x + i);
     sum = sum + gsm_lanczos_d[0];
     const double tmp = x + 607.0 / 128.0 + .5;
-    return ((x + .5) * log(tmp)) - tmp + 0.91893853320467274178 + log(sum / x);   // libdevice: no table fetch from L2
+    return ((x + .5) * gsm_log6_hi(t6, tmp)) - tmp + 0.91893853320467274178 + gsm_log6_hi(t6, sum * __drcp_rn(x));
 }
 
-// a_h / a_aux / a_w: shared-window addresses of the height row, the aux row and the packed words
-template <int LT, int NT>   // NT = worker threads of this phase
-static __device__ __forceinline__ bool lean_pass_a(const GsmLeanC& c, GsmLeanAccA& SA, int n, int tid, uint32_t a_h, uint32_t a_aux,
-                                                   uint32_t a_w) {
-    bool anyda = false;
-    const int npa = (n + 1) >> 1;
-#pragma unroll 1
-    for (int j = tid; j < npa; j += NT) {
-        const int i0 = 2 * j;
-        double2 h2 = lds_v2f64(a_h + j * 16);
-        if (i0 + 1 >= n) h2.y = h2.x;   // padding slot of the last pair
-        double e0, G0, e1, G1;
-        const double a0 = gsm_lean_aux(c, SA, h2.x, e0, G0);
-        const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
-        sts_v2f64(a_aux + j * 16, a0, a1);
-        if (i0 < c.L) {   // leaves: Node.isDirectAncestor -> parent isFake; extinct-leaf terms
-            const uint32_t w2 = lds_u32(a_w + j * 4);
-            const uint32_t p0 = w2 & 0x7fffu;
-            const bool da0 = lds_f64(a_h + p0 * 8) == h2.x;
-            if (da0) {
-                sts_u16(a_w + p0 * 2, lds_u16(a_w + p0 * 2) | 0x8000u);
-                anyda = true;
-            }
-            gsm_lean_leaf_term<LT>(c, SA, !da0, h2.x, a0, e0, G0);
-            if (i0 + 1 < c.L) {
-                const uint32_t p1 = (w2 >> 16) & 0x7fffu;
-                const bool da1 = lds_f64(a_h + p1 * 8) == h2.y;
-                if (da1) {
-                    sts_u16(a_w + p1 * 2, lds_u16(a_w + p1 * 2) | 0x8000u);
-                    anyda = true;
-                }
-                gsm_lean_leaf_term<LT>(c, SA, !da1, h2.y, a1, e1, G1);
-            }
-        }
-    }
-    return anyda;
-}
-
-// ---- pass B: the branch rows (rate, spike, stub count) come through a two-stage ring of chunks of 2 BLOCK nodes,
-// filled by TMA bulk copies (full mbarrier: arrive.expect_tx by the producer, complete_tx by the copies) and handed
-// back by one arrive per warp on the empty mbarrier once the warp holds its pairs in registers.
-// Stage layout: [rate: 2 BLOCK x 8 B][spike: 2 BLOCK x 8 B][stub counts: 2 BLOCK x 4 B].
+// ---- the ring -------------------------------------------------------------------------------------------
+// Virtual chunk v: v < nlc is leaf chunk v (nodes [v * 2 BLOCK, ...) up to L), else internal chunk v - nlc (nodes from
+// L4 = L & ~3 on, up to n - 1).  Stage layout (BLOCK = 256: 16 KB):
+//   [rate: 2 BLOCK x 8][spike: 2 BLOCK x 8][height: 2 BLOCK x 8, leaf chunks only][stub count: 2 BLOCK x 4][parent: 2 BLOCK x 4]
+// full mbarrier: arrive.expect_tx by the requester, complete_tx by the copies.  A warp that holds its pairs of a chunk in
+// registers arrives on the stage's empty mbarrier; the warp whose arrival completes the phase requests the chunk three
+// ahead into the stage it has just freed: nobody waits on an empty barrier.
 struct LeanRing {
-    uint32_t a_ring;     // shared-window address of stage 0
+    uint32_t a_ring;            // shared-window address of stage 0
     uint32_t a_full, a_empty;   // ... of full[0], empty[0]
-    const double* rate;  // row pointers
+    const double* rate;         // row pointers
     const double* spike;
-    const int32_t* nst;  // nullptr: no stub counts
-    int S;               // row pitch in nodes: the last chunk is copied up to the pitch (multiples of 16 bytes)
+    const double* height;
+    const int32_t* nst;         // nullptr: no stub counts
+    const int32_t* parent;
+    int L, L4, nlc, nvc;        // leaves, L & ~3, leaf chunks, all chunks
+    int end_leaf, end_int;      // node ranges to copy: leaf chunks stop at end_leaf (L rounded up to 4), internal at end_int
 };
 
 static __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
@@ -505,8 +502,19 @@ static __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
-static __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrive; true when this arrival completes the phase (pending count before it was 1)
+static __device__ __forceinline__ bool mbar_arrive_last(uint32_t bar) {
+    uint32_t pending;
+    asm volatile(
+        "{\n"
+        ".reg .b64 st;\n"
+        "mbarrier.arrive.shared::cta.b64 st, [%1];\n"
+        "mbarrier.pending_count.b64 %0, st;\n"
+        "}\n"
+        : "=r"(pending)
+        : "r"(bar)
+        : "memory");
+    return pending == 1u;
 }
 static __device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src_gmem),
@@ -514,85 +522,148 @@ static __device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* 
                  : "memory");
 }
 
-// one thread: request chunk ch into stage s
+// one thread: request virtual chunk v into stage s
 template <int BLOCK>
-static __device__ __forceinline__ void ring_issue(const LeanRing& rg, int ch, uint32_t s) {
-    constexpr uint32_t STAGE = BLOCK * 40u;
-    const int o = ch * 2 * BLOCK;
-    int cnt = rg.S - o;
+static __device__ __forceinline__ void ring_issue(const LeanRing& rg, int v, uint32_t s) {
+    constexpr uint32_t STAGE = BLOCK * 64u;
+    const bool leafc = v < rg.nlc;
+    const int o = leafc ? v * 2 * BLOCK : rg.L4 + (v - rg.nlc) * 2 * BLOCK;
+    int cnt = (leafc ? rg.end_leaf : rg.end_int) - o;
     if (cnt > 2 * BLOCK) cnt = 2 * BLOCK;
     const uint32_t b8 = static_cast<uint32_t>(cnt) * 8u, b4 = static_cast<uint32_t>(cnt) * 4u;
     const uint32_t bar = rg.a_full + s * 8u, st = rg.a_ring + s * STAGE;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * b8 + (rg.nst ? b4 : 0u)) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"(2u * b8 + (leafc ? b8 : 0u) + (rg.nst ? 2u * b4 : b4))
+                 : "memory");
     tma_bulk_g2s_a(st, rg.rate + o, b8, bar);
     tma_bulk_g2s_a(st + BLOCK * 16u, rg.spike + o, b8, bar);
-    if (rg.nst) tma_bulk_g2s_a(st + BLOCK * 32u, rg.nst + o, b4, bar);
+    if (leafc) tma_bulk_g2s_a(st + BLOCK * 32u, rg.height + o, b8, bar);
+    if (rg.nst) tma_bulk_g2s_a(st + BLOCK * 48u, rg.nst + o, b4, bar);
+    tma_bulk_g2s_a(st + BLOCK * 56u, rg.parent + o, b4, bar);
 }
 
-// pairs [0, (n-1)/2) in chunks of BLOCK pairs
-static __device__ __forceinline__ int lean_chunks(int n, int block) { return (((n - 1) >> 1) + block - 1) / block; }
+// per-thread state of pass B that is not a sum
+struct LeanBCtx {
+    uint32_t a_hs, a_as;   // shared-window addresses of the internal height / aux arrays, biased: node i is at a_hs + i * 8
+    uint32_t a_fk;         // ... of the fake flags (bytes), biased the same way: node i at a_fk + i
+    uint32_t a_hL, a_aL, a_fL;   // the same arrays addressed by d = i - L
+    uint32_t chk_p;        // max over the nodes of (parent - L) as unsigned: >= n - L means outside [L, n)
+    uint32_t nL;           // n - L
+    double auxz, ez, Gz;   // aux, e, G of height zero
+};
 
-// one node pair j of the main loop
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
-static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccB& SB, int j, const double2 rr, const double2 ss,
-                                                   const int2 kk, uint32_t a_h, uint32_t a_aux, uint32_t a_w,
-                                                   double2* __restrict__ orate2, double2* __restrict__ owsp2) {
-    const double2 h2 = lds_v2f64(a_h + j * 16);
-    const double2 a2 = lds_v2f64(a_aux + j * 16);
-    const uint32_t w2 = lds_u32(a_w + j * 4);
-    const uint32_t w0 = w2 & 0xffffu, w1 = w2 >> 16;
-    const uint32_t p0 = w0 & 0x7fffu, p1 = w1 & 0x7fffu;
-    const double hp0 = lds_f64(a_h + p0 * 8), hp1 = lds_f64(a_h + p1 * 8);
-    const double ap0 = lds_f64(a_aux + p0 * 8), ap1 = lds_f64(a_aux + p1 * 8);
-    uint32_t wp0 = 0u, wp1 = 0u;
+// one node pair (i0, i0 + 1), both leaves (LEAF = 1) or both internal (LEAF = 0)
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT>
+static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, int i0, bool on,
+                                                   const double2 rr, const double2 ss, double2 h2, const int2 kk, int2 pp,
+                                                   int32_t* sh_root_nroot, double2* __restrict__ orate2, double2* __restrict__ owsp2) {
+    double2 a2;
+    double e0 = x.ez, G0 = x.Gz, e1 = x.ez, G1 = x.Gz;
+    if (LEAF == 1) {
+        // aux of the two leaves: the constant if every height of the warp is zero
+        a2 = make_double2(x.auxz, x.auxz);
+        const bool zero = (__double2hiint(h2.x) | __double2loint(h2.x) | __double2hiint(h2.y) | __double2loint(h2.y)) == 0;
+        if (!__all_sync(0xffffffffu, zero || !on)) {
+            if (!on) h2 = make_double2(0.0, 0.0);
+            a2.x = gsm_lean_aux(c, SA, h2.x, e0, G0);
+            a2.y = gsm_lean_aux(c, SA, h2.y, e1, G1);
+        }
+        if (!on) return;
+    } else {
+        if (!on) return;
+        h2 = lds_v2f64(x.a_hs + i0 * 8);
+        a2 = lds_v2f64(x.a_as + i0 * 8);
+    }
+    bool root0 = false, root1 = false;
+    if (GENERAL) {   // a root has no parent: it points to itself
+        root0 = pp.x < 0;
+        root1 = pp.y < 0;
+        if (root0 || root1) {
+            atomicAdd(sh_root_nroot + 1, (root0 ? 1 : 0) + (root1 ? 1 : 0));
+            sh_root_nroot[0] = root0 ? i0 : i0 + 1;
+            if (LEAF == 1) SB.chk = 0xffffffffu;   // a leaf cannot be the root
+            if (root0) pp.x = LEAF == 1 ? c.L : i0;
+            if (root1) pp.y = LEAF == 1 ? c.L : i0 + 1;
+        }
+    }
+    // parent slots: d = parent - L must be in [0, n - L); a malformed tree is flagged (chk_p) and its gathers clamped
+    const uint32_t d0 = static_cast<uint32_t>(pp.x - c.L), d1 = static_cast<uint32_t>(pp.y - c.L);
+    x.chk_p = gsm_umax(x.chk_p, gsm_umax(d0, d1));
+    const uint32_t q0 = d0 < x.nL ? d0 : x.nL - 1u, q1 = d1 < x.nL ? d1 : x.nL - 1u;
+    double hp0 = lds_f64(x.a_hL + q0 * 8), hp1 = lds_f64(x.a_hL + q1 * 8);
+    double ap0 = lds_f64(x.a_aL + q0 * 8), ap1 = lds_f64(x.a_aL + q1 * 8);
+    bool pf0 = false, pf1 = false, fs0 = false, fs1 = false;
     if (GENERAL) {
-        wp0 = lds_u16(a_w + p0 * 2);
-        wp1 = lds_u16(a_w + p1 * 2);
+        pf0 = lds_u8(x.a_fL + q0) != 0;
+        pf1 = lds_u8(x.a_fL + q1) != 0;
+        if (LEAF == 0) {
+            fs0 = lds_u8(x.a_fk + i0) != 0;
+            fs1 = lds_u8(x.a_fk + i0 + 1) != 0;
+        }
+        if (root0) { hp0 = h2.x; ap0 = a2.x; }
+        if (root1) { hp1 = h2.y; ap1 = a2.y; }
+    }
+    if (LEAF == 1 && LT != 0) {
+        const bool da0 = GENERAL && hp0 == h2.x && !root0, da1 = GENERAL && hp1 == h2.y && !root1;
+        gsm_lean_leaf_term<LT>(c, SA, !da0, h2.x, a2.x, e0, G0);
+        gsm_lean_leaf_term<LT>(c, SA, !da1, h2.y, a2.y, e1, G1);
     }
     double er[2], ew[2];
-    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j, w0, wp0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
-    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, 2 * j + 1, w1, wp1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1],
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, i0, root0, pf0, fs0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, i0 + 1, root1, pf1, fs1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1],
                                                      &ew[1]);
     if (WANT_RATES) {
-        if (orate2) orate2[j] = make_double2(er[0], er[1]);
-        if (owsp2) owsp2[j] = make_double2(ew[0], ew[1]);
+        if (orate2) orate2[i0 >> 1] = make_double2(er[0], er[1]);
+        if (owsp2) owsp2[i0 >> 1] = make_double2(ew[0], ew[1]);
     }
 }
 
-// main loop of pass B.  Chunks 0 and 1 were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int BLOCK>
-static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccB& SB, const LeanRing& rg, int n, int tid,
-                                                   uint32_t a_h, uint32_t a_aux, uint32_t a_w, double2* __restrict__ orate2,
-                                                   double2* __restrict__ owsp2) {
-    constexpr uint32_t STAGE = BLOCK * 40u;
-    const int L = c.L;
-    const int npairs = (n - 1) >> 1;
-    const int nch = lean_chunks(n, BLOCK);
+// virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
+// (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK>
+static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
+                                                     const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
+                                                     int32_t* sh_root_nroot, double2* __restrict__ orate2,
+                                                     double2* __restrict__ owsp2) {
+    constexpr uint32_t STAGE = BLOCK * 64u;
     const bool counts = STDW || rg.nst != nullptr;
+    uint32_t s = static_cast<uint32_t>(v0) % GSM_RING_STAGES;
+    uint32_t ph = (static_cast<uint32_t>(v0) / GSM_RING_STAGES) & 1u;
+    int i0 = first + 2 * tid;
 #pragma unroll 1
-    for (int ch = 0; ch < nch; ++ch) {
-        const uint32_t s = static_cast<uint32_t>(ch) & 1u;
-        if (tid == 0 && ch >= 1 && ch + 1 < nch) {
-            // stage s ^ 1 held chunk ch - 1: every warp has taken its pairs -> request chunk ch + 1 into it
-            mbar_wait_a(rg.a_empty + (s ^ 1u) * 8u, static_cast<uint32_t>(((ch + 1) >> 1) - 1) & 1u);
-            ring_issue<BLOCK>(rg, ch + 1, s ^ 1u);
-        }
-        mbar_wait_a(rg.a_full + s * 8u, static_cast<uint32_t>(ch >> 1) & 1u);
+    for (int v = v0; v < v1; ++v) {
+        mbar_wait_a(rg.a_full + s * 8u, ph);
         const uint32_t st = rg.a_ring + s * STAGE + tid * 16u;
         const double2 rr = lds_v2f64(st);
         const double2 ss = lds_v2f64(st + BLOCK * 16u);
+        double2 h2 = make_double2(0.0, 0.0);
+        if (LEAF == 1) h2 = lds_v2f64(st + BLOCK * 32u);
         int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
-        if (counts) kk = lds_v2s32(st + BLOCK * 32u - tid * 8u);
+        if (counts) kk = lds_v2s32(st + BLOCK * 48u - tid * 8u);
+        const int2 pp = lds_v2s32(st + BLOCK * 56u - tid * 8u);
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive_a(rg.a_empty + s * 8u);
-        const int j = ch * BLOCK + tid;
-        if (j < npairs) {
-            const int o = ch * 2 * BLOCK;
-            if (o + 2 * BLOCK <= L) lean_b_pair<GENERAL, WANT_RATES, 1, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
-            else if (o >= L) lean_b_pair<GENERAL, WANT_RATES, 0, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
-            else lean_b_pair<GENERAL, WANT_RATES, 2, STDW>(c, SB, j, rr, ss, kk, a_h, a_aux, a_w, orate2, owsp2);
+        if ((tid & 31) == 0) {
+            if (mbar_arrive_last(rg.a_empty + s * 8u) && v + GSM_RING_STAGES < rg.nvc) ring_issue<BLOCK>(rg, v + GSM_RING_STAGES, s);
+        }
+        const bool on = i0 >= lo && i0 + 1 < hi;
+        lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT>(c, SA, SB, x, i0, on, rr, ss, h2, kk, pp, sh_root_nroot, orate2, owsp2);
+        i0 += 2 * BLOCK;
+        if (++s == GSM_RING_STAGES) {
+            s = 0u;
+            ph ^= 1u;
         }
     }
+}
+
+// main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
+// chunks were requested in phase 0.
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK>
+static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
+                                                   int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
+                                                   double2* __restrict__ owsp2) {
+    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
+                                                           orate2, owsp2);
 }
 
 template <int BLOCK, int MINB, bool WANT_RATES>
@@ -604,20 +675,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     constexpr int NWARP = BLOCK / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ GsmLeanShared<NWARP> sh;
+    __shared__ GsmLeanBlob sh_blob;   // static: its shared-window address is an instruction immediate
     const int S = static_cast<int>(b.stride);
-    double* sh_h = reinterpret_cast<double*>(smem_raw);
-    double* sh_aux = sh_h + S;
-    uint16_t* sh_w = reinterpret_cast<uint16_t*>(sh_aux + S);
-    GsmLeanBlob* sh_blob = reinterpret_cast<GsmLeanBlob*>(smem_raw + static_cast<size_t>(S) * 18u);   // S % 32 == 0: 64-byte aligned
-    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_blob + 1);
+    const int SI = (S >> 1) + 32;     // slots of the internal arrays: n - L4 <= (n + 1) / 2 + 3
+    double* sh_hs = reinterpret_cast<double*>(smem_raw);
+    double* sh_as = sh_hs + SI;
+    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_as + SI);
     GsmLogEntry* sh_ntab = sh_mtab + (GSM_LEAN_MTAB_N + 1);
     unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_ntab + (GSM_LEAN_MAX_NST + 1));   // 16-byte aligned
+    uint8_t* sh_fk = sh_ring + GSM_RING_STAGES * BLOCK * 64;
     GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int64_t t = blockIdx.x;
+    GSM_PHASE_START();
     if (t == 0 && tid == 0) *redo_count_next = 0;   // counter of the next evaluation on this handle (ping-pong)
     int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
     if (n > b.n_nodes) n = b.n_nodes;
@@ -627,7 +700,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     const int64_t row = t * S;
     const int L = (n + 1) >> 1;
-    const int nch = lean_chunks(n, BLOCK);
+    const int L4 = L & ~3;
 
     LeanRing rg;
     rg.a_ring = smem_u32(sh_ring);
@@ -635,129 +708,143 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     rg.a_empty = smem_u32(&sh.empty[0]);
     rg.rate = b.rate + row;
     rg.spike = b.spike + row;
+    rg.height = b.height + row;
     rg.nst = b.stub_mode != GSM_STUBS_NOSTUB ? b.nstubs + row : nullptr;
-    rg.S = S;
+    rg.parent = b.parent + row;
+    rg.L = L;
+    rg.L4 = L4;
+    rg.nlc = ((L >> 1) + BLOCK - 1) / BLOCK;                       // pairs below L: L / 2
+    rg.nvc = rg.nlc + ((n - 1 - L4 + 1) / 2 + BLOCK - 1) / BLOCK;  // pairs (i0, i0 + 1), i0 = L4, L4 + 2, ... with i0 + 1 < n - 1
+    rg.end_leaf = (L + 3) & ~3;
+    rg.end_int = (n - 1 + 3) & ~3;
+    const int nvc = rg.nvc;
 
     // ---- phase 0 ----
     if (tid == 0) {
         mbar_init(&sh.mbar, 1);
-        mbar_init(&sh.full[0], 1);
-        mbar_init(&sh.full[1], 1);
-        mbar_init(&sh.empty[0], NWARP);
-        mbar_init(&sh.empty[1], NWARP);
+#pragma unroll
+        for (int k = 0; k < GSM_RING_STAGES; k++) {
+            mbar_init(&sh.full[k], 1);
+            mbar_init(&sh.empty[k], NWARP);
+        }
         fence_mbar_init();
         sh.root = -1;
         sh.nroot = 0;
         sh.bad = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
-        const uint32_t bytes_p = (static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
-        mbar_arrive_expect_tx(&sh.mbar, bytes_h + bytes_p + static_cast<uint32_t>(sizeof(GsmLeanBlob)));
-        tma_bulk_g2s(sh_h, b.height + row, bytes_h, &sh.mbar);
-        tma_bulk_g2s(sh_aux, b.parent + row, bytes_p, &sh.mbar);   // landing zone; repacked in phase 1
-        tma_bulk_g2s(sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
-        if (nch > 0) ring_issue<BLOCK>(rg, 0, 0u);
-        if (nch > 1) ring_issue<BLOCK>(rg, 1, 1u);
+    // requests spread over the warps (a bulk copy costs its issuing thread a few hundred cycles)
+    if (lane == 0) {
+        if (warp == 0) {
+            const uint32_t bytes_h = (static_cast<uint32_t>(n - L4) * 8u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&sh.mbar, bytes_h + static_cast<uint32_t>(sizeof(GsmLeanBlob)));
+            tma_bulk_g2s(sh_hs, b.height + row + L4, bytes_h, &sh.mbar);
+            tma_bulk_g2s(&sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
+        } else if (warp <= GSM_RING_STAGES) {
+            if (warp - 1 < nvc) ring_issue<BLOCK>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
+        }
+    } else if (tid == 1) {
+        sh.root_last = __ldg(b.parent + row + n - 1) < 0 ? 1 : 0;
     }
     // before any exit from here on: the bulk copies target this CTA's shared memory and must have landed
     auto drain = [&]() {
-        if (nch > 0) mbar_wait_a(rg.a_full, 0u);
-        if (nch > 1) mbar_wait_a(rg.a_full + 8u, 0u);
+#pragma unroll
+        for (int k = 0; k < GSM_RING_STAGES; k++)
+            if (k < nvc) mbar_wait_a(rg.a_full + k * 8u, 0u);
     };
-    // The last warp is the setup warp: per-tree constants now, the Gamma tables while the others repack and run pass A.
-    constexpr int NWORK = BLOCK - 32;
-    const bool setup_warp = warp == NWARP - 1;
     const double* prm = b.params + t * GSM_NPARAM;
-    if (setup_warp && lane == 0)
+    if (warp == NWARP - 1 && lane == 0)
         gsm_setup_scalars(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
     __syncthreads();
+    GSM_PHASE_MARK(0);   // barrier init, TMA requests, per-tree scalars
     mbar_wait(&sh.mbar, 0);
+    GSM_PHASE_MARK(1);   // internal heights + tables landed
     if (!gsm_lean_consts_ok(K)) {   // invalid state (lambda <= mu, shape <= 0, ...): the generic path reproduces the reference
         drain();
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
-    // shared-window base addresses, made opaque so that they stay in registers instead of being re-derived in the loops
-    uint32_t a_h = smem_u32(sh_h), a_aux = smem_u32(sh_aux), a_w = smem_u32(sh_w);
-    asm volatile("" : "+r"(a_h), "+r"(a_aux), "+r"(a_w));
-    if (setup_warp) {
+    GsmLeanC c;
+    gsm_lean_consts(K, c, n);
+    c.t6.log_a = smem_u32(sh_blob.logtab);
+    c.t6.exp_a = smem_u32(sh_blob.exptab);
+    c.t6.rep = static_cast<uint32_t>(lane & 15) * 8u;
+    c.mtab = sh_mtab;
+    c.ntab = sh_ntab;
+    // shared-window addresses of the internal arrays, biased so that node i is at + i * 8
+    LeanBCtx x;
+    x.a_hs = smem_u32(sh_hs) - static_cast<uint32_t>(L4) * 8u;
+    x.a_as = smem_u32(sh_as) - static_cast<uint32_t>(L4) * 8u;
+    x.a_fk = smem_u32(sh_fk) - static_cast<uint32_t>(L4);
+    x.a_hL = x.a_hs + static_cast<uint32_t>(L) * 8u;
+    x.a_aL = x.a_as + static_cast<uint32_t>(L) * 8u;
+    x.a_fL = x.a_fk + static_cast<uint32_t>(L);
+    x.chk_p = 0u;
+    x.nL = static_cast<uint32_t>(n - L);
+
+    // ---- phase 1: Gamma tables (64 lanes), fake flags ----
+    const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);   // sampled ancestors are possible
+    if (tid < GSM_LEAN_MTAB_N - 1) {
         // mtab[m] = {shape m - 1, log shape - logGamma(shape m)}, ntab[m - 1] = {log shape - logGamma(shape m), -log((m - 1)!)}
         // (BSP:97-99 with the Lanczos logGamma of commons-math; STP:567)
+        const int m = tid + 1;
         const double shape = K.shape;
-        const double lsh = log(shape);
         GsmLogEntry e, f;
-#pragma unroll 1
-        for (int m = lane + 1; m < GSM_LEAN_MTAB_N; m += 32) {
-            e.invc = shape * m - 1;
-            e.logc = lsh - lean_log_gamma(shape * m);
-            sh_mtab[m] = e;
-            f.invc = e.logc;
-            f.logc = -g_logfact[m - 1];
-            sh_ntab[m - 1] = f;
-        }
-        if (lane == 0) {
+        e.invc = shape * m - 1;
+        e.logc = gsm_log6_hi(c.t6, shape) - lean_log_gamma(c.t6, shape * m);
+        sh_mtab[m] = e;
+        f.invc = e.logc;
+        f.logc = -g_logfact[m - 1];
+        sh_ntab[m - 1] = f;
+        if (tid == 0) {
             e.invc = -1.0;
             e.logc = 0.0;
             sh_mtab[0] = e;
         }
-    } else {
-        // ---- phase 1: parents -> packed words; BEAST numbering check ----
-        uint32_t over = 0u;   // max of (p - L) as unsigned: >= n - L means a parent index outside [L, n)
-        const uint32_t nL = static_cast<uint32_t>(n - L);
-        bool bad = false;
-        for (int c8 = tid; c8 * 8 < n; c8 += NWORK) {
-            const int4 qa = lds_v4s32(a_aux + c8 * 32), qb = lds_v4s32(a_aux + c8 * 32 + 16);
-            int pv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            if (((qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) < 0) || c8 * 8 + 8 > n) {
-                // chunk holds the root (-1) or runs past the last node: element by element
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int i = c8 * 8 + k;
-                    if (i >= n) pv[k] = L;
-                    else if (pv[k] < 0) {   // root: points to itself; must be an internal node
-                        sh.root = i;
-                        atomicAdd(&sh.nroot, 1);
-                        pv[k] = i;
-                        bad = bad || (i < L);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) over = gsm_umax(over, static_cast<uint32_t>(pv[k] - L));
-            sts_v4u32(a_w + c8 * 16, __byte_perm(pv[0], pv[1], 0x5410), __byte_perm(pv[2], pv[3], 0x5410),
-                      __byte_perm(pv[4], pv[5], 0x5410), __byte_perm(pv[6], pv[7], 0x5410));
-        }
-        if (bad || over >= nL) sh.bad = 1;
-        // the repack reads the landing zone of the parent row, which pass A overwrites with aux: workers only
-        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
     }
+    bool anyda = false;
+    if (detect) {
+        // Node.isDirectAncestor: a leaf at its parent's height -> the parent isFake.  Leaf heights and parents straight from
+        // global memory (the ring will read them again from L2).
+        for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
+        __syncthreads();
+        const double* hrow = b.height + row;
+        const int32_t* prow = b.parent + row;
+        for (int i = tid; i < L; i += BLOCK) {
+            const int32_t p = __ldg(prow + i);
+            if (static_cast<uint32_t>(p - L) < x.nL && __ldg(hrow + i) == lds_f64(x.a_hs + p * 8)) {
+                reinterpret_cast<uint8_t*>(sh_fk)[p - L4] = 1;
+                anyda = true;
+            }
+        }
+    }
+    GSM_PHASE_MARK(2);   // Gamma tables, sampled-ancestor scan
 
-    // ---- phase 2: pass A (workers) ----
-    GsmLeanC c;
-    gsm_lean_consts(K, c, n);
-    c.t6.log_a = smem_u32(sh_blob->logtab);
-    c.t6.exp_a = smem_u32(sh_blob->exptab);
-    c.t6.rep = static_cast<uint32_t>(lane & 15) * 8u;
-    c.mtab = sh_mtab;
-    c.ntab = sh_ntab;
+    // ---- phase 2: pass A: aux of the internal nodes ----
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
-    bool anyda = false;
-    if (!setup_warp && !sh.bad && sh.nroot == 1) {   // (a malformed tree is handed back right after the barrier)
-        if (c.leaf_term == 0) anyda = lean_pass_a<0, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
-        else if (c.leaf_term == 1) anyda = lean_pass_a<1, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
-        else anyda = lean_pass_a<2, NWORK>(c, SA, n, tid, a_h, a_aux, a_w);
+    {
+        const int npa = (n - L4 + 1) >> 1;
+        const uint32_t a_h0 = smem_u32(sh_hs), a_a0 = smem_u32(sh_as);
+#pragma unroll 1
+        for (int j = tid; j < npa; j += BLOCK) {
+            double2 h2 = lds_v2f64(a_h0 + j * 16);
+            if (L4 + 2 * j + 1 >= n) h2.y = h2.x;   // padding slot of the last pair
+            double e0, G0, e1, G1;
+            const double a0 = gsm_lean_aux(c, SA, h2.x, e0, G0);
+            const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
+            sts_v2f64(a_a0 + j * 16, a0, a1);
+        }
     }
+    {
+        GsmLeanAccA S0;
+        gsm_lean_acc_a_zero(S0);
+        x.auxz = gsm_lean_aux(c, S0, 0.0, x.ez, x.Gz);
+    }
+    GSM_PHASE_MARK(3);   // pass A (thread 0's share)
     const bool any = __syncthreads_or(anyda ? 1 : 0) != 0;
-    if (sh.bad || sh.nroot != 1) {
-        drain();
-        if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
-        return;
-    }
-    const int root = sh.root;
-    const bool general = any || root != n - 1;
+    GSM_PHASE_MARK(4);   // waiting for the other warps
+    const bool general = any || !sh.root_last;
 
     // ---- phase 3: pass B ----
     GsmLeanAccB SB;
@@ -765,30 +852,63 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
+    int32_t* rn = &sh.root;   // {root, nroot}
+#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
     if (general) {
-        if (stdw) lean_pass_b<true, WANT_RATES, true, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
-        else lean_pass_b<true, WANT_RATES, false, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
+        if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
+        if (!detect) __syncthreads();
+        if (c.leaf_term == 0) { if (stdw) GSM_PASS_B(true, true, 0); else GSM_PASS_B(true, false, 0); }
+        else if (c.leaf_term == 1) { if (stdw) GSM_PASS_B(true, true, 1); else GSM_PASS_B(true, false, 1); }
+        else { if (stdw) GSM_PASS_B(true, true, 2); else GSM_PASS_B(true, false, 2); }
     } else {
-        if (stdw) lean_pass_b<false, WANT_RATES, true, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
-        else lean_pass_b<false, WANT_RATES, false, BLOCK>(c, SB, rg, n, tid, a_h, a_aux, a_w, orate2, owsp2);
+        if (c.leaf_term == 0) { if (stdw) GSM_PASS_B(false, true, 0); else GSM_PASS_B(false, false, 0); }
+        else if (c.leaf_term == 1) { if (stdw) GSM_PASS_B(false, true, 1); else GSM_PASS_B(false, false, 1); }
+        else { if (stdw) GSM_PASS_B(false, true, 2); else GSM_PASS_B(false, false, 2); }
     }
-    // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree): GENERAL flavour,
-    // own accumulator, one lane of the last warp ----
+#undef GSM_PASS_B
+    // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree) and, when L is odd, the
+    // pair (L-1, L) that straddles the leaf / internal boundary: GENERAL flavour, own accumulators, lanes of the last warp ----
     GsmLeanAccB ST;
     gsm_lean_acc_b_zero(ST);
-    const bool tail_lane = warp == NWARP - 1 && lane == 31;
+    GsmLeanAccA STA;
+    gsm_lean_acc_a_zero(STA);
+    const bool tail_lane = warp == NWARP - 1 && lane >= 29;
     if (tail_lane) {
-        const int i = n - 1;
-        const uint32_t w = sh_w[i];
-        const int p = static_cast<int>(w & 0x7fffu);
-        int32_t nst = -1;
-        if (c.use_counts) nst = b.stub_mode == GSM_STUBS_EXACT ? __ldg(b.nstubs + row + i) : 0;
-        double er, ew;
-        gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, w, sh_w[p], sh_h[i], sh_h[p], sh_aux[i], sh_aux[p],
-                                                    __ldg(b.rate + row + i), __ldg(b.spike + row + i), nst, &er, &ew);
-        if (WANT_RATES) {
-            if (out_rates) out_rates[row + i] = er;
-            if (out_wspikes) out_wspikes[row + i] = ew;
+        int i = -1;
+        if (lane == 31) i = n - 1;
+        else if (L & 1) i = lane == 29 ? L - 1 : L;
+        if (i >= 0) {
+            const double h = __ldg(b.height + row + i);
+            int32_t p = __ldg(b.parent + row + i);
+            const bool root = p < 0;
+            if (root) {
+                atomicAdd(&sh.nroot, 1);
+                sh.root = i;
+                if (i < L) ST.chk = 0xffffffffu;
+                p = i >= L ? i : L;
+            }
+            x.chk_p = gsm_umax(x.chk_p, static_cast<uint32_t>(p - L));
+            if (!(static_cast<uint32_t>(p - L) < x.nL)) p = L;
+            double e, G, aux;
+            if (i < L) aux = gsm_lean_aux(c, STA, h, e, G);
+            else aux = sh_as[i - L4];
+            double hp = sh_hs[p - L4], auxp = sh_as[p - L4];
+            if (root) { hp = h; auxp = aux; }
+            const bool pf = general && sh_fk[p - L4] != 0, fs = general && i >= L && sh_fk[i - L4] != 0;
+            if (i < L) {
+                const bool da = hp == h && !root;
+                if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, STA, !da, h, aux, e, G);
+                else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, STA, !da, h, aux, e, G);
+            }
+            int32_t nst = -1;
+            if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? __ldg(b.nstubs + row + i) : 0;
+            double er, ew;
+            gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, root, pf, fs, h, hp, aux, auxp, __ldg(b.rate + row + i),
+                                                        __ldg(b.spike + row + i), nst, &er, &ew);
+            if (WANT_RATES) {
+                if (out_rates) out_rates[row + i] = er;
+                if (out_wspikes) out_wspikes[row + i] = ew;
+            }
         }
     }
     GsmLean6 s6;
@@ -799,31 +919,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     if (tail_lane) {
         GsmLean6 t6;
-        GsmLeanAccA SA0;
-        gsm_lean_acc_a_zero(SA0);
-        gsm_lean_combine<true>(K, c, SA0, ST, t6);
+        gsm_lean_combine<true>(K, c, STA, ST, t6);
         s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
     }
 
     // ---- phase 4: reductions (fixed order) ----
+    GSM_PHASE_MARK(5);   // pass B (thread 0's share)
     const double v0 = warp_sum(s6.tree), v1 = warp_sum(s6.stub), v2 = warp_sum(s6.spike), v3 = warp_sum(s6.rate),
                  v4 = warp_sum(s6.burst), v5 = warp_sum(s6.dist);
-    const int32_t c0 = 0, c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm),
-                  c2 = __reduce_add_sync(0xffffffffu, SA.n_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + ST.n_fake),
+    const int32_t c0 = 0, c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm + STA.n_leafterm),
+                  c2 = __reduce_add_sync(0xffffffffu, SA.n_plain + STA.n_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + ST.n_fake),
                   c4 = __reduce_add_sync(0xffffffffu, SB.n_extant + ST.n_extant),
                   c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct + ST.n_extinct), c6 = __reduce_add_sync(0xffffffffu, SB.n_da + ST.n_da);
-    const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk)),
-                   u1 = warp_max_u32(gsm_umax(SB.chk_n, ST.chk_n)), u2 = warp_max_u32(SB.chk_len), u3 = warp_max_u32(SA.hmax);
+    const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(gsm_umax(SA.chk, STA.chk), SB.chk), ST.chk)),
+                   u1 = warp_max_u32(gsm_umax(SB.chk_n, ST.chk_n)), u2 = warp_max_u32(SB.chk_len),
+                   u3 = warp_max_u32(gsm_umax(SA.hmax, STA.hmax)), u4 = warp_max_u32(x.chk_p);
     if (lane == 0) {
         sh.red[0][warp] = v0; sh.red[1][warp] = v1; sh.red[2][warp] = v2;
         sh.red[3][warp] = v3; sh.red[4][warp] = v4; sh.red[5][warp] = v5;
         sh.redi[0][warp] = c0; sh.redi[1][warp] = c1; sh.redi[2][warp] = c2; sh.redi[3][warp] = c3;
         sh.redi[4][warp] = c4; sh.redi[5][warp] = c5; sh.redi[6][warp] = c6;
-        sh.redu[0][warp] = u0; sh.redu[1][warp] = u1; sh.redu[2][warp] = u2; sh.redu[3][warp] = u3;
+        sh.redu[0][warp] = u0; sh.redu[1][warp] = u1; sh.redu[2][warp] = u2; sh.redu[3][warp] = u3; sh.redu[4][warp] = u4;
     }
     __syncthreads();
+    GSM_PHASE_MARK(6);   // waiting for the other warps (pass B)
     if (warp == 0) {
-        // lanes 0..5 sum one double each over the warps (fixed order); lanes 8..14 the integers; lanes 16..19 the maxima
+        // lanes 0..5 sum one double each over the warps (fixed order); lanes 8..14 the integers; lanes 16..20 the maxima
         double dv = 0.0;
         int32_t iv = 0;
         uint32_t uv = 0u;
@@ -833,14 +954,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         } else if (lane >= 8 && lane < 15) {
 #pragma unroll
             for (int w = 0; w < NWARP; w++) iv += sh.redi[lane - 8][w];
-        } else if (lane >= 16 && lane < 20) {
+        } else if (lane >= 16 && lane < 21) {
 #pragma unroll
             for (int w = 0; w < NWARP; w++) uv = gsm_umax(uv, sh.redu[lane - 16][w]);
         }
         const uint32_t chk = __shfl_sync(0xffffffffu, uv, 16), chk_n = __shfl_sync(0xffffffffu, uv, 17),
-                       chk_len = __shfl_sync(0xffffffffu, uv, 18), hmax = __shfl_sync(0xffffffffu, uv, 19);
+                       chk_len = __shfl_sync(0xffffffffu, uv, 18), hmax = __shfl_sync(0xffffffffu, uv, 19),
+                       chk_p = __shfl_sync(0xffffffffu, uv, 20);
+        const int root = sh.root;
         bool bad = chk >= GSM_CHK_LIMIT || (c.use_counts && chk_n > static_cast<uint32_t>(GSM_LEAN_MAX_NST)) ||
-                   (!general && chk_len >= GSM_CHK_LIMIT) || hmax >= 0x7ff00000u;
+                   (!general && chk_len >= GSM_CHK_LIMIT) || hmax >= 0x7ff00000u || chk_p >= x.nL || sh.nroot != 1 || root < L;
         if (!bad) bad = !(K.c1 * __hiloint2double(static_cast<int>(hmax) + 1, 0) < 700.0);   // exp(-c1 h) stays in range
         if (bad) {
             if (lane == 0) lean_redo(redo_count, redo_list, rows, t);
@@ -849,12 +972,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             double* rd = reinterpret_cast<double*>(r);
             int32_t* ri = reinterpret_cast<int32_t*>(rd + 7);
             if (lane < 6) rd[lane] = dv;
-            else if (lane == 6) rd[6] = sh_h[root];
+            else if (lane == 6) rd[6] = sh_hs[root - L4];
             else if (lane >= 8 && lane < 15) {
                 // redi order: n_nst, n_leafterm, n_plain, n_fake, n_extant, n_extinct, n_da  == row order
                 ri[lane - 8] = iv;
             } else if (lane == 15) {
-                ri[7] = (sh_w[root] & 0x8000u) ? 1 : 0;
+                ri[7] = (general && sh_fk[root - L4] != 0) ? 1 : 0;
                 ri[8] = 1;
             }
         }
@@ -941,8 +1064,9 @@ size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
 static size_t lean_smem_bytes(int64_t stride, int block) {
-    return static_cast<size_t>(stride) * 18u + sizeof(GsmLeanBlob) + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
-           static_cast<size_t>(block) * 80u;   // + two ring stages of 2 BLOCK nodes x 20 bytes
+    const size_t si = static_cast<size_t>(stride / 2 + 32);   // slots of the internal arrays
+    return si * 16u + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
+           static_cast<size_t>(GSM_RING_STAGES) * block * 64u + ((si + 15u) & ~static_cast<size_t>(15));   // + ring + fake flags
 }
 
 template <typename KERN>

@@ -118,15 +118,16 @@ GSM_HD uint64_t gsm_t6_exp_ld(const GsmT6& t, uint32_t off) {
 }
 
 // ---- table-driven log / exp (arguments must be "regular": see the chk words) ------------------------------------
-// r = z invc - 1 and K = 64 k + i of a positive normal x: log(x) = K ln2/64 + log1p(r)
+// r = z invc - 1 and K = 64 k + i of a positive normal x < 2^1022: log(x) = K ln2/64 + log1p(r).
+// z = 2^-k x is never formed: the power of two goes into the exponent field of the table entry instead (one integer
+// multiply-add on a register the load has just written), and x itself is the FMA operand.
 GSM_HD double gsm_log6_r(const GsmT6& t, double x, int32_t& K) {
-    const int32_t hi = gsm_hi32(x);
-    const int32_t tmp = hi - (int32_t)GSM_LOG6_OFFHI;
+    const int32_t tmp = gsm_hi32(x) - (int32_t)GSM_LOG6_OFFHI;
+    const int32_t kk = tmp >> 20;   // arithmetic shift
     const uint64_t e = gsm_t6_log_ld(t, ((uint32_t)tmp >> 7) & 0x1f80u);
     const int32_t elo = (int32_t)(uint32_t)(e & 0xffffffffu);
-    const double z = gsm_hilo(hi - (tmp & (int32_t)0xfff00000), gsm_lo32(x));
-    K = (tmp >> 20) * 64 + (elo & 63);   // arithmetic shift
-    return fma(z, gsm_hilo((int32_t)(uint32_t)(e >> 32), elo), -1.0);
+    K = kk * 64 + (elo & 63);
+    return fma(x, gsm_hilo((int32_t)(uint32_t)(e >> 32) - kk * (1 << 20), elo), -1.0);
 }
 // log1p(r), |r| <= 0.01218: degree 5, absolute error <= 7e-14 (the per-branch sums)
 GSM_HD double gsm_log6_y3(double r) {
@@ -145,10 +146,9 @@ GSM_HD double gsm_log6_y4(double r) {
     q = fma(q, r, -0.5);
     return fma(q, r2, r);
 }
-// (double)K for |K| < 2^20 without a conversion instruction
-GSM_HD double gsm_k2d(int32_t K) { return gsm_hilo(0x43300000, K + (1 << 20)) - GSM_LK(GSM_LK_KBIAS); }
-// (double)n for 0 <= n < 2^31
-GSM_HD double gsm_u2d(int32_t n) { return gsm_hilo(0x43300000, n) - GSM_LK(GSM_LK_TWO52); }
+// int -> double: the conversion instruction runs on its own pipe, next to the fp64 and integer ones
+GSM_HD double gsm_k2d(int32_t K) { return (double)K; }
+GSM_HD double gsm_u2d(int32_t n) { return (double)n; }
 
 GSM_HD double gsm_log6(const GsmT6& t, double x) {   // degree 5
     int32_t K;
@@ -177,8 +177,8 @@ GSM_HD double gsm_exp6(const GsmT6& t, double x) {
     return fma(scale, em1, scale);
 }
 
-// "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal finite double
-#define GSM_CHK_LIMIT 0x7fe00000u
+// "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal double < 2^1022
+#define GSM_CHK_LIMIT 0x7fc00000u
 GSM_HD uint32_t gsm_chk_pos(double x) { return (uint32_t)(gsm_hi32(x) - 0x00100000); }
 GSM_HD uint32_t gsm_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
@@ -206,8 +206,8 @@ struct GsmLeanC {
 // true when the per-tree constants allow the lean path at all (everything else goes to the generic kernel)
 GSM_HD bool gsm_lean_consts_ok(const GsmTreeConsts& K) {
     if (K.stp_early || K.spike_invalid || K.rate_invalid) return false;
-    const bool fin = (K.c1 >= 0.0) && (K.c1 < INFINITY) && (K.opc2 > 1e-300) && (K.opc2 < INFINITY) && (K.omc2 > -INFINITY) &&
-                     (K.omc2 < INFINITY) && (K.opc2 + K.omc2 > 1e-300);
+    const bool fin = (K.c1 >= 0.0) && (K.c1 < INFINITY) && (K.opc2 > 1e-300) && (K.opc2 < 1e300) && (K.omc2 > -1e300) &&
+                     (K.omc2 < 1e300) && (K.opc2 + K.omc2 > 1e-300);   // G(h) stays a positive normal number < 2^1022
     const bool par = (K.shape > 1e-300) && (K.shape < 1e300) && (K.sigma < 1e150) && (K.base == K.base) &&
                      (K.spike_mean == K.spike_mean) && (fabs(K.kE) < INFINITY) && (fabs(K.kS) < INFINITY) &&
                      (K.psi < 700.0);   // exp(psi) overflow makes STP -inf (STP:176-178): generic path
@@ -295,18 +295,19 @@ GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
     S.chk = S.chk_n = S.chk_len = 0u;
 }
 
-// One node i.  w: own packed word (parent index | FAKE << 15), wp: the parent's word (GENERAL only).
+// One node i.  GENERAL only: root (the node has no parent: the caller passes hp = h, auxp = aux), pf (the parent is
+// fake), fake_self.
 //   GENERAL  false: ordinary tree (no zero-length branch in the main loop); true: any tree
 //   LEAF     1: i < L, 0: i >= L (compile-time for chunks on one side of L), 2: decided here
 //   STDW     the default wiring (stub counts wired to clock model, spike prior and tree prior; relaxed clock) is
 //            compiled in; false: the wiring is read from c
 template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
-GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32_t w, uint32_t wp, double h, double hp,
-                            double aux, double auxp, double rate, double spike, int32_t nst_raw, double* out_rate,
+GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool root, bool parent_fake, bool fake_self, double h,
+                            double hp, double aux, double auxp, double rate, double spike, int32_t nst_raw, double* out_rate,
                             double* out_wspike) {
     const bool use_counts = STDW || c.use_counts, s2p = STDW || c.s2p, s2c = STDW || c.s2c, stub_term = STDW || c.stub_term,
                use_rate = STDW || c.use_rate;
-    const double len = hp - h;                          // a root points to itself: 0
+    const double len = hp - h;                          // root: 0
     const double dA = aux - auxp;
     const double E2 = fma(len, c.kEh, dA);              // half the expected stub count (STP:749-769)
     const bool have_len = len > 0.0;                    // STP:558 / PRCM:229
@@ -314,13 +315,11 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, uint32
     const int32_t ns = s2p ? nst : 0;                   // BSP:81
     const bool leaf = LEAF == 2 ? (i < c.L) : (LEAF == 1);
     int32_t m = ns + 1;                                 // BSP:197-213
-    bool da = false, pf = false, fake_self = false;
+    bool da = false, pf = false;
     if (GENERAL) {
-        const bool root = (int32_t)(w & 0x7fffu) == i;
         const bool zero = len == 0.0;
         da = leaf && zero && !root;                                                     // Node.isDirectAncestor
-        pf = ((wp & 0x8000u) != 0) && !root;                                            // parent isFake
-        fake_self = (w & 0x8000u) != 0;
+        pf = parent_fake && !root;                                                      // parent isFake
         m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
         if (!(have_len || zero)) S.chk = 0xffffffffu;                                   // negative / NaN length
         if (m == 0 && spike != 0.0) S.chk = 0xffffffffu;                                // BSP:86-95 -> -inf

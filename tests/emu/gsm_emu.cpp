@@ -121,39 +121,58 @@ static void init_blob() {
     g_blob_init = true;
 }
 
-// main loop of pass B as the kernel splits it: chunks of 2 BLOCK nodes, each all-leaf, all-internal or mixed; node n-1
-// is the tail
+// pass B as the kernel splits it: leaf pairs (aux of a leaf computed on the spot), internal pairs from L4 = L & ~3 on, the
+// tail (node n-1 and, when L is odd, the pair that straddles L)
 template <bool GENERAL, bool WANT, bool STDW>
-static void lean_b_all(const GsmLeanC& c, GsmLeanAccB& SB, GsmLeanAccB& ST, int n, int32_t stub_mode, const double* h,
-                       const double* aux, const uint16_t* w, const double* rate, const double* spike, const int32_t* nstubs,
+static void lean_b_all(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, GsmLeanAccA& STA, GsmLeanAccB& ST, int n, int32_t stub_mode,
+                       const double* h, const double* aux_int /* [i - L4] */, const int32_t* par, const uint8_t* fk /* [i - L4] */,
+                       const double* rate, const double* spike, const int32_t* nstubs, int* root_out, int* nroot, bool* bad,
                        double* out_rates, double* out_wsp) {
     double dr, dw;
-    const int L = c.L;
-    const int BLOCK = n <= 512 ? 128 : 256;
-    const int npairs = (n - 1) >> 1;
-    auto node = [&](int i, int leaf) {
-        const int p = w[i] & 0x7fff;
-        const int32_t k = nstubs ? nstubs[i] : -1;
+    const int L = c.L, L4 = L & ~3;
+    const uint32_t nL = (uint32_t)(n - L);
+    auto node = [&](int i, int leafclass, GsmLeanAccA& A, GsmLeanAccB& B, bool tail) {
+        int32_t p = par[i];
+        const bool root = p < 0;
+        if (root && (GENERAL || tail)) {
+            ++*nroot;
+            *root_out = i;
+            if (i < L) *bad = true;
+            p = i >= L ? i : L;
+        }
+        if (!((uint32_t)(p - L) < nL)) { *bad = true; p = L; }   // chk_p
+        double e = 0, G = 0, aux;
+        if (i < L) aux = gsm_lean_aux(c, A, h[i], e, G);
+        else aux = aux_int[i - L4];
+        double hp = h[p], auxp = aux_int[p - L4];
+        if (root && (GENERAL || tail)) { hp = h[i]; auxp = aux; }
+        const bool gen = GENERAL || tail;
+        const bool pf = gen && fk[p - L4] != 0, fs = gen && i >= L && fk[i - L4] != 0;
+        if (i < L) {
+            const bool da = gen && hp == h[i] && !root;
+            if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, A, !da, h[i], aux, e, G);
+            else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, A, !da, h[i], aux, e, G);
+        }
+        int32_t k = nstubs ? nstubs[i] : -1;
+        if (tail) {
+            k = -1;
+            if (c.use_counts) k = (i < n - 1 || stub_mode == GSM_STUBS_EXACT) ? (nstubs ? nstubs[i] : 0) : 0;
+        }
         double* o_r = out_rates ? out_rates + i : &dr;
         double* o_w = out_wsp ? out_wsp + i : &dw;
-        if (leaf == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
-        else if (leaf == 0) gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
-        else gsm_lean_b_node<GENERAL, WANT, 2, STDW>(c, SB, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k, o_r, o_w);
+        const bool rt = root && gen;
+        if (tail) gsm_lean_b_node<true, WANT, 2, false>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
+        else if (leafclass == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
+        else gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
     };
-    for (int j = 0; j < npairs; j++) {
-        const int o = (j / BLOCK) * 2 * BLOCK;
-        const int leaf = (o + 2 * BLOCK <= L) ? 1 : (o >= L ? 0 : 2);
-        node(2 * j, leaf);
-        node(2 * j + 1, leaf);
+    for (int i0 = 0; i0 + 1 < L; i0 += 2) { node(i0, 1, SA, SB, false); node(i0 + 1, 1, SA, SB, false); }
+    for (int i0 = L4; i0 + 1 < n - 1; i0 += 2) {
+        if (i0 < L) continue;
+        node(i0, 0, SA, SB, false);
+        node(i0 + 1, 0, SA, SB, false);
     }
-    {   // tail (GENERAL flavour, runtime leaf test and wiring): node n-1
-        const int i = n - 1;
-        const int p = w[i] & 0x7fff;
-        int32_t k = -1;
-        if (c.use_counts) k = stub_mode == GSM_STUBS_EXACT ? (nstubs ? nstubs[i] : 0) : 0;
-        gsm_lean_b_node<true, WANT, 2, false>(c, ST, i, w[i], w[p], h[i], h[p], aux[i], aux[p], rate[i], spike[i], k,
-                                              out_rates ? out_rates + i : &dr, out_wsp ? out_wsp + i : &dw);
-    }
+    if (L & 1) { node(L - 1, 2, STA, ST, true); node(L, 2, STA, ST, true); }
+    node(n - 1, 2, STA, ST, true);
 }
 
 // returns false when the tree is handed back to the generic path
@@ -162,7 +181,7 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
                            const double* rate, const double* spike, const int32_t* nstubs, const double* params,
                            int32_t use_spike, double* out, double* out_rates, double* out_wsp) {
     if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) return false;
-    const int L = (n + 1) >> 1;
+    const int L = (n + 1) >> 1, L4 = L & ~3;
     GsmTreeConsts K;
     memset(&K, 0, sizeof K);
     gsm_setup_scalars(K, params, use_spike, flags, stub_mode);
@@ -176,58 +195,50 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
         ntab[m - 1].logc = -g_logfact_host[m - 1];
     }
     if (!gsm_lean_consts_ok(K)) return false;
-    std::vector<uint16_t> w(n);
-    int root = -1, nroot = 0;
-    bool bad = false;
-    for (int i = 0; i < n; i++) {
-        int p = par_in[i];
-        if (p < 0) { root = i; nroot++; p = i; bad = bad || (i < L); }
-        else bad = bad || p < L || p >= n;
-        w[i] = (uint16_t)(p & 0x7fff);
-    }
-    if (bad || nroot != 1) return false;
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
     c.t6.log_t = g_blob.logtab; c.t6.exp_t = g_blob.exptab; c.mtab = mtab; c.ntab = ntab;
-    GsmLeanAccA SA;
-    gsm_lean_acc_a_zero(SA);
-    std::vector<double> aux(n);
+    const uint32_t nL = (uint32_t)(n - L);
+    // phase 1: sampled-ancestor scan (only where they can occur)
+    const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);
+    std::vector<uint8_t> fk(n - L4 + 8, 0);
     bool anyda = false;
-    for (int i = 0; i < n; i++) {
-        double e, G;
-        aux[i] = gsm_lean_aux(c, SA, h[i], e, G);
-        if (i < L) {
-            const int p = w[i] & 0x7fff;
-            const bool da = h[p] == h[i];
-            if (da) { w[p] |= 0x8000; anyda = true; }
-            if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, SA, !da, h[i], aux[i], e, G);
-            else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, SA, !da, h[i], aux[i], e, G);
+    if (detect)
+        for (int i = 0; i < L; i++) {
+            const int32_t p = par_in[i];
+            if ((uint32_t)(p - L) < nL && h[i] == h[p]) { fk[p - L4] = 1; anyda = true; }
         }
+    // phase 2: aux of the internal nodes (and of the up to three leaves from L4 on)
+    GsmLeanAccA SA, STA;
+    gsm_lean_acc_a_zero(SA);
+    gsm_lean_acc_a_zero(STA);
+    std::vector<double> aux_int(n - L4 + 8, 0.0);
+    for (int i = L4; i < n; i++) {
+        double e, G;
+        aux_int[i - L4] = gsm_lean_aux(c, SA, h[i], e, G);
     }
-    const bool general = anyda || root != n - 1;
+    const bool general = anyda || !(par_in[n - 1] < 0);
     GsmLeanAccB SB, ST;
     gsm_lean_acc_b_zero(SB);
     gsm_lean_acc_b_zero(ST);
     const int32_t* ns = c.use_counts ? nstubs : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
-    if (general) {
-        if (stdw) lean_b_all<true, WANT, true>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
-        else lean_b_all<true, WANT, false>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
-    } else {
-        if (stdw) lean_b_all<false, WANT, true>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
-        else lean_b_all<false, WANT, false>(c, SB, ST, n, stub_mode, h, aux.data(), w.data(), rate, spike, ns, out_rates, out_wsp);
-    }
+    int root = -1, nroot = 0;
+    bool bad = false;
+#define EMU_B(G, W) lean_b_all<G, WANT, W>(c, SA, SB, STA, ST, n, stub_mode, h, aux_int.data(), par_in, fk.data(), rate, spike, ns, &root, &nroot, &bad, out_rates, out_wsp)
+    if (general) { if (stdw) EMU_B(true, true); else EMU_B(true, false); }
+    else { if (stdw) EMU_B(false, true); else EMU_B(false, false); }
+#undef EMU_B
     GsmLean6 s6, t6;
-    GsmLeanAccA SA0;
-    gsm_lean_acc_a_zero(SA0);
     if (general) gsm_lean_combine<true>(K, c, SA, SB, s6);
     else gsm_lean_combine<false>(K, c, SA, SB, s6);
-    gsm_lean_combine<true>(K, c, SA0, ST, t6);
+    gsm_lean_combine<true>(K, c, STA, ST, t6);
     s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
-    const uint32_t chk = gsm_umax(gsm_umax(SA.chk, SB.chk), ST.chk), chk_n = gsm_umax(SB.chk_n, ST.chk_n);
+    const uint32_t chk = gsm_umax(gsm_umax(gsm_umax(SA.chk, STA.chk), SB.chk), ST.chk), chk_n = gsm_umax(SB.chk_n, ST.chk_n);
+    const uint32_t hmax = gsm_umax(SA.hmax, STA.hmax);
     bool redo = chk >= GSM_CHK_LIMIT || (c.use_counts && chk_n > (uint32_t)GSM_LEAN_MAX_NST) ||
-                (!general && SB.chk_len >= GSM_CHK_LIMIT) || SA.hmax >= 0x7ff00000u;
-    if (!redo) redo = !(K.c1 * gsm_hilo((int32_t)SA.hmax + 1, 0) < 700.0);
+                (!general && SB.chk_len >= GSM_CHK_LIMIT) || hmax >= 0x7ff00000u || bad || nroot != 1 || root < L;
+    if (!redo) redo = !(K.c1 * gsm_hilo((int32_t)hmax + 1, 0) < 700.0);
     if (redo) return false;
     // ---- gsm_post_kernel part 1 ----
     GsmTreeConsts K2;
@@ -241,9 +252,9 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     A.n_extant = SB.n_extant + ST.n_extant;
     A.n_extinct = SB.n_extinct + ST.n_extinct;
     A.n_da = SB.n_da + ST.n_da;
-    gsm_lean_finish(K2, c2, s6, 0, SA.n_leafterm, SA.n_plain, SB.n_fake + ST.n_fake, n, A);
+    gsm_lean_finish(K2, c2, s6, 0, SA.n_leafterm + STA.n_leafterm, SA.n_plain + STA.n_plain, SB.n_fake + ST.n_fake, n, A);
     gsm_finish_consts(K2, h[root]);
-    gsm_finalize(K2, A, n, (w[root] & 0x8000) != 0, out);
+    gsm_finalize(K2, A, n, general && fk[root - L4] != 0, out);
     return true;
 }
 

@@ -2,7 +2,11 @@
 """Times gsm_eval_kernel launch configurations on one resident batch (GPU box only; tuning aid)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes
 import torch
+from gammaspikemodel_b200 import _lib
+if os.environ.get("GSM_LIB_PATH"):   # debug build with phase counters (tools/build_dbg.sh)
+    _lib.LIB_PATH = os.environ["GSM_LIB_PATH"]
 from gammaspikemodel_b200 import GsmEngine, abi, synthetic
 
 kind, trees, taxa = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
@@ -22,6 +26,16 @@ for blk, minb in cfgs:
     for _ in range(10): eng.eval_device(out, None, None, st.cuda_stream)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    dbg = getattr(_lib.load(), "gsm_debug_phase_cycles", None) if os.environ.get("GSM_LIB_PATH") else None
+    if dbg is not None:
+        buf = (ctypes.c_ulonglong * 8)()
+        dbg(buf, 1)
+        for _ in range(2): eng.eval_device(out, None, None, st.cuda_stream)
+        torch.cuda.synchronize()
+        dbg(buf, 1)
+        tot = sum(buf) or 1
+        names = ["setup+requests", "wait rows", "repack", "pass A", "wait A/tables", "pass B", "wait B", "-"]
+        print("phase cycles per tree (thread 0): " + ", ".join("%s %.0f (%.0f%%)" % (n, c / (2 * b.n_trees), 100 * c / tot) for n, c in zip(names, buf)), flush=True)
     cur = out.clone()
     same = True if ref is None else bool(torch.equal(torch.nan_to_num(cur), torch.nan_to_num(ref)))
     maxdiff = 0.0 if ref is None else float((torch.nan_to_num(cur) - torch.nan_to_num(ref)).abs().max())
