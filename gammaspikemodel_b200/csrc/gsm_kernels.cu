@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 //   phase 4  per-thread combination to six sums, warp-shuffle + cross-warp reduction, 128-byte scratch row
 // BEAST's numbering (leaves 0..L-1, every parent in [L, n), one root) is validated on the fly (chk_p).
 // ---------------------------------------------------------------------------------------------------------
+#ifndef GSM_RING_STAGES
 #define GSM_RING_STAGES 3
+#endif
 template <int NWARP>
 struct GsmLeanShared {
     GsmTreeConsts K;
@@ -475,8 +477,7 @@ static __device__ __forceinline__ double lean_log_gamma(const GsmT6& t6, double 
 // L4 = L & ~3 on, up to n - 1).  Stage layout (BLOCK = 256: 16 KB):
 //   [rate: 2 BLOCK x 8][spike: 2 BLOCK x 8][height: 2 BLOCK x 8, leaf chunks only][stub count: 2 BLOCK x 4][parent: 2 BLOCK x 4]
 // full mbarrier: arrive.expect_tx by the requester, complete_tx by the copies.  A warp that holds its pairs of a chunk in
-// registers arrives on the stage's empty mbarrier; the warp whose arrival completes the phase requests the chunk three
-// ahead into the stage it has just freed: nobody waits on an empty barrier.
+// registers arrives on the stage's empty mbarrier.
 struct LeanRing {
     uint32_t a_ring;            // shared-window address of stage 0
     uint32_t a_full, a_empty;   // ... of full[0], empty[0]
@@ -502,19 +503,8 @@ static __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
-// arrive; true when this arrival completes the phase (pending count before it was 1)
-static __device__ __forceinline__ bool mbar_arrive_last(uint32_t bar) {
-    uint32_t pending;
-    asm volatile(
-        "{\n"
-        ".reg .b64 st;\n"
-        "mbarrier.arrive.shared::cta.b64 st, [%1];\n"
-        "mbarrier.pending_count.b64 %0, st;\n"
-        "}\n"
-        : "=r"(pending)
-        : "r"(bar)
-        : "memory");
-    return pending == 1u;
+static __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 static __device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src_gmem),
@@ -589,7 +579,7 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
     // parent slots: d = parent - L must be in [0, n - L); a malformed tree is flagged (chk_p) and its gathers clamped
     const uint32_t d0 = static_cast<uint32_t>(pp.x - c.L), d1 = static_cast<uint32_t>(pp.y - c.L);
     x.chk_p = gsm_umax(x.chk_p, gsm_umax(d0, d1));
-    const uint32_t q0 = d0 < x.nL ? d0 : x.nL - 1u, q1 = d1 < x.nL ? d1 : x.nL - 1u;
+    const uint32_t q0 = umin(d0, x.nL - 1u), q1 = umin(d1, x.nL - 1u);
     double hp0 = lds_f64(x.a_hL + q0 * 8), hp1 = lds_f64(x.a_hL + q1 * 8);
     double ap0 = lds_f64(x.a_aL + q0 * 8), ap1 = lds_f64(x.a_aL + q1 * 8);
     bool pf0 = false, pf1 = false, fs0 = false, fs1 = false;
@@ -643,7 +633,14 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
         const int2 pp = lds_v2s32(st + BLOCK * 56u - tid * 8u);
         __syncwarp();
         if ((tid & 31) == 0) {
-            if (mbar_arrive_last(rg.a_empty + s * 8u) && v + GSM_RING_STAGES < rg.nvc) ring_issue<BLOCK>(rg, v + GSM_RING_STAGES, s);
+            mbar_arrive_a(rg.a_empty + s * 8u);
+            // Chunk v + STAGES - 1 goes into the stage chunk v - 1 came from, once every warp has taken its pairs of v - 1.
+            // The requesting duty rotates over the warps, so that no warp falls behind the others because of it.
+            if ((tid >> 5) == (v & (BLOCK / 32 - 1)) && v >= 1 && v + GSM_RING_STAGES - 1 < rg.nvc) {
+                const uint32_t sp = s == 0u ? GSM_RING_STAGES - 1u : s - 1u;
+                mbar_wait_a(rg.a_empty + sp * 8u, (s == 0u ? ph ^ 1u : ph));
+                ring_issue<BLOCK>(rg, v + GSM_RING_STAGES - 1, sp);
+            }
         }
         const bool on = i0 >= lo && i0 + 1 < hi;
         lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT>(c, SA, SB, x, i0, on, rr, ss, h2, kk, pp, sh_root_nroot, orate2, owsp2);
@@ -675,10 +672,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     constexpr int NWARP = BLOCK / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ GsmLeanShared<NWARP> sh;
-    __shared__ GsmLeanBlob sh_blob;   // static: its shared-window address is an instruction immediate
+    // The two replicated tables sit on 8 KB boundaries of the shared window (entry offsets are OR-ed into their addresses):
+    // the dynamic segment carries 8 KB of slack for that.
+    const uint32_t a_dyn = smem_u32(smem_raw);
+    unsigned char* sm0 = smem_raw + ((8192u - (a_dyn & 8191u)) & 8191u);
+    GsmLeanBlob& sh_blob = *reinterpret_cast<GsmLeanBlob*>(sm0);
     const int S = static_cast<int>(b.stride);
     const int SI = (S >> 1) + 32;     // slots of the internal arrays: n - L4 <= (n + 1) / 2 + 3
-    double* sh_hs = reinterpret_cast<double*>(smem_raw);
+    double* sh_hs = reinterpret_cast<double*>(sm0 + sizeof(GsmLeanBlob));
     double* sh_as = sh_hs + SI;
     GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_as + SI);
     GsmLogEntry* sh_ntab = sh_mtab + (GSM_LEAN_MTAB_N + 1);
@@ -766,9 +767,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
-    c.t6.log_a = smem_u32(sh_blob.logtab);
-    c.t6.exp_a = smem_u32(sh_blob.exptab);
-    c.t6.rep = static_cast<uint32_t>(lane & 15) * 8u;
+    c.t6.log_ar = smem_u32(sh_blob.logtab) | (static_cast<uint32_t>(lane & 15) * 8u);
+    c.t6.exp_ar = smem_u32(sh_blob.exptab) | (static_cast<uint32_t>(lane & 15) * 8u);
     c.mtab = sh_mtab;
     c.ntab = sh_ntab;
     // shared-window addresses of the internal arrays, biased so that node i is at + i * 8
@@ -824,10 +824,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     {
+        // the warps that did not compute Gamma table entries take all of pass A (BLOCK = 64: everybody takes part)
+        constexpr int NA = BLOCK > 64 ? BLOCK - 64 : BLOCK;
         const int npa = (n - L4 + 1) >> 1;
         const uint32_t a_h0 = smem_u32(sh_hs), a_a0 = smem_u32(sh_as);
 #pragma unroll 1
-        for (int j = tid; j < npa; j += BLOCK) {
+        for (int j = BLOCK > 64 ? tid - 64 : tid; j < npa && j >= 0; j += NA) {
             double2 h2 = lds_v2f64(a_h0 + j * 16);
             if (L4 + 2 * j + 1 >= n) h2.y = h2.x;   // padding slot of the last pair
             double e0, G0, e1, G1;
@@ -1065,7 +1067,7 @@ size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
 static size_t lean_smem_bytes(int64_t stride, int block) {
     const size_t si = static_cast<size_t>(stride / 2 + 32);   // slots of the internal arrays
-    return si * 16u + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
+    return 8192u + sizeof(GsmLeanBlob) + si * 16u + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
            static_cast<size_t>(GSM_RING_STAGES) * block * 64u + ((si + 15u) & ~static_cast<size_t>(15));   // + ring + fake flags
 }
 

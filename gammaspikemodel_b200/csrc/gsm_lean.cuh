@@ -34,9 +34,9 @@
 // (profiles/r01_v5_lean_ncu_summary.txt: 77 % of the L1/shared pipe, the top unit).  Here every lane of a half-warp
 // owns a replica of the table that lives in its own pair of banks: entry j of replica q is at byte (j * 16 + q) * 8, so
 // an LDS.64 is two wavefronts whatever the indices are.
-//   log: x = 2^k z with z in [c0, 2 c0), c0 ~ 2^(-1/128); entry j (64 linear sub-intervals of z) is invc_j ~ 2^(-i_j/64)
+//   log: x = 2^k z with z in [1, 2); entry j (64 linear sub-intervals of z) is invc_j ~ 2^(-i_j/64)
 //        with i_j = round(64 log2(centre_j)) kept in the low 6 bits of the entry itself.  Then
-//            log(x) = (64 k + i_j) ln2/64 + log1p(r),  r = z invc_j - 1,  |r| <= 0.01218,
+//            log(x) = (64 k + i_j) ln2/64 + log1p(r),  r = z invc_j - 1,  |r| <= 0.01248,
 //        i.e. no second table for log(c_j), and sums of logs collect the integer part in integer registers.
 //   exp: 2^(j/64); |r| <= ln2/128.
 #define GSM_T6_N 64
@@ -84,52 +84,71 @@ static __constant__ double gsm_lean_k_d[GSM_LK_N] = GSM_LK_INIT;
 // one thread's view of the two replicated tables
 struct GsmT6 {
 #if defined(__CUDACC__)
-    uint32_t log_a, exp_a;   // device: shared-window byte addresses of the tables (CTA-uniform)
-    uint32_t rep;            // this lane's replica offset in bytes: (lane & 15) * 8
+    // device: shared-window byte address of the table (8 KB aligned: the entry offset is OR-ed in) | this lane's replica
+    // offset (lane & 15) * 8
+    uint32_t log_ar, exp_ar;
 #else
     const uint64_t* log_t;   // host (CPU-side logic tests): replica 0
     const uint64_t* exp_t;
 #endif
 };
-// entry at byte offset `off` (a multiple of 128) of a table
-GSM_HD uint64_t gsm_t6_log_ld(const GsmT6& t, uint32_t off) {
+// d = (a & c) | b / (a & ~c) | (b & c) in one instruction
+GSM_HD uint32_t gsm_and_or(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
-    uint64_t v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.log_a + (off | t.rep)));
-    return v;
-#elif defined(__CUDACC__)
-    (void)t; (void)off;
-    return 0;
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 #else
-    return t.log_t[off >> 3];
+    return (a & c) | b;
 #endif
 }
-GSM_HD uint64_t gsm_t6_exp_ld(const GsmT6& t, uint32_t off) {
+GSM_HD uint32_t gsm_bitsel(uint32_t a, uint32_t b, uint32_t c) {   // bits of b where c is set, bits of a elsewhere
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return (a & ~c) | (b & c);
+#endif
+}
+// entry j of a table; jb = j << 7 plus arbitrary bits outside 0x1f80
+GSM_HD uint64_t gsm_t6_log_ld(const GsmT6& t, uint32_t jb) {
 #if defined(__CUDA_ARCH__)
     uint64_t v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.exp_a + (off | t.rep)));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(gsm_and_or(jb, t.log_ar, 0x1f80u)));
     return v;
 #elif defined(__CUDACC__)
-    (void)t; (void)off;
+    (void)t; (void)jb;
     return 0;
 #else
-    return t.exp_t[off >> 3];
+    return t.log_t[(jb & 0x1f80u) >> 3];
+#endif
+}
+GSM_HD uint64_t gsm_t6_exp_ld(const GsmT6& t, uint32_t jb) {
+#if defined(__CUDA_ARCH__)
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(gsm_and_or(jb, t.exp_ar, 0x1f80u)));
+    return v;
+#elif defined(__CUDACC__)
+    (void)t; (void)jb;
+    return 0;
+#else
+    return t.exp_t[(jb & 0x1f80u) >> 3];
 #endif
 }
 
 // ---- table-driven log / exp (arguments must be "regular": see the chk words) ------------------------------------
-// r = z invc - 1 and K = 64 k + i of a positive normal x < 2^1022: log(x) = K ln2/64 + log1p(r).
-// z = 2^-k x is never formed: the power of two goes into the exponent field of the table entry instead (one integer
-// multiply-add on a register the load has just written), and x itself is the FMA operand.
+// r = z invc - 1 and K = 64 k + i of a positive normal x: log(x) = K ln2/64 + log1p(r).  Integer work per call: two shifts,
+// three three-input logic operations, one add.
 GSM_HD double gsm_log6_r(const GsmT6& t, double x, int32_t& K) {
-    const int32_t tmp = gsm_hi32(x) - (int32_t)GSM_LOG6_OFFHI;
-    const int32_t kk = tmp >> 20;   // arithmetic shift
-    const uint64_t e = gsm_t6_log_ld(t, ((uint32_t)tmp >> 7) & 0x1f80u);
-    const int32_t elo = (int32_t)(uint32_t)(e & 0xffffffffu);
-    K = kk * 64 + (elo & 63);
-    return fma(x, gsm_hilo((int32_t)(uint32_t)(e >> 32) - kk * (1 << 20), elo), -1.0);
+    const uint32_t hi = (uint32_t)gsm_hi32(x);
+    const uint64_t e = gsm_t6_log_ld(t, hi >> 7);
+    const uint32_t elo = (uint32_t)(e & 0xffffffffu);
+    const double z = gsm_hilo((int32_t)gsm_bitsel(0x3ff00000u, hi, 0x000fffffu), gsm_lo32(x));   // 2^-k x in [1, 2)
+    K = (int32_t)gsm_bitsel(hi >> 14, elo, 63u) - 64 * 1023;
+    return fma(z, gsm_hilo((int32_t)(uint32_t)(e >> 32), (int32_t)elo), -1.0);
 }
-// log1p(r), |r| <= 0.01218: degree 5, absolute error <= 7e-14 (the per-branch sums)
+// log1p(r), |r| <= 0.01248: degree 5, absolute error <= 8e-14 (the per-branch sums)
 GSM_HD double gsm_log6_y3(double r) {
     const double r2 = r * r;
     double q = fma(GSM_LK(GSM_LK_Q3 + 3), r, GSM_LK(GSM_LK_Q3 + 2));
@@ -168,7 +187,7 @@ GSM_HD double gsm_exp6(const GsmT6& t, double x) {
     const int32_t ki = gsm_lo32(kd);
     kd -= GSM_LK(GSM_LK_SHIFT);
     const double r = fma(kd, GSM_LK(GSM_LK_NLN2N), x);
-    const uint64_t e = gsm_t6_exp_ld(t, ((uint32_t)ki & 63u) << 7);
+    const uint64_t e = gsm_t6_exp_ld(t, (uint32_t)ki << 7);
     const double scale = gsm_hilo((int32_t)((uint32_t)(e >> 32) + ((uint32_t)ki << 14)), (int32_t)(uint32_t)(e & 0xffffffffu));
     const double r2 = r * r;
     double q = fma(GSM_LK(GSM_LK_E2 + 2), r, GSM_LK(GSM_LK_E2 + 1));
@@ -177,8 +196,8 @@ GSM_HD double gsm_exp6(const GsmT6& t, double x) {
     return fma(scale, em1, scale);
 }
 
-// "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal double < 2^1022
-#define GSM_CHK_LIMIT 0x7fc00000u
+// "specialness" of a log argument as an unsigned number: >= GSM_CHK_LIMIT unless x is a positive normal finite double
+#define GSM_CHK_LIMIT 0x7fe00000u
 GSM_HD uint32_t gsm_chk_pos(double x) { return (uint32_t)(gsm_hi32(x) - 0x00100000); }
 GSM_HD uint32_t gsm_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
@@ -403,10 +422,21 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
             S.n_extant += (!da && low) ? 1 : 0;
             S.n_extinct += (!da && ext) ? 1 : 0;
         } else {
+#if defined(__CUDA_ARCH__)
+            // two compares, two predicated increments
+            asm("{\n\t.reg .pred lo, ex;\n\t"
+                "setp.le.f64 lo, %2, %4;\n\t"
+                "setp.gt.and.f64 ex, %3, %4, !lo;\n\t"
+                "@lo add.s32 %0, %0, 1;\n\t"
+                "@ex add.s32 %1, %1, 1;\n\t}"
+                : "+r"(S.n_extant), "+r"(S.n_extinct)
+                : "d"(h), "d"(len), "d"(GSM_LK(GSM_LK_LEAF_EPS)));
+#else
             const bool low = h <= GSM_LK(GSM_LK_LEAF_EPS);
             const bool ext = !low && (len > GSM_LK(GSM_LK_LEAF_EPS));
             S.n_extant += low ? 1 : 0;
             S.n_extinct += ext ? 1 : 0;
+#endif
         }
     } else {
         S.auxint += aux;

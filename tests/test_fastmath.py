@@ -55,7 +55,7 @@ def test_lean_log6_exp6_accuracy():
     y1 = np.empty(1)
     one = np.array([1.0])
     emu().gsm_emu_log6_vec(one.ctypes.data_as(C.c_void_p), y1.ctypes.data_as(C.c_void_p), C.c_int64(1), C.c_int32(0))
-    assert y1[0] == 0.0
+    assert abs(y1[0]) < 1e-13
     x = np.concatenate([rng.uniform(-699, 0, 400_000), rng.uniform(-1, 1, 200_000), rng.uniform(-1e-5, 1e-5, 50_000)])
     y = _call(emu().gsm_emu_exp6_vec, x)
     ref = np.exp(x.astype(np.longdouble))
