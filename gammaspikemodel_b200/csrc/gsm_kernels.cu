@@ -461,15 +461,25 @@ static __device__ __forceinline__ void lean_redo(int32_t* __restrict__ redo_coun
     rows[t].status = 0;
 }
 
+// 1 / x for a positive normal x: hardware approximation + two Newton steps (relative error ~1e-16), no special cases
+static __device__ __forceinline__ double lean_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    return fma(fma(-x, r, 1.0), r, r);
+}
 // commons-math Lanczos logGamma (same terms, same summation order as gsm_log_gamma / the Java loop) with reciprocals
 // instead of divisions and the kernel's table-driven logarithm: agrees with the Java value to ~1e-15 relative.
 static __device__ __forceinline__ double lean_log_gamma(const GsmT6& t6, double x) {
+    double q[15];
+#pragma unroll
+    for (int i = 14; i > 0; --i) q[i] = gsm_lanczos_d[i] * lean_rcp(x + i);
     double sum = 0.0;
 #pragma unroll
-    for (int i = 14; i > 0; --i) sum = sum + gsm_lanczos_d[i] * __drcp_rn(x + i);
+    for (int i = 14; i > 0; --i) sum = sum + q[i];
     sum = sum + gsm_lanczos_d[0];
     const double tmp = x + 607.0 / 128.0 + .5;
-    return ((x + .5) * gsm_log6_hi(t6, tmp)) - tmp + 0.91893853320467274178 + gsm_log6_hi(t6, sum * __drcp_rn(x));
+    return ((x + .5) * gsm_log6_hi(t6, tmp)) - tmp + 0.91893853320467274178 + gsm_log6_hi(t6, sum * lean_rcp(x));
 }
 
 // ---- the ring -------------------------------------------------------------------------------------------
@@ -1165,7 +1175,7 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
     int launches = 0;
     if (lean) {
         int block = b.n_nodes <= 512 ? 128 : 256;
-        int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2800 ? 3 : 2);
+        int minb = b.n_nodes <= 512 ? 4 : 2;
         if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
         if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
 #define GSM_CFG(B, M) \
