@@ -23,6 +23,7 @@ __device__ double g_logfact[GSM_LOGFACT_N];
 #ifdef GSM_PHASE_TIMING
 // debug builds (tools/build_dbg.sh): cycles spent by thread 0 of every CTA of the lean kernel between phase boundaries
 __device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_warp_cycles[16];   // pass B duration per warp (lane 0)
 extern "C" int gsm_debug_phase_cycles(unsigned long long* out, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
     if (e == cudaSuccess && reset) {
@@ -31,6 +32,16 @@ extern "C" int gsm_debug_phase_cycles(unsigned long long* out, int reset) {
     }
     return static_cast<int>(e);
 }
+extern "C" int gsm_debug_warp_cycles(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_warp_cycles, sizeof(g_warp_cycles));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {};
+        e = cudaMemcpyToSymbol(g_warp_cycles, z, sizeof(z));
+    }
+    return static_cast<int>(e);
+}
+#define GSM_WARP_T0() const long long tw0_ = clock64()
+#define GSM_WARP_T1(stage) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_warp_cycles[(threadIdx.x >> 5) + 8 * (stage)], static_cast<unsigned long long>(clock64() - tw0_)); } while (0)
 #define GSM_PHASE_MARK(k)                                                          \
     do {                                                                           \
         if (threadIdx.x == 0) {                                                    \
@@ -43,6 +54,8 @@ extern "C" int gsm_debug_phase_cycles(unsigned long long* out, int reset) {
 #else
 #define GSM_PHASE_MARK(k) do { } while (0)
 #define GSM_PHASE_START() do { } while (0)
+#define GSM_WARP_T0() do { } while (0)
+#define GSM_WARP_T1(stage) do { } while (0)
 #endif
 // constant tables of the lean path (stubtab is filled by gsm_init_tables)
 __device__ GsmLeanBlob g_lean_blob;   // replicated log / exp tables, filled by gsm_init_tables
@@ -449,6 +462,11 @@ struct GsmLeanShared {
     uint64_t full[GSM_RING_STAGES];    // ring: chunk landed
     uint64_t empty[GSM_RING_STAGES];   // ring: every warp holds its pairs of the chunk in registers
     int32_t root, nroot, bad, root_last;
+    double tail_d[3][3];     // height, rate, spike of the up to three tail nodes (asynchronous copies, phase 0)
+    int32_t tail_i[3][2];    // parent, stub count
+    double tail_s6[3][6];    // their combined sums ...
+    int32_t tail_c[3][6];    // ... counts (leafterm, plain, fake, extant, extinct, da) ...
+    uint32_t tail_u[3][4];   // ... and check words (chk, chk_n, hmax, chk_p)
     double red[6][NWARP];
     int32_t redi[7][NWARP];
     uint32_t redu[5][NWARP];
@@ -520,6 +538,13 @@ static __device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* 
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src_gmem),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+
+static __device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
 // one thread: request virtual chunk v into stage s
@@ -757,11 +782,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     } else if (tid == 1) {
         sh.root_last = __ldg(b.parent + row + n - 1) < 0 ? 1 : 0;
     }
+    // The tail nodes (node n-1 and, when L is odd, L-1 and L) are evaluated by three lanes after pass B from rows read
+    // straight from global memory: requested now, as asynchronous copies, so that their latency is long gone by then.
+    const bool tail_lane = warp == (NWARP > 1 ? 1 : 0) && lane >= 29;
+    int tail_node = -1;
+    if (tail_lane) {
+        if (lane == 31) tail_node = n - 1;
+        else if (L & 1) tail_node = lane == 29 ? L - 1 : L;
+        if (tail_node >= 0) {
+            const int k = lane - 29;
+            cp_async_8(smem_u32(&sh.tail_d[k][0]), b.height + row + tail_node);
+            cp_async_8(smem_u32(&sh.tail_d[k][1]), b.rate + row + tail_node);
+            cp_async_8(smem_u32(&sh.tail_d[k][2]), b.spike + row + tail_node);
+            cp_async_4(smem_u32(&sh.tail_i[k][0]), b.parent + row + tail_node);
+            if (b.stub_mode != GSM_STUBS_NOSTUB) cp_async_4(smem_u32(&sh.tail_i[k][1]), b.nstubs + row + tail_node);
+        }
+    }
     // before any exit from here on: the bulk copies target this CTA's shared memory and must have landed
     auto drain = [&]() {
 #pragma unroll
         for (int k = 0; k < GSM_RING_STAGES; k++)
             if (k < nvc) mbar_wait_a(rg.a_full + k * 8u, 0u);
+        asm volatile("cp.async.wait_all;" ::: "memory");
     };
     const double* prm = b.params + t * GSM_NPARAM;
     if (warp == NWARP - 1 && lane == 0)
@@ -828,7 +870,64 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             }
         }
     }
-    GSM_PHASE_MARK(2);   // Gamma tables, sampled-ancestor scan
+    // One tail node, evaluated by its lane with the GENERAL flavour; the combined sums go to shared memory.
+    //   early  (right here, for a tree that is certainly ordinary: no sampled-ancestor scan, root = node n-1): the lane
+    //          computes the aux values it needs itself, while the other warps run pass A
+    //   late   (after pass B): aux and the fake flags come from shared memory
+    auto tail_eval = [&](bool early, bool gen) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        const int i = tail_node;
+        const int k = lane - 29;
+        GsmLeanAccB ST;
+        gsm_lean_acc_b_zero(ST);
+        GsmLeanAccA STA;
+        gsm_lean_acc_a_zero(STA);
+        uint32_t chk_p = 0u;
+        const double h = sh.tail_d[k][0];
+        int32_t p = sh.tail_i[k][0];
+        const bool root = p < 0;
+        if (root) {
+            atomicAdd(&sh.nroot, 1);
+            sh.root = i;
+            if (i < L) ST.chk = 0xffffffffu;
+            p = i >= L ? i : L;
+        }
+        chk_p = static_cast<uint32_t>(p - L);
+        if (!(static_cast<uint32_t>(p - L) < x.nL)) p = L;
+        double e, G, aux, ep, Gp;
+        if (i < L || early) aux = gsm_lean_aux(c, STA, h, e, G);
+        else aux = sh_as[i - L4];
+        double hp = sh_hs[p - L4], auxp;
+        if (root) { hp = h; auxp = aux; }
+        else if (early) auxp = gsm_lean_aux(c, STA, hp, ep, Gp);
+        else auxp = sh_as[p - L4];
+        const bool pf = gen && sh_fk[p - L4] != 0, fs = gen && i >= L && sh_fk[i - L4] != 0;
+        if (i < L) {
+            const bool da = hp == h && !root;
+            if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, STA, !da, h, aux, e, G);
+            else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, STA, !da, h, aux, e, G);
+        }
+        int32_t nst = -1;
+        if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? sh.tail_i[k][1] : 0;
+        double er, ew;
+        gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, root, pf, fs, h, hp, aux, auxp, sh.tail_d[k][1], sh.tail_d[k][2], nst, &er,
+                                                    &ew);
+        if (WANT_RATES) {
+            if (out_rates) out_rates[row + i] = er;
+            if (out_wspikes) out_wspikes[row + i] = ew;
+        }
+        GsmLean6 t6;
+        gsm_lean_combine<true>(K, c, STA, ST, t6);
+        double* o = sh.tail_s6[k];
+        o[0] = t6.tree; o[1] = t6.stub; o[2] = t6.spike; o[3] = t6.rate; o[4] = t6.burst; o[5] = t6.dist;
+        int32_t* oc = sh.tail_c[k];
+        oc[0] = STA.n_leafterm; oc[1] = STA.n_plain; oc[2] = ST.n_fake; oc[3] = ST.n_extant; oc[4] = ST.n_extinct; oc[5] = ST.n_da;
+        uint32_t* ou = sh.tail_u[k];
+        ou[0] = gsm_umax(STA.chk, ST.chk); ou[1] = ST.chk_n; ou[2] = STA.hmax; ou[3] = chk_p;
+    };
+    const bool early_tail = !detect && sh.root_last != 0;
+    if (tail_lane && tail_node >= 0 && early_tail) tail_eval(true, false);
+    GSM_PHASE_MARK(2);   // Gamma tables, sampled-ancestor scan, tail nodes
 
     // ---- phase 2: pass A: aux of the internal nodes ----
     GsmLeanAccA SA;
@@ -859,6 +958,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     const bool general = any || !sh.root_last;
 
     // ---- phase 3: pass B ----
+    GSM_WARP_T0();
     GsmLeanAccB SB;
     gsm_lean_acc_b_zero(SB);
     double2* orate2 = (WANT_RATES && out_rates) ? reinterpret_cast<double2*>(out_rates + row) : nullptr;
@@ -878,74 +978,42 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         else { if (stdw) GSM_PASS_B(false, true, 2); else GSM_PASS_B(false, false, 2); }
     }
 #undef GSM_PASS_B
+    GSM_WARP_T1(0);
     // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree) and, when L is odd, the
-    // pair (L-1, L) that straddles the leaf / internal boundary: GENERAL flavour, own accumulators, lanes of the last warp ----
-    GsmLeanAccB ST;
-    gsm_lean_acc_b_zero(ST);
-    GsmLeanAccA STA;
-    gsm_lean_acc_a_zero(STA);
-    const bool tail_lane = warp == NWARP - 1 && lane >= 29;
-    if (tail_lane) {
-        int i = -1;
-        if (lane == 31) i = n - 1;
-        else if (L & 1) i = lane == 29 ? L - 1 : L;
-        if (i >= 0) {
-            const double h = __ldg(b.height + row + i);
-            int32_t p = __ldg(b.parent + row + i);
-            const bool root = p < 0;
-            if (root) {
-                atomicAdd(&sh.nroot, 1);
-                sh.root = i;
-                if (i < L) ST.chk = 0xffffffffu;
-                p = i >= L ? i : L;
-            }
-            x.chk_p = gsm_umax(x.chk_p, static_cast<uint32_t>(p - L));
-            if (!(static_cast<uint32_t>(p - L) < x.nL)) p = L;
-            double e, G, aux;
-            if (i < L) aux = gsm_lean_aux(c, STA, h, e, G);
-            else aux = sh_as[i - L4];
-            double hp = sh_hs[p - L4], auxp = sh_as[p - L4];
-            if (root) { hp = h; auxp = aux; }
-            const bool pf = general && sh_fk[p - L4] != 0, fs = general && i >= L && sh_fk[i - L4] != 0;
-            if (i < L) {
-                const bool da = hp == h && !root;
-                if (c.leaf_term == 1) gsm_lean_leaf_term<1>(c, STA, !da, h, aux, e, G);
-                else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, STA, !da, h, aux, e, G);
-            }
-            int32_t nst = -1;
-            if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? __ldg(b.nstubs + row + i) : 0;
-            double er, ew;
-            gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, root, pf, fs, h, hp, aux, auxp, __ldg(b.rate + row + i),
-                                                        __ldg(b.spike + row + i), nst, &er, &ew);
-            if (WANT_RATES) {
-                if (out_rates) out_rates[row + i] = er;
-                if (out_wspikes) out_wspikes[row + i] = ew;
-            }
-        }
-    }
+    // pair (L-1, L) that straddles the leaf / internal boundary ----
+    const bool tail_on = tail_lane && tail_node >= 0;
+    if (tail_on && !early_tail) tail_eval(false, general);
     GsmLean6 s6;
     if (general) {
         gsm_lean_combine<true>(K, c, SA, SB, s6);
     } else {
         gsm_lean_combine<false>(K, c, SA, SB, s6);
     }
-    if (tail_lane) {
-        GsmLean6 t6;
-        gsm_lean_combine<true>(K, c, STA, ST, t6);
-        s6.tree += t6.tree; s6.stub += t6.stub; s6.spike += t6.spike; s6.rate += t6.rate; s6.burst += t6.burst; s6.dist += t6.dist;
+    int32_t t_leafterm = 0, t_plain = 0, t_fake = 0, t_extant = 0, t_extinct = 0, t_da = 0;
+    uint32_t t_chk = 0u, t_chk_n = 0u, t_hmax = 0u;
+    if (tail_on) {
+        const int k = lane - 29;
+        const double* o = sh.tail_s6[k];
+        s6.tree += o[0]; s6.stub += o[1]; s6.spike += o[2]; s6.rate += o[3]; s6.burst += o[4]; s6.dist += o[5];
+        const int32_t* oc = sh.tail_c[k];
+        t_leafterm = oc[0]; t_plain = oc[1]; t_fake = oc[2]; t_extant = oc[3]; t_extinct = oc[4]; t_da = oc[5];
+        const uint32_t* ou = sh.tail_u[k];
+        t_chk = ou[0]; t_chk_n = ou[1]; t_hmax = ou[2];
+        x.chk_p = gsm_umax(x.chk_p, ou[3]);
     }
 
     // ---- phase 4: reductions (fixed order) ----
+    GSM_WARP_T1(1);
     GSM_PHASE_MARK(5);   // pass B (thread 0's share)
     const double v0 = warp_sum(s6.tree), v1 = warp_sum(s6.stub), v2 = warp_sum(s6.spike), v3 = warp_sum(s6.rate),
                  v4 = warp_sum(s6.burst), v5 = warp_sum(s6.dist);
-    const int32_t c0 = 0, c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm + STA.n_leafterm),
-                  c2 = __reduce_add_sync(0xffffffffu, SA.n_plain + STA.n_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + ST.n_fake),
-                  c4 = __reduce_add_sync(0xffffffffu, SB.n_extant + ST.n_extant),
-                  c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct + ST.n_extinct), c6 = __reduce_add_sync(0xffffffffu, SB.n_da + ST.n_da);
-    const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(gsm_umax(SA.chk, STA.chk), SB.chk), ST.chk)),
-                   u1 = warp_max_u32(gsm_umax(SB.chk_n, ST.chk_n)), u2 = warp_max_u32(SB.chk_len),
-                   u3 = warp_max_u32(gsm_umax(SA.hmax, STA.hmax)), u4 = warp_max_u32(x.chk_p);
+    const int32_t c0 = 0, c1 = __reduce_add_sync(0xffffffffu, SA.n_leafterm + t_leafterm),
+                  c2 = __reduce_add_sync(0xffffffffu, SA.n_plain + t_plain), c3 = __reduce_add_sync(0xffffffffu, SB.n_fake + t_fake),
+                  c4 = __reduce_add_sync(0xffffffffu, SB.n_extant + t_extant),
+                  c5 = __reduce_add_sync(0xffffffffu, SB.n_extinct + t_extinct), c6 = __reduce_add_sync(0xffffffffu, SB.n_da + t_da);
+    const uint32_t u0 = warp_max_u32(gsm_umax(gsm_umax(SA.chk, SB.chk), t_chk)),
+                   u1 = warp_max_u32(gsm_umax(SB.chk_n, t_chk_n)), u2 = warp_max_u32(SB.chk_len),
+                   u3 = warp_max_u32(gsm_umax(SA.hmax, t_hmax)), u4 = warp_max_u32(x.chk_p);
     if (lane == 0) {
         sh.red[0][warp] = v0; sh.red[1][warp] = v1; sh.red[2][warp] = v2;
         sh.red[3][warp] = v3; sh.red[4][warp] = v4; sh.red[5][warp] = v5;

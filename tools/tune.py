@@ -35,6 +35,11 @@ for blk, minb in cfgs:
         dbg(buf, 1)
         tot = sum(buf) or 1
         names = ["setup+requests", "wait rows", "repack", "pass A", "wait A/tables", "pass B", "wait B", "-"]
+        wdbg = getattr(_lib.load(), "gsm_debug_warp_cycles", None)
+        if wdbg is not None:
+            wb = (ctypes.c_ulonglong * 16)()
+            wdbg(wb, 1)
+            print("pass B cycles per tree by warp (chunk loops / + tail + combine): " + " ".join("%.0f/%.0f" % (wb[i] / (2 * b.n_trees), wb[i + 8] / (2 * b.n_trees)) for i in range(8)), flush=True)
         print("phase cycles per tree (thread 0): " + ", ".join("%s %.0f (%.0f%%)" % (n, c / (2 * b.n_trees), 100 * c / tot) for n, c in zip(names, buf)), flush=True)
     cur = out.clone()
     same = True if ref is None else bool(torch.equal(torch.nan_to_num(cur), torch.nan_to_num(ref)))
