@@ -362,7 +362,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "gsm_eval_kernel", "kernel_ms": kern_ms_max,
+                         "traffic": traffic, "kernel": "gsm_lean_kernel", "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }

@@ -926,6 +926,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         ou[0] = gsm_umax(STA.chk, ST.chk); ou[1] = ST.chk_n; ou[2] = STA.hmax; ou[3] = chk_p;
     };
     const bool early_tail = !detect && sh.root_last != 0;
+    // The early tail lanes (warp 1) read Gamma table entries written by warp 0: the two Gamma warps meet on a named
+    // barrier of their own first (they finish their entries at the same time; the pass A warps are not held up).
+    if (early_tail && NWARP > 1 && warp < 2) asm volatile("bar.sync 1, 64;" ::: "memory");
     if (tail_lane && tail_node >= 0 && early_tail) tail_eval(true, false);
     GSM_PHASE_MARK(2);   // Gamma tables, sampled-ancestor scan, tail nodes
 

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/s22_pytest.log
-GSM_LIB_PATH=$PWD/build/libgsm_b200_dbg.so timeout 300 python tools/tune.py C4 20000 2000 256x2 > gpurun_out/s22.log 2>&1
-timeout 300 python tools/tune.py C4 20000 2000 256x2 >> gpurun_out/s22.log 2>&1
-timeout 300 python tools/tune.py C3 20000 1000 256x2 >> gpurun_out/s22.log 2>&1
-timeout 300 python tools/tune.py C2 10000 200 128x4 >> gpurun_out/s22.log 2>&1
-cat gpurun_out/s22_pytest.log gpurun_out/s22.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r1b_pytest.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r1b_bench.json 2> gpurun_out/r1b_bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1b_bench_ref.json 2>> gpurun_out/r1b_bench.err
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gsm_ -c 40 --csv --log-file gpurun_out/r1b_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_list.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:gsm_lean --launch-skip 3 -c 1 -o gpurun_out/prof_r1b_lean -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_full.log 2>&1
+cat gpurun_out/r1b_pytest.log gpurun_out/r1b_bench.json gpurun_out/r1b_bench_ref.json; tail -3 gpurun_out/r1b_bench.err
