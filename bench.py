@@ -25,6 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# keep stdout clean for the JSON line: libraries that print to fd 1 (NCCL "NCCL version ...") go to stderr instead
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
 METRIC = "branch_logp_evals_per_sec"
 UNIT = "branch evals/s"
 BYTES_PER_BRANCH = 32      # height 8 + rate 8 + spike 8 + stub count 4 + parent 4
@@ -100,6 +105,20 @@ class ClockSampler(threading.Thread):
                 "samples": len(vals)}
 
 
+def host_threads():
+    """host cores this process may use (the CPU arm runs OpenMP over trees on all of them)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else written to fd 1 (NCCL's version banner ...) was
+    redirected to stderr at start-up"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def cpu_time(a, flags, mode, threads, target_s):
     """Time the CPU restatement of the reference (oracle/) on host arrays `a`, repeating the pass until about
     `target_s` seconds of work have been measured.  Returns (branch evals / s, seconds, passes)."""
@@ -137,7 +156,7 @@ def run_reference(args, rank):
     import oracle
     from gammaspikemodel_b200 import synthetic
     kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
-    threads = oracle.max_threads()
+    threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     trees = min(trees_per_gpu, 8192)
     batch = synthetic.make_batch_chunked(kind, trees, taxa, seed=synthetic.SEEDS[kind], chunk=2048)
     a = host_sample(batch, trees)
@@ -159,7 +178,7 @@ def run_reference(args, rank):
                                        "OpenMP over trees, C restatement of the Java reference (no JVM in this image)" % (trees, n_nodes)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -327,7 +346,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
-        threads = oracle.max_threads()
+        threads = host_threads()
         t_all, t_one = min(T, 8192), min(T, 512)
         v_all, dt_all, reps_all = cpu_time(host_sample(batch, t_all), batch.flags, batch.stub_mode, threads, 10.0)
         v_one, dt_one, reps_one = cpu_time(host_sample(batch, t_one), batch.flags, batch.stub_mode, 1, 5.0)
@@ -366,7 +385,7 @@ def main():
                          "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if distributed:
         dist.destroy_process_group()

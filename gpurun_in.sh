@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r1b_pytest.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r1b_bench.json 2> gpurun_out/r1b_bench.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1b_bench_ref.json 2>> gpurun_out/r1b_bench.err
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gsm_ -c 40 --csv --log-file gpurun_out/r1b_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_list.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:gsm_lean --launch-skip 3 -c 1 -o gpurun_out/prof_r1b_lean -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_full.log 2>&1
-cat gpurun_out/r1b_pytest.log gpurun_out/r1b_bench.json gpurun_out/r1b_bench_ref.json; tail -3 gpurun_out/r1b_bench.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r1b_bench_n2.json 2> gpurun_out/r1b_bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r1b_bench_ref_n2.json 2>> gpurun_out/r1b_bench_n2.err
+cat gpurun_out/r1b_bench_n2.json gpurun_out/r1b_bench_ref_n2.json; tail -5 gpurun_out/r1b_bench_n2.err
