@@ -455,6 +455,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 #ifndef GSM_RING_STAGES
 #define GSM_RING_STAGES 3
 #endif
+#ifndef GSM_PA_DYN
+#define GSM_PA_DYN 0   // 1: pass A by dynamic batches also for BLOCK >= 256
+#endif
+// node pairs per thread and chunk of pass B: the 128 x 2 configuration (few warps, 255 registers) interleaves two pairs
+__host__ __device__ constexpr int gsm_lean_pairs(int block, int minb) { return (block == 128 && minb == 2) ? 2 : 1; }
+// dynamic shared memory of the lean kernel, as offsets from its start (the shared-window address a_dyn):
+//   [gap up to the next 8 KB boundary | blob: log / exp tables 16 KB | internal heights, aux: si x 16 | ring]
+// "small" = Gamma tables (mtab, ntab) + fake flags: in the gap when they fit there, else after the ring.
+struct GsmLeanLayout {
+    uint32_t blob, small, total;
+};
+__host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si, uint32_t ring_bytes) {
+    GsmLeanLayout l;
+    const uint32_t gap = (8192u - (a_dyn & 8191u)) & 8191u;
+    const uint32_t small = (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * 16u + ((static_cast<uint32_t>(si) + 15u) & ~15u);
+    const uint32_t end = gap + static_cast<uint32_t>(sizeof(GsmLeanBlob)) + static_cast<uint32_t>(si) * 16u + ring_bytes;
+    l.blob = gap;
+    if (gap >= small) {
+        l.small = 0u;
+        l.total = end;
+    } else {
+        l.small = end;
+        l.total = end + small;
+    }
+    return l;
+}
+// ring stages (<= GSM_RING_STAGES)
+__host__ __device__ constexpr int gsm_lean_stages(int block, int minb) { return (void)block, (void)minb, GSM_RING_STAGES; }
 template <int NWARP>
 struct GsmLeanShared {
     GsmTreeConsts K;
@@ -462,6 +490,7 @@ struct GsmLeanShared {
     uint64_t full[GSM_RING_STAGES];    // ring: chunk landed
     uint64_t empty[GSM_RING_STAGES];   // ring: every warp holds its pairs of the chunk in registers
     int32_t root, nroot, bad, root_last;
+    int32_t pa_next;         // pass A: next batch of pairs
     double tail_d[3][3];     // height, rate, spike of the up to three tail nodes (asynchronous copies, phase 0)
     int32_t tail_i[3][2];    // parent, stub count
     double tail_s6[3][6];    // their combined sums ...
@@ -547,10 +576,11 @@ static __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// one thread: request virtual chunk v into stage s
-template <int BLOCK>
+// one thread: request virtual chunk v into stage s.  CH = nodes per chunk (PAIRS node pairs per thread).
+template <int CH>
 static __device__ __forceinline__ void ring_issue(const LeanRing& rg, int v, uint32_t s) {
-    constexpr uint32_t STAGE = BLOCK * 64u;
+    constexpr uint32_t STAGE = CH * 32u;
+    constexpr int BLOCK = CH / 2;   // layout unit below: CH nodes = 2 BLOCK
     const bool leafc = v < rg.nlc;
     const int o = leafc ? v * 2 * BLOCK : rg.L4 + (v - rg.nlc) * 2 * BLOCK;
     int cnt = (leafc ? rg.end_leaf : rg.end_int) - o;
@@ -644,43 +674,61 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
 }
 
 // virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
-// (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK>
+// (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi.  PAIRS node pairs per thread and chunk (pair tid + p BLOCK).
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST>
 static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
                                                      const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
                                                      int32_t* sh_root_nroot, double2* __restrict__ orate2,
                                                      double2* __restrict__ owsp2) {
-    constexpr uint32_t STAGE = BLOCK * 64u;
+    constexpr int HB = BLOCK * PAIRS;            // pairs per chunk
+    constexpr uint32_t STAGE = HB * 64u;
     const bool counts = STDW || rg.nst != nullptr;
-    uint32_t s = static_cast<uint32_t>(v0) % GSM_RING_STAGES;
-    uint32_t ph = (static_cast<uint32_t>(v0) / GSM_RING_STAGES) & 1u;
+    uint32_t s = static_cast<uint32_t>(v0) % NST;
+    uint32_t ph = (static_cast<uint32_t>(v0) / NST) & 1u;
     int i0 = first + 2 * tid;
+    // this thread's slot of stage 0 and the first mbarrier: kept in registers (opaque to the compiler, which otherwise
+    // re-derives them from the kernel parameters in every iteration)
+    uint32_t st0 = rg.a_ring + static_cast<uint32_t>(tid) * 16u, a_full = rg.a_full;
+    uint32_t st1 = st0 - static_cast<uint32_t>(tid) * 8u;   // the 4-byte rows: pair q at + q * 8
+    asm volatile("" : "+r"(st0), "+r"(a_full), "+r"(st1));
+    const uint32_t a_empty = a_full + static_cast<uint32_t>(rg.a_empty - rg.a_full);
 #pragma unroll 1
     for (int v = v0; v < v1; ++v) {
-        mbar_wait_a(rg.a_full + s * 8u, ph);
-        const uint32_t st = rg.a_ring + s * STAGE + tid * 16u;
-        const double2 rr = lds_v2f64(st);
-        const double2 ss = lds_v2f64(st + BLOCK * 16u);
-        double2 h2 = make_double2(0.0, 0.0);
-        if (LEAF == 1) h2 = lds_v2f64(st + BLOCK * 32u);
-        int2 kk = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
-        if (counts) kk = lds_v2s32(st + BLOCK * 48u - tid * 8u);
-        const int2 pp = lds_v2s32(st + BLOCK * 56u - tid * 8u);
+        mbar_wait_a(a_full + s * 8u, ph);
+        double2 rr[PAIRS], ss[PAIRS], h2[PAIRS];
+        int2 kk[PAIRS], pp[PAIRS];
+#pragma unroll
+        for (int p = 0; p < PAIRS; p++) {
+            const uint32_t st = st0 + s * STAGE + static_cast<uint32_t>(p * BLOCK) * 16u;
+            rr[p] = lds_v2f64(st);
+            ss[p] = lds_v2f64(st + HB * 16u);
+            h2[p] = make_double2(0.0, 0.0);
+            if (LEAF == 1) h2[p] = lds_v2f64(st + HB * 32u);
+            kk[p] = make_int2(-1, -1);    // without stub counts getNStubsOnBranch == -1 (Stubs:348-350)
+            const uint32_t sq = st1 + s * STAGE + static_cast<uint32_t>(p * BLOCK) * 8u;
+            if (counts) kk[p] = lds_v2s32(sq + HB * 48u);
+            pp[p] = lds_v2s32(sq + HB * 56u);
+        }
         __syncwarp();
         if ((tid & 31) == 0) {
-            mbar_arrive_a(rg.a_empty + s * 8u);
+            mbar_arrive_a(a_empty + s * 8u);
             // Chunk v + STAGES - 1 goes into the stage chunk v - 1 came from, once every warp has taken its pairs of v - 1.
             // The requesting duty rotates over the warps, so that no warp falls behind the others because of it.
-            if ((tid >> 5) == (v & (BLOCK / 32 - 1)) && v >= 1 && v + GSM_RING_STAGES - 1 < rg.nvc) {
-                const uint32_t sp = s == 0u ? GSM_RING_STAGES - 1u : s - 1u;
-                mbar_wait_a(rg.a_empty + sp * 8u, (s == 0u ? ph ^ 1u : ph));
-                ring_issue<BLOCK>(rg, v + GSM_RING_STAGES - 1, sp);
+            if ((tid >> 5) == (v & (BLOCK / 32 - 1)) && v >= 1 && v + NST - 1 < rg.nvc) {
+                const uint32_t sp = s == 0u ? NST - 1u : s - 1u;
+                mbar_wait_a(a_empty + sp * 8u, (s == 0u ? ph ^ 1u : ph));
+                ring_issue<2 * HB>(rg, v + NST - 1, sp);
             }
         }
-        const bool on = i0 >= lo && i0 + 1 < hi;
-        lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT>(c, SA, SB, x, i0, on, rr, ss, h2, kk, pp, sh_root_nroot, orate2, owsp2);
-        i0 += 2 * BLOCK;
-        if (++s == GSM_RING_STAGES) {
+#pragma unroll
+        for (int p = 0; p < PAIRS; p++) {
+            const int ip = i0 + 2 * p * BLOCK;
+            const bool on = ip >= lo && ip + 1 < hi;
+            lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT>(c, SA, SB, x, ip, on, rr[p], ss[p], h2[p], kk[p], pp[p], sh_root_nroot,
+                                                             orate2, owsp2);
+        }
+        i0 += 2 * HB;
+        if (++s == NST) {
             s = 0u;
             ph ^= 1u;
         }
@@ -689,12 +737,12 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
 
 // main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
 // chunks were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
                                                    int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
                                                    double2* __restrict__ owsp2) {
-    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
-    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
+    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
                                                            orate2, owsp2);
 }
 
@@ -705,21 +753,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
                                                                int32_t* __restrict__ redo_list, double* __restrict__ out_rates,
                                                                double* __restrict__ out_wspikes) {
     constexpr int NWARP = BLOCK / 32;
+    constexpr int PAIRS = gsm_lean_pairs(BLOCK, MINB);   // node pairs per thread and chunk
+    constexpr int HB = BLOCK * PAIRS;                    // pairs per chunk
+    constexpr int NST = gsm_lean_stages(BLOCK, MINB);    // ring stages
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ GsmLeanShared<NWARP> sh;
-    // The two replicated tables sit on 8 KB boundaries of the shared window (entry offsets are OR-ed into their addresses):
-    // the dynamic segment carries 8 KB of slack for that.
+    // The two replicated tables sit on 8 KB boundaries of the shared window (entry offsets are OR-ed into their addresses).
+    // The gap in front of them holds the small per-tree arrays (Gamma tables, fake flags) when it is large enough; the host
+    // sizes the dynamic segment from the same rule (gsm_lean_layout), knowing where it starts (probe launch: rows == nullptr).
     const uint32_t a_dyn = smem_u32(smem_raw);
-    unsigned char* sm0 = smem_raw + ((8192u - (a_dyn & 8191u)) & 8191u);
-    GsmLeanBlob& sh_blob = *reinterpret_cast<GsmLeanBlob*>(sm0);
+    if (rows == nullptr) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) redo_count[0] = static_cast<int32_t>(a_dyn);
+        return;
+    }
     const int S = static_cast<int>(b.stride);
     const int SI = (S >> 1) + 32;     // slots of the internal arrays: n - L4 <= (n + 1) / 2 + 3
+    const GsmLeanLayout lay = gsm_lean_layout(a_dyn, SI, NST * HB * 64);
+    unsigned char* sm0 = smem_raw + lay.blob;
+    GsmLeanBlob& sh_blob = *reinterpret_cast<GsmLeanBlob*>(sm0);
     double* sh_hs = reinterpret_cast<double*>(sm0 + sizeof(GsmLeanBlob));
     double* sh_as = sh_hs + SI;
-    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(sh_as + SI);
+    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_as + SI);   // 16-byte aligned
+    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.small);
     GsmLogEntry* sh_ntab = sh_mtab + (GSM_LEAN_MTAB_N + 1);
-    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_ntab + (GSM_LEAN_MAX_NST + 1));   // 16-byte aligned
-    uint8_t* sh_fk = sh_ring + GSM_RING_STAGES * BLOCK * 64;
+    uint8_t* sh_fk = reinterpret_cast<uint8_t*>(sh_ntab + (GSM_LEAN_MAX_NST + 1));
     GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
@@ -730,6 +787,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     if (t == 0 && tid == 0) *redo_count_next = 0;   // counter of the next evaluation on this handle (ping-pong)
     int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
     if (n > b.n_nodes) n = b.n_nodes;
+    uint32_t dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    if (lay.total > dyn_bytes) n = 0;   // the launch did not provide this layout (cannot happen with launch_lean): generic path
     if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) {   // not a binary BEAST tree the lean path covers
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
@@ -749,8 +809,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     rg.parent = b.parent + row;
     rg.L = L;
     rg.L4 = L4;
-    rg.nlc = ((L >> 1) + BLOCK - 1) / BLOCK;                       // pairs below L: L / 2
-    rg.nvc = rg.nlc + ((n - 1 - L4 + 1) / 2 + BLOCK - 1) / BLOCK;  // pairs (i0, i0 + 1), i0 = L4, L4 + 2, ... with i0 + 1 < n - 1
+    rg.nlc = ((L >> 1) + HB - 1) / HB;                       // pairs below L: L / 2
+    rg.nvc = rg.nlc + ((n - 1 - L4 + 1) / 2 + HB - 1) / HB;  // pairs (i0, i0 + 1), i0 = L4, L4 + 2, ... with i0 + 1 < n - 1
     rg.end_leaf = (L + 3) & ~3;
     rg.end_int = (n - 1 + 3) & ~3;
     const int nvc = rg.nvc;
@@ -759,7 +819,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     if (tid == 0) {
         mbar_init(&sh.mbar, 1);
 #pragma unroll
-        for (int k = 0; k < GSM_RING_STAGES; k++) {
+        for (int k = 0; k < NST; k++) {
             mbar_init(&sh.full[k], 1);
             mbar_init(&sh.empty[k], NWARP);
         }
@@ -767,6 +827,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         sh.root = -1;
         sh.nroot = 0;
         sh.bad = 0;
+        sh.pa_next = 0;
     }
     __syncthreads();
     // requests spread over the warps (a bulk copy costs its issuing thread a few hundred cycles)
@@ -776,8 +837,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             mbar_arrive_expect_tx(&sh.mbar, bytes_h + static_cast<uint32_t>(sizeof(GsmLeanBlob)));
             tma_bulk_g2s(sh_hs, b.height + row + L4, bytes_h, &sh.mbar);
             tma_bulk_g2s(&sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
-        } else if (warp <= GSM_RING_STAGES) {
-            if (warp - 1 < nvc) ring_issue<BLOCK>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
+        } else if (warp <= NST) {
+            if (warp - 1 < nvc) ring_issue<2 * HB>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
         }
     } else if (tid == 1) {
         sh.root_last = __ldg(b.parent + row + n - 1) < 0 ? 1 : 0;
@@ -801,7 +862,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     // before any exit from here on: the bulk copies target this CTA's shared memory and must have landed
     auto drain = [&]() {
 #pragma unroll
-        for (int k = 0; k < GSM_RING_STAGES; k++)
+        for (int k = 0; k < NST; k++)
             if (k < nvc) mbar_wait_a(rg.a_full + k * 8u, 0u);
         asm volatile("cp.async.wait_all;" ::: "memory");
     };
@@ -936,18 +997,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     GsmLeanAccA SA;
     gsm_lean_acc_a_zero(SA);
     {
-        // the warps that did not compute Gamma table entries take all of pass A (BLOCK = 64: everybody takes part)
-        constexpr int NA = BLOCK > 64 ? BLOCK - 64 : BLOCK;
         const int npa = (n - L4 + 1) >> 1;
         const uint32_t a_h0 = smem_u32(sh_hs), a_a0 = smem_u32(sh_as);
-#pragma unroll 1
-        for (int j = BLOCK > 64 ? tid - 64 : tid; j < npa && j >= 0; j += NA) {
+        auto pair_aux = [&](int j) {
             double2 h2 = lds_v2f64(a_h0 + j * 16);
             if (L4 + 2 * j + 1 >= n) h2.y = h2.x;   // padding slot of the last pair
             double e0, G0, e1, G1;
             const double a0 = gsm_lean_aux(c, SA, h2.x, e0, G0);
             const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
             sts_v2f64(a_a0 + j * 16, a0, a1);
+        };
+        if (GSM_PA_DYN || BLOCK < 256) {
+            // Warps take batches of 32 pairs from a shared counter: the two Gamma warps join when their table entries are done.
+#pragma unroll 1
+            for (;;) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&sh.pa_next, 32);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                if (j >= npa) break;
+                j += lane;
+                if (j < npa) pair_aux(j);
+            }
+        } else {
+            // the warps that did not compute Gamma table entries take all of pass A
+#pragma unroll 1
+            for (int j = tid - 64; j < npa && j >= 0; j += BLOCK - 64) pair_aux(j);
         }
     }
     {
@@ -968,7 +1042,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
     int32_t* rn = &sh.root;   // {root, nroot}
-#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
+#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
     if (general) {
         if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
         if (!detect) __syncthreads();
@@ -1146,10 +1220,9 @@ cudaError_t gsm_init_tables() {
 size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
-static size_t lean_smem_bytes(int64_t stride, int block) {
-    const size_t si = static_cast<size_t>(stride / 2 + 32);   // slots of the internal arrays
-    return 8192u + sizeof(GsmLeanBlob) + si * 16u + (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * sizeof(GsmLogEntry) +
-           static_cast<size_t>(GSM_RING_STAGES) * block * 64u + ((si + 15u) & ~static_cast<size_t>(15));   // + ring + fake flags
+static size_t lean_smem_bytes(int64_t stride, int a_dyn, int pairs_per_chunk, int stages) {
+    const int si = static_cast<int>(stride / 2 + 32);   // slots of the internal arrays
+    return gsm_lean_layout(static_cast<uint32_t>(a_dyn), si, static_cast<uint32_t>(stages) * pairs_per_chunk * 64u).total;
 }
 
 template <typename KERN>
@@ -1176,21 +1249,39 @@ static cudaError_t launch_generic(const GsmBatch& b, double* o, double* r, doubl
     return cudaGetLastError();
 }
 
+// shared-window address at which a kernel's dynamic shared memory starts (probe launch, once per kernel and process)
+template <typename KERN>
+static cudaError_t lean_probe(KERN kern, int block, const GsmBatch& b, const GsmScratch& sc, cudaStream_t st, int* a_dyn) {
+    kern<<<1, block, 0, st>>>(b, nullptr, sc.redo + 2, nullptr, nullptr, nullptr, nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int32_t v = 0;
+    if ((e = cudaMemcpyAsync(&v, sc.redo + 2, sizeof v, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    *a_dyn = v;
+    return cudaSuccess;
+}
+
 template <int BLOCK, int MINB>
 static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
-    const size_t smem = lean_smem_bytes(b.stride, BLOCK);
+    static int a_dyn[2] = {-1, -1};
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
     int32_t* cnt = sc.redo + (sc.epoch & 1);
     int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
     int32_t* list = sc.redo + 4;
+    constexpr int HB = BLOCK * gsm_lean_pairs(BLOCK, MINB), NST = gsm_lean_stages(BLOCK, MINB);
     cudaError_t e;
     if (r || w) {
         auto kern = gsm_lean_kernel<BLOCK, MINB, true>;
+        if (a_dyn[1] < 0 && (e = lean_probe(kern, BLOCK, b, sc, st, &a_dyn[1])) != cudaSuccess) return e;
+        const size_t smem = lean_smem_bytes(b.stride, a_dyn[1], HB, NST);
         if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     } else {
         auto kern = gsm_lean_kernel<BLOCK, MINB, false>;
+        if (a_dyn[0] < 0 && (e = lean_probe(kern, BLOCK, b, sc, st, &a_dyn[0])) != cudaSuccess) return e;
+        const size_t smem = lean_smem_bytes(b.stride, a_dyn[0], HB, NST);
         if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     }
@@ -1225,6 +1316,9 @@ static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* 
 
 static int g_sm_count = 0;
 
+// launch configurations of the lean kernel that are compiled in
+#define GSM_LEAN_CFGS GSM_CFG(128, 4) GSM_CFG(128, 3) GSM_CFG(256, 2)
+
 // Launch configuration: one CTA per tree.  The shared-memory footprint per node (18 B lean, 22 B generic) bounds
 // the number of resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in
 // profiles/.  GSM_BLOCK / GSM_MINB / GSM_GENERIC override the choice for tuning runs.
@@ -1245,13 +1339,15 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
     cudaError_t e = cudaErrorInvalidConfiguration;
     int launches = 0;
     if (lean) {
-        int block = b.n_nodes <= 512 ? 128 : 256;
-        int minb = b.n_nodes <= 512 ? 4 : 2;
+        // measured (profiles/r01_tuning.md): small trees want many small CTAs per SM (the per-tree prologue of one CTA
+        // overlaps the main loops of the others); from ~2,000 nodes on shared memory allows two CTAs per SM only
+        int block = b.n_nodes <= 2048 ? 128 : 256;
+        int minb = b.n_nodes <= 512 ? 4 : (b.n_nodes <= 2048 ? 3 : 2);
         if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
         if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
 #define GSM_CFG(B, M) \
     if (block == B && minb == M) e = launch_lean<B, M>(b, sc, d_out_rates, d_out_wspikes, stream);
-        GSM_CFG(128, 6) GSM_CFG(128, 4) GSM_CFG(256, 3) GSM_CFG(256, 2) GSM_CFG(288, 2) GSM_CFG(384, 2) GSM_CFG(512, 1)
+        GSM_LEAN_CFGS
 #undef GSM_CFG
         if (e != cudaSuccess) return -static_cast<int>(e);
         if (b.n_nodes <= 2048) e = launch_post<256, 3>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);
