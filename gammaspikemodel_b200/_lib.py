@@ -26,6 +26,7 @@ SIGNATURES = {
     "gsm_upload_tree_params": (C.c_int, [_vp, _vp, _vp]),
     "gsm_eval": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_eval_host": (C.c_int, [_vp, _i64, _i32] + [_vp] * 11),
+    "gsm_eval_dirty": (C.c_int, [_vp, _i64] + [_vp] * 10),
     "gsm_stub_cdf": (C.c_int, [_vp, _i64, _i32, _vp, _i32, C.POINTER(_i32)]),
     "gsm_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gsm_host_free": (C.c_int, [_vp]),

@@ -56,6 +56,8 @@ struct gsm_handle {
     int64_t slot_trees = 0;
     int64_t slot_stride = 0;
     bool slot_rates = false, slot_wsp = false;
+    unsigned char* d_prop = nullptr;   // device copy of a proposal batch (gsm_eval_dirty), grow-only
+    int64_t prop_cap = 0;
     GsmScratch scratch;          // lean-path scratch of the handle's own stream
     int64_t scratch_trees = 0;
     std::string err;
@@ -232,7 +234,7 @@ int gsm_destroy(gsm_handle* h) {
     free_slots(h);
     dfree(h->d_height); dfree(h->d_rate); dfree(h->d_spike); dfree(h->d_parent); dfree(h->d_nstubs);
     dfree(h->d_node_count); dfree(h->d_params); dfree(h->d_use); dfree(h->d_out); dfree(h->d_out_rates);
-    dfree(h->d_out_wsp); dfree(h->d_cdf);
+    dfree(h->d_out_wsp); dfree(h->d_cdf); dfree(h->d_prop);
     free_scratch(h->scratch, h->scratch_trees);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -428,6 +430,101 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
         GSM_CUDA(h, cudaMemcpyAsync(out_tree + t0 * GSM_NOUT, s.out, T * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (out_rates) GSM_CUDA(h, d2h_rows(out_rates + off, (int64_t)n_nodes, s.out_rates, stride, T, s.stream));
         if (out_wspikes) GSM_CUDA(h, d2h_rows(out_wspikes + off, (int64_t)n_nodes, s.out_wsp, stride, T, s.stream));
+        GSM_CUDA(h, cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (Slot& s : h->slots) {
+        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+        s.busy = false;
+    }
+    return GSM_OK;
+}
+
+int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, const int64_t* dirty_ptr,
+                   const int32_t* dirty_nodes, const double* new_height, const double* new_rate, const double* new_spike,
+                   const int32_t* new_nstubs, const double* new_params, const uint8_t* new_use_spike, double* out_tree) {
+    if (!h) return GSM_E_ARG;
+    if (n_props < 0) return fail(h, GSM_E_ARG, "gsm_eval_dirty: negative n_props");
+    if (n_props == 0) return GSM_OK;
+    if (!tree_of_prop || !dirty_ptr || !out_tree) return fail(h, GSM_E_ARG, "gsm_eval_dirty: NULL required array");
+    GsmBatch src;
+    int rc = resident_batch(h, &src);
+    if (rc != GSM_OK) return rc;
+    const int64_t D = dirty_ptr[n_props];
+    if (dirty_ptr[0] != 0 || D < 0) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_ptr must start at 0 and be non-decreasing");
+    if (D > 0 && !dirty_nodes) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_nodes is NULL");
+    for (int64_t p = 0; p < n_props; p++) {
+        if (tree_of_prop[p] < 0 || tree_of_prop[p] >= src.n_trees)
+            return fail(h, GSM_E_ARG, "gsm_eval_dirty: proposal %lld refers to tree %d of %lld", (long long)p, tree_of_prop[p], (long long)src.n_trees);
+        if (dirty_ptr[p + 1] < dirty_ptr[p]) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_ptr decreases at proposal %lld", (long long)p);
+    }
+    for (int64_t d = 0; d < D; d++)
+        if (dirty_nodes[d] < 0 || dirty_nodes[d] >= src.n_nodes)
+            return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty node %d outside [0, %d)", dirty_nodes[d], src.n_nodes);
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    // ---- proposal arrays -> one device buffer (16-byte aligned sections) ----
+    auto al = [](int64_t v) { return (v + 15) & ~static_cast<int64_t>(15); };
+    const int64_t o_tree = 0, o_ptr = al(o_tree + n_props * 4), o_nodes = al(o_ptr + (n_props + 1) * 8), o_h = al(o_nodes + D * 4),
+                  o_r = al(o_h + (new_height ? D * 8 : 0)), o_s = al(o_r + (new_rate ? D * 8 : 0)), o_k = al(o_s + (new_spike ? D * 8 : 0)),
+                  o_par = al(o_k + (new_nstubs ? D * 4 : 0)), o_use = al(o_par + (new_params ? n_props * GSM_NPARAM * 8 : 0)),
+                  total = al(o_use + (new_use_spike ? n_props : 0)) + 16;
+    if (h->prop_cap < total) {
+        dfree(h->d_prop);
+        h->prop_cap = 0;
+        GSM_CUDA(h, dalloc(&h->d_prop, total));
+        h->prop_cap = total;
+    }
+    unsigned char* base = h->d_prop;
+    auto up = [&](int64_t off, const void* src_, int64_t bytes) -> cudaError_t {
+        if (!src_ || bytes <= 0) return cudaSuccess;
+        return cudaMemcpyAsync(base + off, src_, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, h->stream);
+    };
+    GSM_CUDA(h, up(o_tree, tree_of_prop, n_props * 4));
+    GSM_CUDA(h, up(o_ptr, dirty_ptr, (n_props + 1) * 8));
+    GSM_CUDA(h, up(o_nodes, dirty_nodes, D * 4));
+    GSM_CUDA(h, up(o_h, new_height, D * 8));
+    GSM_CUDA(h, up(o_r, new_rate, D * 8));
+    GSM_CUDA(h, up(o_s, new_spike, D * 8));
+    GSM_CUDA(h, up(o_k, new_nstubs, D * 4));
+    GSM_CUDA(h, up(o_par, new_params, n_props * GSM_NPARAM * 8));
+    GSM_CUDA(h, up(o_use, new_use_spike, n_props));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));   // the slots' streams read this buffer
+    GsmProposals pr{};
+    pr.tree_of_prop = reinterpret_cast<const int32_t*>(base + o_tree);
+    pr.dirty_ptr = reinterpret_cast<const int64_t*>(base + o_ptr);
+    pr.dirty_nodes = reinterpret_cast<const int32_t*>(base + o_nodes);
+    pr.new_height = new_height ? reinterpret_cast<const double*>(base + o_h) : nullptr;
+    pr.new_rate = new_rate ? reinterpret_cast<const double*>(base + o_r) : nullptr;
+    pr.new_spike = new_spike ? reinterpret_cast<const double*>(base + o_s) : nullptr;
+    pr.new_nstubs = new_nstubs ? reinterpret_cast<const int32_t*>(base + o_k) : nullptr;
+    pr.new_params = new_params ? reinterpret_cast<const double*>(base + o_par) : nullptr;
+    pr.new_use_spike = new_use_spike ? reinterpret_cast<const uint8_t*>(base + o_use) : nullptr;
+    // ---- proposed states, chunk by chunk, through the two staging slots ----
+    int64_t chunk_mb = 256;
+    if (const char* env = getenv("GSM_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));   // test hook: force small chunks
+    int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (src.stride * 32));
+    chunk = std::min(chunk, n_props);
+    rc = ensure_slots(h, chunk, src.stride, false, false);
+    if (rc != GSM_OK) return rc;
+    chunk = std::min(h->slot_trees, n_props);
+    int64_t k = 0;
+    for (int64_t p0 = 0; p0 < n_props; p0 += chunk, ++k) {
+        const int64_t P = std::min(chunk, n_props - p0);
+        Slot& s = h->slots[k & 1];
+        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+        GsmBatchMut dst{s.height, s.parent, s.node_count, s.rate, s.spike, s.nstubs, s.params, s.use_spike};
+        int nl = gsm_launch_patch(src, pr, p0, P, dst, s.stream);
+        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty patch launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+        h->launches += nl;
+        GsmBatch b = src;
+        b.n_trees = P;
+        b.height = s.height; b.parent = s.parent; b.node_count = s.node_count;
+        b.rate = src.rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = src.nstubs ? s.nstubs : nullptr;
+        b.params = s.params; b.use_spike = s.use_spike;
+        nl = gsm_launch_eval(b, s.scratch, s.out, nullptr, nullptr, s.stream);
+        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+        h->launches += nl;
+        GSM_CUDA(h, cudaMemcpyAsync(out_tree + p0 * GSM_NOUT, s.out, P * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         GSM_CUDA(h, cudaEventRecord(s.done, s.stream));
         s.busy = true;
     }

@@ -1372,6 +1372,65 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
     return launches;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// proposal batch (gsm_eval_dirty): one CTA per proposal copies the rows of its tree (16-byte accesses) and then
+// applies the proposal's edits
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gsm_patch_kernel(const GsmBatch src, const GsmProposals pr, int64_t p0, const GsmBatchMut dst) {
+    const int64_t q = blockIdx.x;            // row of the destination batch
+    const int64_t p = p0 + q;                // proposal
+    const int64_t t = pr.tree_of_prop[p];
+    const int64_t S = src.stride;
+    const int64_t so = t * S, doff = q * S;
+    const int tid = threadIdx.x;
+    // rows are 128-byte aligned and S % 32 == 0: whole rows as 16-byte words
+    {
+        const double2* h = reinterpret_cast<const double2*>(src.height + so);
+        const double2* s_ = reinterpret_cast<const double2*>(src.spike + so);
+        double2* dh = reinterpret_cast<double2*>(dst.height + doff);
+        double2* ds = reinterpret_cast<double2*>(dst.spike + doff);
+        for (int64_t i = tid; i < S / 2; i += blockDim.x) {
+            dh[i] = h[i];
+            ds[i] = s_[i];
+        }
+        if (src.rate) {
+            const double2* r = reinterpret_cast<const double2*>(src.rate + so);
+            double2* dr = reinterpret_cast<double2*>(dst.rate + doff);
+            for (int64_t i = tid; i < S / 2; i += blockDim.x) dr[i] = r[i];
+        }
+        const int4* pa = reinterpret_cast<const int4*>(src.parent + so);
+        int4* dp = reinterpret_cast<int4*>(dst.parent + doff);
+        for (int64_t i = tid; i < S / 4; i += blockDim.x) dp[i] = pa[i];
+        if (src.nstubs) {
+            const int4* k = reinterpret_cast<const int4*>(src.nstubs + so);
+            int4* dk = reinterpret_cast<int4*>(dst.nstubs + doff);
+            for (int64_t i = tid; i < S / 4; i += blockDim.x) dk[i] = k[i];
+        }
+    }
+    if (tid < GSM_NPARAM) dst.params[q * GSM_NPARAM + tid] = pr.new_params ? pr.new_params[p * GSM_NPARAM + tid] : src.params[t * GSM_NPARAM + tid];
+    if (tid == 32) dst.use_spike[q] = pr.new_use_spike ? pr.new_use_spike[p] : (src.use_spike ? src.use_spike[t] : static_cast<uint8_t>(1));
+    if (tid == 33) dst.node_count[q] = src.node_count ? src.node_count[t] : src.n_nodes;
+    __syncthreads();   // the edits overwrite what this CTA has just copied
+    const int64_t d0 = pr.dirty_ptr[p], d1 = pr.dirty_ptr[p + 1];
+    for (int64_t d = d0 + tid; d < d1; d += blockDim.x) {
+        const int32_t node = pr.dirty_nodes[d];
+        if (node < 0 || node >= src.n_nodes) continue;   // validated on the host as well
+        if (pr.new_height) dst.height[doff + node] = pr.new_height[d];
+        if (pr.new_rate && src.rate) dst.rate[doff + node] = pr.new_rate[d];
+        if (pr.new_spike) dst.spike[doff + node] = pr.new_spike[d];
+        if (pr.new_nstubs && src.nstubs) dst.nstubs[doff + node] = pr.new_nstubs[d];
+    }
+}
+
+int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, int64_t count, const GsmBatchMut& dst,
+                     cudaStream_t stream) {
+    if (count <= 0) return 0;
+    gsm_patch_kernel<<<static_cast<unsigned>(count), 256, 0, stream>>>(src, pr, p0, dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}
+
 int gsm_launch_stub_cdf(const GsmBatch& b, int64_t tree, int32_t node, double* d_cdf, int32_t cap, int32_t* d_len,
                         cudaStream_t stream) {
     gsm_stub_cdf_kernel<<<1, 32, 0, stream>>>(b, tree, node, d_cdf, cap, d_len);

@@ -42,6 +42,26 @@ size_t gsm_scratch_row_bytes();
 int gsm_launch_eval(const GsmBatch& b, GsmScratch& scratch, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                     cudaStream_t stream);
 
+// Proposal batch (gsm_eval_dirty): dst rows [p] = src rows [tree_of_prop[p0 + p]] with the CSR edits of proposal p0 + p
+// applied; dst has the same n_nodes / stride as src.  Device pointers throughout; a null edit array = unchanged.
+struct GsmProposals {
+    const int32_t* tree_of_prop;   // [P]
+    const int64_t* dirty_ptr;      // [P + 1]
+    const int32_t* dirty_nodes;    // [D]
+    const double* new_height;      // [D] or nullptr
+    const double* new_rate;
+    const double* new_spike;
+    const int32_t* new_nstubs;
+    const double* new_params;      // [P][GSM_NPARAM] or nullptr
+    const uint8_t* new_use_spike;  // [P] or nullptr
+};
+struct GsmBatchMut {   // writable twin of GsmBatch's arrays
+    double* height; int32_t* parent; int32_t* node_count; double* rate; double* spike; int32_t* nstubs; double* params;
+    uint8_t* use_spike;
+};
+int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, int64_t count, const GsmBatchMut& dst,
+                     cudaStream_t stream);
+
 // Fills the device-side sum_{i=2..n} log(i) table of the current device (idempotent).
 cudaError_t gsm_init_tables();
 

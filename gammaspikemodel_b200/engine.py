@@ -117,6 +117,26 @@ class GsmEngine:
                                          vp(spike), vp(nstubs), vp(params), vp(use_spike), vp(out_tree), vp(out_rates),
                                          vp(out_wspikes)))
 
+    def eval_dirty(self, tree_of_prop, dirty_ptr, dirty_nodes, new_height=None, new_rate=None, new_spike=None,
+                   new_nstubs=None, new_params=None, new_use_spike=None):
+        """Proposal batch on the resident batch (gsm_eval_dirty): returns out [n_props][NOUT]."""
+        tree_of_prop = _np(tree_of_prop, np.int32)
+        P = tree_of_prop.shape[0]
+        dirty_ptr = _np(dirty_ptr, np.int64, (P + 1,))
+        D = int(dirty_ptr[-1]) if P else 0
+        dirty_nodes = _np(dirty_nodes, np.int32, (D,))
+        new_height = _np(new_height, np.float64, (D,))
+        new_rate = _np(new_rate, np.float64, (D,))
+        new_spike = _np(new_spike, np.float64, (D,))
+        new_nstubs = _np(new_nstubs, np.int32, (D,))
+        new_params = _np(new_params, np.float64, (P, abi.NPARAM))
+        new_use_spike = _np(new_use_spike, np.uint8, (P,))
+        out = np.empty((P, abi.NOUT), np.float64)
+        self._ck(self._lib.gsm_eval_dirty(self._h, P, _p(tree_of_prop), _p(dirty_ptr), _p(dirty_nodes), _p(new_height),
+                                          _p(new_rate), _p(new_spike), _p(new_nstubs), _p(new_params), _p(new_use_spike),
+                                          _p(out)))
+        return out
+
     def stub_cdf(self, tree, node, cap=4096):
         buf = np.empty(cap, np.float64)
         n = C.c_int32(0)

@@ -224,3 +224,81 @@ def make_batch_chunked(kind, n_trees, n_taxa, seed=None, device="cpu", chunk=163
     return Batch(n_trees=n_trees, n_taxa=b0.n_taxa, n_nodes=b0.n_nodes, stride=b0.stride, flags=b0.flags,
                  stub_mode=b0.stub_mode, height=cat("height"), parent=cat("parent"), rate=cat("rate"),
                  spike=cat("spike"), nstubs=cat("nstubs"), params=cat("params"), use_spike=cat("use_spike"), kind=b0.kind)
+
+
+def make_proposals(a, n_props, seed=None, hyper=True):
+    """BASELINE config 5: a batch of MCMC proposals on the host arrays `a` (dense [T][N] numpy arrays as the C ABI takes
+    them), drawn from the operator mix of the reference's template (GammaSpikeClockModel.xml:80-112):
+    ~80 % touch <= 4 branches, ~20 % touch every branch or a per-tree scalar.
+
+        35 %  SpikeUpRateDown (SpikeUpRateDown.java:23-47): one branch, rate * s, spike / s
+        15 %  SpikeFlipOperator (SpikeFlipOperator.java:30-67): one spike redrawn
+        20 %  StumpedTreeConstantDistanceOperator (:61-183): one internal height + the three adjacent rates
+        10 %  stub count +-1 on one branch
+        10 %  StumpedTreeScaler (:63-161): every height scaled
+        10 %  hyper-parameter / indicator move (scale operators on GSMspikeShape, GSMclockSD, lambda; BitFlip on
+              GSMuseSpikeModel): per-tree scalars replaced (only when hyper=True)
+
+    Returns the gsm_eval_dirty arguments as a dict of numpy arrays (CSR)."""
+    import numpy as np
+    rng = np.random.default_rng(SEEDS["C5"] if seed is None else seed)
+    height, parent = a["height"], a["parent"]
+    T, N = height.shape
+    L = (N + 1) // 2
+    tree_of_prop = rng.integers(0, T, n_props).astype(np.int32)
+    kind = rng.choice(6 if hyper else 5, n_props, p=[.35, .15, .20, .10, .10, .10] if hyper else [.35 / .9, .15 / .9, .20 / .9, .10 / .9, .10 / .9])
+    ptr = np.zeros(n_props + 1, np.int64)
+    nodes, nh, nr, ns, nk = [], [], [], [], []
+    new_params = a["params"][tree_of_prop].copy()
+    new_use = a["use_spike"][tree_of_prop].copy()
+    for p in range(n_props):
+        t = int(tree_of_prop[p])
+        h, par, rate, spike, nst = height[t], parent[t], a["rate"][t], a["spike"][t], a["nstubs"][t]
+
+        def put(i, hh=None, rr=None, ss=None, kk=None):
+            nodes.append(i)
+            nh.append(h[i] if hh is None else hh)
+            nr.append(rate[i] if rr is None else rr)
+            ns.append(spike[i] if ss is None else ss)
+            nk.append(nst[i] if kk is None else kk)
+        k = int(kind[p])
+        if k == 0:
+            i = int(rng.integers(0, N - 1))
+            s = float(np.exp(0.3 * rng.standard_normal()))
+            put(i, rr=rate[i] * s, ss=spike[i] / s)
+        elif k == 1:
+            i = int(rng.integers(0, N - 1))
+            put(i, ss=(0.0 if spike[i] == 0.0 else float(rng.exponential(0.5))))
+        elif k == 2:
+            i = int(rng.integers(L, N))
+            ch = np.nonzero(par == i)[0]
+            lo = float(h[ch].max()) if len(ch) else 0.0
+            hi = float(h[par[i]]) if par[i] >= 0 else float(h[i]) * 1.2 + 1e-3
+            put(i, hh=lo + (hi - lo) * float(rng.uniform(0.05, 0.95)), rr=rate[i] * float(rng.uniform(0.8, 1.25)))
+            for c in ch[:2]:
+                put(int(c), rr=rate[c] * float(rng.uniform(0.8, 1.25)))
+        elif k == 3:
+            i = int(rng.integers(0, N - 1))
+            put(i, kk=max(0, int(nst[i]) + (1 if rng.random() < 0.5 else -1)))
+        elif k == 4:
+            s = float(rng.uniform(0.9, 1.1))
+            for i in range(N):
+                put(i, hh=h[i] * s)
+        else:
+            which = int(rng.integers(0, 4))
+            if which == 0:
+                new_params[p, abi.P_SPIKE_SHAPE] *= float(rng.uniform(0.8, 1.25))
+            elif which == 1:
+                new_params[p, abi.P_CLOCK_SD] *= float(rng.uniform(0.8, 1.25))
+            elif which == 2:
+                new_params[p, abi.P_LAMBDA] *= float(rng.uniform(1.0, 1.25))
+            else:
+                new_use[p] = 1 - new_use[p]
+        ptr[p + 1] = len(nodes)
+    out = dict(tree_of_prop=tree_of_prop, dirty_ptr=ptr, dirty_nodes=np.asarray(nodes, np.int32),
+               new_height=np.asarray(nh, np.float64), new_rate=np.asarray(nr, np.float64),
+               new_spike=np.asarray(ns, np.float64), new_nstubs=np.asarray(nk, np.int32))
+    if hyper:
+        out["new_params"] = new_params
+        out["new_use_spike"] = new_use.astype(np.uint8)
+    return out

@@ -138,6 +138,22 @@ int  gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes,
                    const double* params, const uint8_t* use_spike,
                    double* out_tree, double* out_rates, double* out_wspikes);
 
+/* MCMC proposal batch on the resident batch (BASELINE config 5: chains x proposals on one tree each).  The
+ * reference re-evaluates all N branches after every proposal (BSP:294-295, STP:842; the proposals are the operators
+ * SpikeUpRateDown.java:23-47, SpikeFlipOperator.java:30-67, StumpedTreeConstantDistanceOperator.java:61-183,
+ * StumpedTreeScaler.java:63-161, ... and BEAST's scale / bit-flip operators on the hyper-parameters).  Here proposal p
+ * is "tree tree_of_prop[p] of the resident batch with the nodes dirty_nodes[dirty_ptr[p] .. dirty_ptr[p+1]) replaced"
+ * (CSR; the nodes of one proposal must be distinct): new_height / new_rate / new_spike / new_nstubs hold one value per
+ * CSR entry, and a NULL array leaves that quantity as it is.  new_params [n_props][GSM_NPARAM] / new_use_spike
+ * [n_props] (either may be NULL) replace the per-tree scalars: hyper-parameter and indicator moves, which dirty every
+ * branch.  out_tree [n_props][GSM_NOUT] receives the result row of each proposed state, bit-identical to gsm_eval on
+ * that state.  The resident batch itself is not modified (an accepted proposal is uploaded by the caller).  The
+ * proposed states are materialised on the device, chunk by chunk, and run through the same kernels as gsm_eval. */
+int  gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, const int64_t* dirty_ptr,
+                    const int32_t* dirty_nodes, const double* new_height, const double* new_rate,
+                    const double* new_spike, const int32_t* new_nstubs, const double* new_params,
+                    const uint8_t* new_use_spike, double* out_tree);
+
 /* BranchSpikePrior.getCumulativeProbs(mu, nodeNr) (BSP:315-389) for one branch of one resident tree, with
  * mu = StumpedTreePrior.getMeanStubNumber(h_node, h_parent) (STP:876-892) as Stubs.sampleNStubsOnBranch
  * computes it (Stubs:424-447).  Writes min(*len, cap) cumulative probabilities; *len = the Java array length. */

@@ -126,3 +126,18 @@ def variant(a, flags, **edits):
     for k, v in edits.items():
         b["params"][:, idx[k]] = v
     return b
+
+
+def apply_proposals(a, pr):
+    """host arrays of the proposed states [P][N] (what gsm_eval_dirty evaluates): tree tree_of_prop[p] with the CSR edits"""
+    t = pr["tree_of_prop"]
+    b = {k: a[k][t].copy() for k in ("height", "parent", "rate", "spike", "nstubs")}
+    b["params"] = pr["new_params"].copy() if pr.get("new_params") is not None else a["params"][t].copy()
+    b["use_spike"] = pr["new_use_spike"].copy() if pr.get("new_use_spike") is not None else a["use_spike"][t].copy()
+    ptr = pr["dirty_ptr"]
+    rows = np.repeat(np.arange(len(t)), np.diff(ptr))
+    cols = pr["dirty_nodes"]
+    for key, name in (("height", "new_height"), ("rate", "new_rate"), ("spike", "new_spike"), ("nstubs", "new_nstubs")):
+        if pr.get(name) is not None:
+            b[key][rows, cols] = pr[name]
+    return b
