@@ -815,6 +815,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     rg.end_int = (n - 1 + 3) & ~3;
     const int nvc = rg.nvc;
 
+    // global loads whose latency would otherwise sit between the first two barriers: issued before anything else
+    int32_t parent_last = 0;
+    double prm_v[GSM_NPARAM];
+    int32_t use_v = 1;
+    if (tid == 1) parent_last = __ldg(b.parent + row + n - 1);
+    if (warp == NWARP - 1 && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < GSM_NPARAM; k++) prm_v[k] = __ldg(b.params + t * GSM_NPARAM + k);
+        if (b.use_spike) use_v = static_cast<int32_t>(__ldg(b.use_spike + t));
+    }
     // ---- phase 0 ----
     if (tid == 0) {
         mbar_init(&sh.mbar, 1);
@@ -841,7 +851,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             if (warp - 1 < nvc) ring_issue<2 * HB>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
         }
     } else if (tid == 1) {
-        sh.root_last = __ldg(b.parent + row + n - 1) < 0 ? 1 : 0;
+        sh.root_last = parent_last < 0 ? 1 : 0;
     }
     // The tail nodes (node n-1 and, when L is odd, L-1 and L) are evaluated by three lanes after pass B from rows read
     // straight from global memory: requested now, as asynchronous copies, so that their latency is long gone by then.
@@ -866,9 +876,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             if (k < nvc) mbar_wait_a(rg.a_full + k * 8u, 0u);
         asm volatile("cp.async.wait_all;" ::: "memory");
     };
-    const double* prm = b.params + t * GSM_NPARAM;
-    if (warp == NWARP - 1 && lane == 0)
-        gsm_setup_scalars(K, prm, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
+    if (warp == NWARP - 1 && lane == 0) gsm_setup_scalars(K, prm_v, use_v, b.flags, b.stub_mode);
     __syncthreads();
     GSM_PHASE_MARK(0);   // barrier init, TMA requests, per-tree scalars
     mbar_wait(&sh.mbar, 0);
@@ -1019,9 +1027,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
                 if (j < npa) pair_aux(j);
             }
         } else {
-            // the warps that did not compute Gamma table entries take all of pass A
+            // the warps that did not compute Gamma table entries take all of pass A, two pairs (four nodes) at a time
+            constexpr int NA = BLOCK - 64;
 #pragma unroll 1
-            for (int j = tid - 64; j < npa && j >= 0; j += BLOCK - 64) pair_aux(j);
+            for (int j = tid - 64; j < npa && j >= 0; j += 2 * NA) {
+                const int j2 = j + NA;
+                if (j2 < npa) {
+                    const double2 ha = lds_v2f64(a_h0 + j * 16);
+                    double2 hb = lds_v2f64(a_h0 + j2 * 16);
+                    if (L4 + 2 * j2 + 1 >= n) hb.y = hb.x;   // padding slot of the last pair
+                    const double h4[4] = {ha.x, ha.y, hb.x, hb.y};
+                    double a4[4];
+                    gsm_lean_aux4(c, SA, h4, a4);
+                    sts_v2f64(a_a0 + j * 16, a4[0], a4[1]);
+                    sts_v2f64(a_a0 + j2 * 16, a4[2], a4[3]);
+                } else {
+                    pair_aux(j);
+                }
+            }
         }
     }
     {
@@ -1317,7 +1340,11 @@ static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* 
 static int g_sm_count = 0;
 
 // launch configurations of the lean kernel that are compiled in
+#ifdef GSM_DEV_BUILD
+#define GSM_LEAN_CFGS GSM_CFG(256, 2)
+#else
 #define GSM_LEAN_CFGS GSM_CFG(128, 4) GSM_CFG(128, 3) GSM_CFG(256, 2)
+#endif
 
 // Launch configuration: one CTA per tree.  The shared-memory footprint per node (18 B lean, 22 B generic) bounds
 // the number of resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in

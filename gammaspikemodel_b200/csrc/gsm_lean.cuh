@@ -266,6 +266,46 @@ GSM_HD double gsm_lean_aux(const GsmLeanC& c, GsmLeanAccA& S, double h, double& 
     return gsm_log6_hi(c.t6, G);
 }
 
+// aux of four nodes at once, stage by stage (the table loads of the four are issued back to back, the four polynomial
+// chains interleave): the same operations per node as gsm_lean_aux, bit for bit.
+GSM_HD void gsm_lean_aux4(const GsmLeanC& c, GsmLeanAccA& S, const double* h, double* aux) {
+    double r[4];
+    uint64_t e[4];
+    int32_t ki[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        S.hmax = gsm_umax(S.hmax, (uint32_t)gsm_hi32(h[k]));
+        const double x = c.neg_c1 * h[k];
+        double kd = fma(x, GSM_LK(GSM_LK_INVLN2N), GSM_LK(GSM_LK_SHIFT));
+        ki[k] = gsm_lo32(kd);
+        kd -= GSM_LK(GSM_LK_SHIFT);
+        r[k] = fma(kd, GSM_LK(GSM_LK_NLN2N), x);
+        e[k] = gsm_t6_exp_ld(c.t6, (uint32_t)ki[k] << 7);
+    }
+    double G[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double scale = gsm_hilo((int32_t)((uint32_t)(e[k] >> 32) + ((uint32_t)ki[k] << 14)), (int32_t)(uint32_t)(e[k] & 0xffffffffu));
+        const double r2 = r[k] * r[k];
+        double q = fma(GSM_LK(GSM_LK_E2 + 2), r[k], GSM_LK(GSM_LK_E2 + 1));
+        q = fma(q, r[k], 0.5);
+        const double em1 = fma(q, r2, r[k]);
+        G[k] = fma(c.omc2, fma(scale, em1, scale), c.opc2);
+    }
+    uint64_t le[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) le[k] = gsm_t6_log_ld(c.t6, (uint32_t)gsm_hi32(G[k]) >> 7);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t hi = (uint32_t)gsm_hi32(G[k]);
+        const uint32_t elo = (uint32_t)(le[k] & 0xffffffffu);
+        const double z = gsm_hilo((int32_t)gsm_bitsel(0x3ff00000u, hi, 0x000fffffu), gsm_lo32(G[k]));
+        const int32_t K = (int32_t)gsm_bitsel(hi >> 14, elo, 63u) - 64 * 1023;
+        const double rr = fma(z, gsm_hilo((int32_t)(uint32_t)(le[k] >> 32), (int32_t)elo), -1.0);
+        aux[k] = fma(gsm_k2d(K), GSM_LK(GSM_LK_LN2_64), gsm_log6_y4(rr));
+    }
+}
+
 // LT = c.leaf_term (compile-time in the kernel's loops); leaf and not a direct ancestor is decided by the caller
 template <int LT>
 GSM_HD void gsm_lean_leaf_term(const GsmLeanC& c, GsmLeanAccA& S, bool leaf_not_da, double h, double aux, double e, double G) {

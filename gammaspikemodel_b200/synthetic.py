@@ -39,6 +39,12 @@ class Batch:
         kw = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
         return Batch(**kw)
 
+    def rows(self, t0, t1):
+        """trees [t0, t1) as a Batch of views (no copy): a shard or a chunk of a resident batch"""
+        kw = {k: (v[t0:t1] if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
+        kw["n_trees"] = t1 - t0
+        return Batch(**kw)
+
     def dense(self, name):
         """[T, n_nodes] contiguous host numpy view of a branch array (the layout the C ABI takes)."""
         return getattr(self, name)[:, : self.n_nodes].contiguous().cpu().numpy()
