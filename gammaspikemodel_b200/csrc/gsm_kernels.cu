@@ -460,25 +460,46 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 #endif
 // node pairs per thread and chunk of pass B: the 128 x 2 configuration (few warps, 255 registers) interleaves two pairs
 __host__ __device__ constexpr int gsm_lean_pairs(int block, int minb) { return (block == 128 && minb == 2) ? 2 : 1; }
-// dynamic shared memory of the lean kernel, as offsets from its start (the shared-window address a_dyn):
-//   [gap up to the next 8 KB boundary | blob: log / exp tables 16 KB | internal heights, aux: si x 16 | ring]
-// "small" = Gamma tables (mtab, ntab) + fake flags: in the gap when they fit there, else after the ring.
+// dynamic shared memory of the lean kernel, as offsets from its start (the shared-window address a_dyn).  The log table
+// (8 KB) sits on an 8 KB boundary of the window and the exp table (4 KB) on a 4 KB boundary: right in front of the log
+// table when the gap there is large enough, else behind it.  Then internal heights + aux (si x 16 bytes) and the ring.
+// The three small per-tree arrays (mtab, ntab, fake flags) fill what is left of the gap, first fit, else follow the ring.
 struct GsmLeanLayout {
-    uint32_t blob, small, total;
+    uint32_t logtab, exptab, arrays, ring, mtab, ntab, fk, total;
 };
+__host__ __device__ inline int gsm_lean_si(int n_nodes) { return (((n_nodes + 1) >> 1) + 8 + 1) & ~1; }   // n - L4 + pad, even
 __host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si, uint32_t ring_bytes) {
     GsmLeanLayout l;
     const uint32_t gap = (8192u - (a_dyn & 8191u)) & 8191u;
-    const uint32_t small = (GSM_LEAN_MTAB_N + 1 + GSM_LEAN_MAX_NST + 1) * 16u + ((static_cast<uint32_t>(si) + 15u) & ~15u);
-    const uint32_t end = gap + static_cast<uint32_t>(sizeof(GsmLeanBlob)) + static_cast<uint32_t>(si) * 16u + ring_bytes;
-    l.blob = gap;
-    if (gap >= small) {
-        l.small = 0u;
-        l.total = end;
+    uint32_t free0 = 0u, free1 = gap;             // free part of the gap
+    l.logtab = gap;
+    uint32_t end = gap + GSM_T6_WORDS * 8u;
+    if (gap >= GSM_T6E_WORDS * 8u) {
+        l.exptab = gap - GSM_T6E_WORDS * 8u;
+        free1 = l.exptab;
     } else {
-        l.small = end;
-        l.total = end + small;
+        l.exptab = end;
+        end += GSM_T6E_WORDS * 8u;
     }
+    l.arrays = end;
+    end += static_cast<uint32_t>(si) * 16u;
+    l.ring = end;
+    end += ring_bytes;
+    const uint32_t sz[3] = {(GSM_LEAN_MTAB_N + 1) * 16u, (GSM_LEAN_MAX_NST + 1) * 16u, (static_cast<uint32_t>(si) + 15u) & ~15u};
+    uint32_t off[3];
+    for (int k = 0; k < 3; k++) {
+        if (free1 - free0 >= sz[k]) {
+            off[k] = free0;
+            free0 += sz[k];
+        } else {
+            off[k] = end;
+            end += sz[k];
+        }
+    }
+    l.mtab = off[0];
+    l.ntab = off[1];
+    l.fk = off[2];
+    l.total = end;
     return l;
 }
 // ring stages (<= GSM_RING_STAGES)
@@ -767,16 +788,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         return;
     }
     const int S = static_cast<int>(b.stride);
-    const int SI = (S >> 1) + 32;     // slots of the internal arrays: n - L4 <= (n + 1) / 2 + 3
+    const int SI = gsm_lean_si(b.n_nodes);     // slots of the internal arrays: n - L4 <= (n + 1) / 2 + 3, + the pair padding
     const GsmLeanLayout lay = gsm_lean_layout(a_dyn, SI, NST * HB * 64);
-    unsigned char* sm0 = smem_raw + lay.blob;
-    GsmLeanBlob& sh_blob = *reinterpret_cast<GsmLeanBlob*>(sm0);
-    double* sh_hs = reinterpret_cast<double*>(sm0 + sizeof(GsmLeanBlob));
+    uint64_t* sh_logtab = reinterpret_cast<uint64_t*>(smem_raw + lay.logtab);
+    uint64_t* sh_exptab = reinterpret_cast<uint64_t*>(smem_raw + lay.exptab);
+    double* sh_hs = reinterpret_cast<double*>(smem_raw + lay.arrays);
     double* sh_as = sh_hs + SI;
-    unsigned char* sh_ring = reinterpret_cast<unsigned char*>(sh_as + SI);   // 16-byte aligned
-    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.small);
-    GsmLogEntry* sh_ntab = sh_mtab + (GSM_LEAN_MTAB_N + 1);
-    uint8_t* sh_fk = reinterpret_cast<uint8_t*>(sh_ntab + (GSM_LEAN_MAX_NST + 1));
+    unsigned char* sh_ring = smem_raw + lay.ring;   // 16-byte aligned
+    GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.mtab);
+    GsmLogEntry* sh_ntab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.ntab);
+    uint8_t* sh_fk = smem_raw + lay.fk;
     GsmTreeConsts& K = sh.K;
 
     const int tid = threadIdx.x;
@@ -845,8 +866,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         if (warp == 0) {
             const uint32_t bytes_h = (static_cast<uint32_t>(n - L4) * 8u + 15u) & ~15u;
             mbar_arrive_expect_tx(&sh.mbar, bytes_h + static_cast<uint32_t>(sizeof(GsmLeanBlob)));
+            tma_bulk_g2s(sh_exptab, g_lean_blob.exptab, GSM_T6E_WORDS * 8u, &sh.mbar);
             tma_bulk_g2s(sh_hs, b.height + row + L4, bytes_h, &sh.mbar);
-            tma_bulk_g2s(&sh_blob, &g_lean_blob, static_cast<uint32_t>(sizeof(GsmLeanBlob)), &sh.mbar);
+            tma_bulk_g2s(sh_logtab, g_lean_blob.logtab, GSM_T6_WORDS * 8u, &sh.mbar);
         } else if (warp <= NST) {
             if (warp - 1 < nvc) ring_issue<2 * HB>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
         }
@@ -888,8 +910,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
-    c.t6.log_ar = smem_u32(sh_blob.logtab) | (static_cast<uint32_t>(lane & 15) * 8u);
-    c.t6.exp_ar = smem_u32(sh_blob.exptab) | (static_cast<uint32_t>(lane & 15) * 8u);
+    c.t6.log_ar = smem_u32(sh_logtab) | (static_cast<uint32_t>(lane & 15) * 8u);
+    c.t6.exp_ar = smem_u32(sh_exptab) | (static_cast<uint32_t>(lane & 7) * 8u);
     c.mtab = sh_mtab;
     c.ntab = sh_ntab;
     // shared-window addresses of the internal arrays, biased so that node i is at + i * 8
@@ -1243,9 +1265,8 @@ cudaError_t gsm_init_tables() {
 size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
-static size_t lean_smem_bytes(int64_t stride, int a_dyn, int pairs_per_chunk, int stages) {
-    const int si = static_cast<int>(stride / 2 + 32);   // slots of the internal arrays
-    return gsm_lean_layout(static_cast<uint32_t>(a_dyn), si, static_cast<uint32_t>(stages) * pairs_per_chunk * 64u).total;
+static size_t lean_smem_bytes(int32_t n_nodes, int a_dyn, int pairs_per_chunk, int stages) {
+    return gsm_lean_layout(static_cast<uint32_t>(a_dyn), gsm_lean_si(n_nodes), static_cast<uint32_t>(stages) * pairs_per_chunk * 64u).total;
 }
 
 template <typename KERN>
@@ -1285,26 +1306,40 @@ static cudaError_t lean_probe(KERN kern, int block, const GsmBatch& b, const Gsm
     return cudaSuccess;
 }
 
+// dynamic + static + driver-reserved shared memory one CTA of the lean kernel <BLOCK, MINB> takes for this batch
+template <int BLOCK, int MINB>
+static cudaError_t lean_cta_bytes(const GsmBatch& b, const GsmScratch& sc, bool rates, cudaStream_t st, size_t* dyn, size_t* all) {
+    static int a_dyn[2] = {-1, -1};
+    constexpr int HB = BLOCK * gsm_lean_pairs(BLOCK, MINB), NST = gsm_lean_stages(BLOCK, MINB);
+    const int k = rates ? 1 : 0;
+    if (a_dyn[k] < 0) {
+        cudaError_t e;
+        if (rates) e = lean_probe(gsm_lean_kernel<BLOCK, MINB, true>, BLOCK, b, sc, st, &a_dyn[k]);
+        else e = lean_probe(gsm_lean_kernel<BLOCK, MINB, false>, BLOCK, b, sc, st, &a_dyn[k]);
+        if (e != cudaSuccess) return e;
+    }
+    *dyn = lean_smem_bytes(b.n_nodes, a_dyn[k], HB, NST);
+    // the dynamic segment starts at a_dyn = reserved + static (rounded): a_dyn + dyn is the CTA's whole footprint
+    *all = static_cast<size_t>(a_dyn[k]) + *dyn;
+    return cudaSuccess;
+}
+
 template <int BLOCK, int MINB>
 static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
-    static int a_dyn[2] = {-1, -1};
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
     int32_t* cnt = sc.redo + (sc.epoch & 1);
     int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
     int32_t* list = sc.redo + 4;
-    constexpr int HB = BLOCK * gsm_lean_pairs(BLOCK, MINB), NST = gsm_lean_stages(BLOCK, MINB);
     cudaError_t e;
+    size_t smem = 0, all = 0;
+    if ((e = lean_cta_bytes<BLOCK, MINB>(b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
     if (r || w) {
         auto kern = gsm_lean_kernel<BLOCK, MINB, true>;
-        if (a_dyn[1] < 0 && (e = lean_probe(kern, BLOCK, b, sc, st, &a_dyn[1])) != cudaSuccess) return e;
-        const size_t smem = lean_smem_bytes(b.stride, a_dyn[1], HB, NST);
         if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     } else {
         auto kern = gsm_lean_kernel<BLOCK, MINB, false>;
-        if (a_dyn[0] < 0 && (e = lean_probe(kern, BLOCK, b, sc, st, &a_dyn[0])) != cudaSuccess) return e;
-        const size_t smem = lean_smem_bytes(b.stride, a_dyn[0], HB, NST);
         if ((e = prep(kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     }
@@ -1338,10 +1373,11 @@ static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* 
 }
 
 static int g_sm_count = 0;
+static size_t g_smem_per_sm = 0;
 
 // launch configurations of the lean kernel that are compiled in
 #ifdef GSM_DEV_BUILD
-#define GSM_LEAN_CFGS GSM_CFG(256, 2)
+#define GSM_LEAN_CFGS GSM_CFG(256, 2) GSM_CFG(128, 3)
 #else
 #define GSM_LEAN_CFGS GSM_CFG(128, 4) GSM_CFG(128, 3) GSM_CFG(256, 2)
 #endif
@@ -1357,6 +1393,9 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         g_sm_count = n > 0 ? n : 148;
+        int sm_bytes = 0;
+        cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        g_smem_per_sm = sm_bytes > 0 ? static_cast<size_t>(sm_bytes) : 233472u;
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(b.rate) | reinterpret_cast<uintptr_t>(b.spike) |
                            reinterpret_cast<uintptr_t>(b.nstubs) | reinterpret_cast<uintptr_t>(b.height) |
@@ -1368,8 +1407,20 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
     if (lean) {
         // measured (profiles/r01_tuning.md): small trees want many small CTAs per SM (the per-tree prologue of one CTA
         // overlaps the main loops of the others); from ~2,000 nodes on shared memory allows two CTAs per SM only
-        int block = b.n_nodes <= 2048 ? 128 : 256;
-        int minb = b.n_nodes <= 512 ? 4 : (b.n_nodes <= 2048 ? 3 : 2);
+        // 128 x 4 up to 512 nodes; 128 x 3 as long as three of its CTAs fit the SM's shared memory (up to ~4,300 nodes);
+        // 256 x 2 above
+        int block = 128, minb = 4;
+        if (b.n_nodes > 512) {
+            size_t dyn = 0, all = 0;
+            cudaError_t pe = lean_cta_bytes<128, 3>(b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
+            if (pe != cudaSuccess) return -static_cast<int>(pe);
+            if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) <= g_smem_per_sm) {
+                minb = 3;
+            } else {
+                block = 256;
+                minb = 2;
+            }
+        }
         if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
         if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
 #define GSM_CFG(B, M) \

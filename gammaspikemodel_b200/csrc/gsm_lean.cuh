@@ -41,21 +41,25 @@
 //   exp: 2^(j/64); |r| <= ln2/128.
 #define GSM_T6_N 64
 #define GSM_T6_REP 16
-#define GSM_T6_WORDS (GSM_T6_N * GSM_T6_REP)   // uint64 words per replicated table (8 KB)
+#define GSM_T6_WORDS (GSM_T6_N * GSM_T6_REP)   // uint64 words of the replicated log table (8 KB, on an 8 KB boundary)
+// The exp table is looked up once per internal node (pass A) and per leaf above height zero, against ~3.5 log lookups per
+// node: it gets 8 replicas only (entry j of replica q at byte (j * 8 + q) * 8; 4 KB on a 4 KB boundary; two lanes of a
+// half-warp share a replica) and the 4 KB saved decide whether three CTAs fit an SM at 2,000 taxa.
+#define GSM_T6E_REP 8
+#define GSM_T6E_WORDS (GSM_T6_N * GSM_T6E_REP)
 
 // device image of both replicated tables (one TMA bulk copy per CTA); filled by gsm_init_tables / the emulator
 struct __attribute__((aligned(128))) GsmLeanBlob {
     uint64_t logtab[GSM_T6_WORDS];
-    uint64_t exptab[GSM_T6_WORDS];
+    uint64_t exptab[GSM_T6E_WORDS];
 };
 static const uint64_t gsm_log6_tab_h[GSM_LOG6_TAB_N] = GSM_LOG6_TAB_INIT;
 static const uint64_t gsm_exp6_tab_h[GSM_EXP6_TAB_N] = GSM_EXP6_TAB_INIT;
 inline void gsm_lean_blob_fill(GsmLeanBlob& b) {
-    for (int j = 0; j < GSM_T6_N; j++)
-        for (int q = 0; q < GSM_T6_REP; q++) {
-            b.logtab[j * GSM_T6_REP + q] = gsm_log6_tab_h[j];
-            b.exptab[j * GSM_T6_REP + q] = gsm_exp6_tab_h[j];
-        }
+    for (int j = 0; j < GSM_T6_N; j++) {
+        for (int q = 0; q < GSM_T6_REP; q++) b.logtab[j * GSM_T6_REP + q] = gsm_log6_tab_h[j];
+        for (int q = 0; q < GSM_T6E_REP; q++) b.exptab[j * GSM_T6E_REP + q] = gsm_exp6_tab_h[j];
+    }
 }
 
 GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
@@ -84,8 +88,8 @@ static __constant__ double gsm_lean_k_d[GSM_LK_N] = GSM_LK_INIT;
 // one thread's view of the two replicated tables
 struct GsmT6 {
 #if defined(__CUDACC__)
-    // device: shared-window byte address of the table (8 KB aligned: the entry offset is OR-ed in) | this lane's replica
-    // offset (lane & 15) * 8
+    // device: shared-window byte address of the table (log: 8 KB aligned, exp: 4 KB aligned: the entry offset is OR-ed in)
+    // | this lane's replica offset (log: (lane & 15) * 8, exp: (lane & 7) * 8)
     uint32_t log_ar, exp_ar;
 #else
     const uint64_t* log_t;   // host (CPU-side logic tests): replica 0
@@ -124,16 +128,17 @@ GSM_HD uint64_t gsm_t6_log_ld(const GsmT6& t, uint32_t jb) {
     return t.log_t[(jb & 0x1f80u) >> 3];
 #endif
 }
+// exp table: jb = j << 6 plus arbitrary bits outside 0xfc0
 GSM_HD uint64_t gsm_t6_exp_ld(const GsmT6& t, uint32_t jb) {
 #if defined(__CUDA_ARCH__)
     uint64_t v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(gsm_and_or(jb, t.exp_ar, 0x1f80u)));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(gsm_and_or(jb, t.exp_ar, 0xfc0u)));
     return v;
 #elif defined(__CUDACC__)
     (void)t; (void)jb;
     return 0;
 #else
-    return t.exp_t[(jb & 0x1f80u) >> 3];
+    return t.exp_t[(jb & 0xfc0u) >> 3];
 #endif
 }
 
@@ -187,7 +192,7 @@ GSM_HD double gsm_exp6(const GsmT6& t, double x) {
     const int32_t ki = gsm_lo32(kd);
     kd -= GSM_LK(GSM_LK_SHIFT);
     const double r = fma(kd, GSM_LK(GSM_LK_NLN2N), x);
-    const uint64_t e = gsm_t6_exp_ld(t, (uint32_t)ki << 7);
+    const uint64_t e = gsm_t6_exp_ld(t, (uint32_t)ki << 6);
     const double scale = gsm_hilo((int32_t)((uint32_t)(e >> 32) + ((uint32_t)ki << 14)), (int32_t)(uint32_t)(e & 0xffffffffu));
     const double r2 = r * r;
     double q = fma(GSM_LK(GSM_LK_E2 + 2), r, GSM_LK(GSM_LK_E2 + 1));
@@ -280,7 +285,7 @@ GSM_HD void gsm_lean_aux4(const GsmLeanC& c, GsmLeanAccA& S, const double* h, do
         ki[k] = gsm_lo32(kd);
         kd -= GSM_LK(GSM_LK_SHIFT);
         r[k] = fma(kd, GSM_LK(GSM_LK_NLN2N), x);
-        e[k] = gsm_t6_exp_ld(c.t6, (uint32_t)ki[k] << 7);
+        e[k] = gsm_t6_exp_ld(c.t6, (uint32_t)ki[k] << 6);
     }
     double G[4];
 #pragma unroll
