@@ -6,8 +6,8 @@
 
 One step = one pass of the hot path (clock-rate map + spike / rate / stub prior logP + tree prior +
 ProportionOfSaltation sums) over one resident synthetic batch: gsm_lean_kernel + gsm_post_kernel per rank; at N>1
-the shard is evaluated in 4 chunks and the NCCL all-gather of a chunk's per-tree result rows (the only collective on
-the path) overlaps the next chunk's kernels.
+the NCCL all-gather of a step's per-tree result rows (the only collective on the path) runs on a second stream and
+overlaps the next step's kernels.
 Default workload: the per-GPU shard of BASELINE config 4 (1M trees x 2,000 taxa over 8 GPUs =
 125,000 trees x 3,999 nodes per GPU, 16 GB of inputs, far larger than L2); scaling is weak, so N=8 is
 exactly the 1M-tree configuration.
@@ -232,49 +232,46 @@ def main():
     T, N, S = batch.n_trees, batch.n_nodes, batch.stride
     branches = T * N
 
-    # One evaluation of the shard = `chunks` launches of the hot path on consecutive tree ranges.  At N > 1 the NCCL
-    # all-gather of a chunk's result rows runs on a second stream while the next chunk is evaluated; at
-    # N = 1 there is no exchange and the shard is one chunk.
-    distributed_chunks = 4 if T >= 4096 else 1
-    chunks = distributed_chunks if distributed else 1
-    bounds = [(c * T) // chunks for c in range(chunks + 1)]
-    out = torch.empty((T, abi.NOUT), dtype=torch.float64, device=dev)
+    # One step = one evaluation of the whole shard (gsm_lean_kernel + gsm_post_kernel).  At N > 1 the NCCL all-gather of
+    # a step's result rows (the only collective on the path, 64 B per tree) is issued on a second stream and overlaps the
+    # next step's kernels: two result buffers alternate, and a buffer is rewritten only after its gather has finished.
+    nbuf = 2 if distributed else 1
+    out_b = [torch.empty((T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)]
     out_rates = torch.empty((T, S), dtype=torch.float64, device=dev) if args.want_rates else None
-    engs, outs, rates_c, gathered = [], [], [], []
-    for c in range(chunks):
-        t0, t1 = bounds[c], bounds[c + 1]
-        e = GsmEngine(device=local_rank)
-        e.set_mode(batch.stub_mode, batch.flags)
-        e.bind_batch(batch.rows(t0, t1))
-        engs.append(e)
-        outs.append(out[t0:t1])
-        rates_c.append(out_rates[t0:t1] if out_rates is not None else None)
-        gathered.append(torch.empty((world * (t1 - t0), abi.NOUT), dtype=torch.float64, device=dev) if distributed else None)
+    gathered = [torch.empty((world * T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)] if distributed else None
+    eng = GsmEngine(device=local_rank)
+    eng.set_mode(batch.stub_mode, batch.flags)
+    eng.bind_batch(batch)
+    engs = [eng]
     # real (non-default) streams: the kernels and the timing events go on `tstream`, the gathers on `cstream`
     tstream = torch.cuda.Stream(device=dev)
-    cstream = torch.cuda.Stream(device=dev) if distributed else None
+    cstream = torch.cuda.Stream(device=dev, priority=-1) if distributed else None
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    done_ev = [torch.cuda.Event() for _ in range(chunks)]       # chunk evaluated (kernel stream)
-    free_ev = [torch.cuda.Event() for _ in range(chunks)]       # chunk's rows gathered: they may be overwritten
+    done_ev = [torch.cuda.Event() for _ in range(nbuf)]       # step evaluated (kernel stream)
+    free_ev = [torch.cuda.Event() for _ in range(nbuf)]       # its rows gathered: the buffer may be rewritten
     launch_total = lambda: sum(e.launch_count for e in engs)
+    step_no = [0]
 
     def step(k_events=None):
-        for c in range(chunks):
-            if distributed:
-                tstream.wait_event(free_ev[c])
-            if k_events is not None:
-                k_events[c][0].record()
-            engs[c].eval_device(outs[c], rates_c[c], None, stream)
-            if k_events is not None:
-                k_events[c][1].record()
-            if distributed:
-                done_ev[c].record(tstream)
-                with torch.cuda.stream(cstream):
-                    cstream.wait_event(done_ev[c])
-                    dist.all_gather_into_tensor(gathered[c], outs[c])
-                    free_ev[c].record(cstream)
+        i = step_no[0] % nbuf
+        step_no[0] += 1
+        if distributed:
+            tstream.wait_event(free_ev[i])
+        if k_events is not None:
+            k_events[0][0].record()
+        eng.eval_device(out_b[i], out_rates, None, stream)
+        if k_events is not None:
+            k_events[0][1].record()
+        if distributed:
+            done_ev[i].record(tstream)
+            with torch.cuda.stream(cstream):
+                cstream.wait_event(done_ev[i])
+                dist.all_gather_into_tensor(gathered[i], out_b[i])
+                free_ev[i].record(cstream)
+        return out_b[i]
 
+    chunks = 1
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -289,8 +286,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = launch_total()
     e0.record()
+    out = None
     for s in range(args.steps):
-        step(k_ev[s])
+        out = step(k_ev[s])
     if distributed:
         tstream.wait_stream(cstream)      # the timed region ends when the last gather has landed
     e1.record()
@@ -402,8 +400,9 @@ def main():
                        "branches_per_step": world * branches, "outputs": "logP+rates" if args.want_rates else "logP",
                        "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
                        if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
-                       "gather": ("nccl all_gather of the [T,8] result rows each step, in %d chunks on a second stream, "
-                                  "overlapping the next chunk's kernels" % chunks) if distributed else "none (1 GPU)",
+                       "gather": ("nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the "
+                                  "next step's kernels (two result buffers); the timed region ends after the last gather")
+                       if distributed else "none (1 GPU)",
                        "launches_per_step": launches // max(1, args.steps),
                        "generate_s": round(t_gen, 1), "parity_sample": parity},
             "clocks": sampler.summary(),

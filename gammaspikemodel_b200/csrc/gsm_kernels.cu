@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             tma_bulk_g2s(sh_exptab, g_lean_blob.exptab, GSM_T6E_WORDS * 8u, &sh.mbar);
             tma_bulk_g2s(sh_hs, b.height + row + L4, bytes_h, &sh.mbar);
             tma_bulk_g2s(sh_logtab, g_lean_blob.logtab, GSM_T6_WORDS * 8u, &sh.mbar);
-        } else if (warp <= NST) {
+        } else if (warp <= NST && warp != NWARP - 1) {
             if (warp - 1 < nvc) ring_issue<2 * HB>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
         }
     } else if (tid == 1) {
@@ -898,8 +898,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             if (k < nvc) mbar_wait_a(rg.a_full + k * 8u, 0u);
         asm volatile("cp.async.wait_all;" ::: "memory");
     };
+    // The lane that computes the per-tree scalars does that first: when its warp also has a chunk to request (four-warp
+    // CTAs), the request follows the barrier (that chunk is the last of the first three to be consumed).
     if (warp == NWARP - 1 && lane == 0) gsm_setup_scalars(K, prm_v, use_v, b.flags, b.stub_mode);
     __syncthreads();
+    if (warp == NWARP - 1 && lane == 0 && warp <= NST && warp - 1 < nvc)
+        ring_issue<2 * HB>(rg, warp - 1, static_cast<uint32_t>(warp - 1));
     GSM_PHASE_MARK(0);   // barrier init, TMA requests, per-tree scalars
     mbar_wait(&sh.mbar, 0);
     GSM_PHASE_MARK(1);   // internal heights + tables landed
@@ -1037,16 +1041,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
             const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
             sts_v2f64(a_a0 + j * 16, a0, a1);
         };
+        auto pair_aux2 = [&](int j, int j2) {   // two pairs = four nodes, staged (gsm_lean_aux4)
+            const double2 ha = lds_v2f64(a_h0 + j * 16);
+            double2 hb = lds_v2f64(a_h0 + j2 * 16);
+            if (L4 + 2 * j2 + 1 >= n) hb.y = hb.x;   // padding slot of the last pair
+            const double h4[4] = {ha.x, ha.y, hb.x, hb.y};
+            double a4[4];
+            gsm_lean_aux4(c, SA, h4, a4);
+            sts_v2f64(a_a0 + j * 16, a4[0], a4[1]);
+            sts_v2f64(a_a0 + j2 * 16, a4[2], a4[3]);
+        };
         if (GSM_PA_DYN || BLOCK < 256) {
-            // Warps take batches of 32 pairs from a shared counter: the two Gamma warps join when their table entries are done.
+            // Warps take batches of 64 pairs (two per lane) from a shared counter: the two Gamma warps join when their table
+            // entries are done.
 #pragma unroll 1
             for (;;) {
                 int j = 0;
-                if (lane == 0) j = atomicAdd(&sh.pa_next, 32);
+                if (lane == 0) j = atomicAdd(&sh.pa_next, 64);
                 j = __shfl_sync(0xffffffffu, j, 0);
                 if (j >= npa) break;
                 j += lane;
-                if (j < npa) pair_aux(j);
+                if (j + 32 < npa) pair_aux2(j, j + 32);
+                else if (j < npa) pair_aux(j);
             }
         } else {
             // the warps that did not compute Gamma table entries take all of pass A, two pairs (four nodes) at a time
@@ -1054,18 +1070,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
 #pragma unroll 1
             for (int j = tid - 64; j < npa && j >= 0; j += 2 * NA) {
                 const int j2 = j + NA;
-                if (j2 < npa) {
-                    const double2 ha = lds_v2f64(a_h0 + j * 16);
-                    double2 hb = lds_v2f64(a_h0 + j2 * 16);
-                    if (L4 + 2 * j2 + 1 >= n) hb.y = hb.x;   // padding slot of the last pair
-                    const double h4[4] = {ha.x, ha.y, hb.x, hb.y};
-                    double a4[4];
-                    gsm_lean_aux4(c, SA, h4, a4);
-                    sts_v2f64(a_a0 + j * 16, a4[0], a4[1]);
-                    sts_v2f64(a_a0 + j2 * 16, a4[2], a4[3]);
-                } else {
-                    pair_aux(j);
-                }
+                if (j2 < npa) pair_aux2(j, j2);
+                else pair_aux(j);
             }
         }
     }
@@ -1377,7 +1383,7 @@ static size_t g_smem_per_sm = 0;
 
 // launch configurations of the lean kernel that are compiled in
 #ifdef GSM_DEV_BUILD
-#define GSM_LEAN_CFGS GSM_CFG(256, 2) GSM_CFG(128, 3)
+#define GSM_LEAN_CFGS GSM_CFG(128, 3)
 #else
 #define GSM_LEAN_CFGS GSM_CFG(128, 4) GSM_CFG(128, 3) GSM_CFG(256, 2)
 #endif
