@@ -219,6 +219,9 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The gather (64 B per tree) runs under the next step's kernels, which fill every SM: keep NCCL's footprint small
+        # (a few CTAs move 64 MB in well under one step) instead of letting it take tens of SMs for a short burst.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         dist.init_process_group("nccl", device_id=dev)
 
     kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]

@@ -155,11 +155,11 @@ GSM_HD double gsm_log6_r(const GsmT6& t, double x, int32_t& K) {
 }
 // log1p(r), |r| <= 0.01248: degree 5, absolute error <= 8e-14 (the per-branch sums)
 GSM_HD double gsm_log6_y3(double r) {
+    // Estrin's scheme: the same five operations as Horner's, a dependency chain of three instead of four
     const double r2 = r * r;
-    double q = fma(GSM_LK(GSM_LK_Q3 + 3), r, GSM_LK(GSM_LK_Q3 + 2));
-    q = fma(q, r, GSM_LK(GSM_LK_Q3 + 1));
-    q = fma(q, r, GSM_LK(GSM_LK_Q3 + 0));
-    return fma(q, r2, r);
+    const double a = fma(GSM_LK(GSM_LK_Q3 + 1), r, GSM_LK(GSM_LK_Q3 + 0));
+    const double b = fma(GSM_LK(GSM_LK_Q3 + 3), r, GSM_LK(GSM_LK_Q3 + 2));
+    return fma(fma(b, r2, a), r2, r);
 }
 // ... degree 6, absolute error <= 4e-16 (aux, which feeds differences)
 GSM_HD double gsm_log6_y4(double r) {
