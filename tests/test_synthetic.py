@@ -37,3 +37,26 @@ def test_generation_is_deterministic_and_chunking_is_consistent():
     assert all(np.array_equal(a.dense(k), b.dense(k)) for k in ("height", "parent", "rate", "spike", "nstubs"))
     c = synthetic.make_batch_chunked("C4", 10, 20, chunk=4)
     assert c.n_trees == 10 and c.height.shape == (10, c.stride)
+
+
+def test_proposal_generator_is_well_formed_and_changes_the_state():
+    """config 5 generator (host side): CSR shape, distinct nodes per proposal, and the oracle sees the edits"""
+    import numpy as np
+    from helpers import apply_proposals, host_arrays, run_oracle
+    b = synthetic.make_batch("C3", 6, 40)
+    a = host_arrays(b)
+    pr = synthetic.make_proposals(a, 200)
+    ptr = pr["dirty_ptr"]
+    assert ptr[0] == 0 and np.all(np.diff(ptr) >= 0) and ptr[-1] == len(pr["dirty_nodes"])
+    assert pr["tree_of_prop"].min() >= 0 and pr["tree_of_prop"].max() < 6
+    for p in range(200):
+        nodes = pr["dirty_nodes"][ptr[p]:ptr[p + 1]]
+        assert len(np.unique(nodes)) == len(nodes) and (len(nodes) == 0 or (nodes.min() >= 0 and nodes.max() < b.n_nodes))
+    sizes = np.diff(ptr)
+    assert (sizes <= 4).mean() > 0.7 and (sizes == b.n_nodes).any()          # mostly local moves, some touch every branch
+    base = run_oracle(a, b.flags, b.stub_mode, rates=False)["out"][pr["tree_of_prop"]]
+    prop = run_oracle(apply_proposals(a, pr), b.flags, b.stub_mode, rates=False)["out"]
+    changed = ~np.all((base == prop) | (np.isnan(base) & np.isnan(prop)), axis=1)
+    assert changed.mean() > 0.9
+    again = synthetic.make_proposals(a, 200)
+    assert all(np.array_equal(pr[k], again[k]) for k in pr)                   # deterministic (seed C5)
