@@ -237,8 +237,10 @@ def main():
 
     # One step = one evaluation of the whole shard (gsm_lean_kernel + gsm_post_kernel).  At N > 1 the NCCL all-gather of
     # a step's result rows (the only collective on the path, 64 B per tree) is issued on a second stream and overlaps the
-    # next step's kernels: two result buffers alternate, and a buffer is rewritten only after its gather has finished.
-    nbuf = 2 if distributed else 1
+    # next step's kernels: three result buffers rotate, and a buffer is rewritten only after its gather has finished.
+    # (NCCL's CTAs find room on the SMs mostly between two kernels; with three buffers the kernel of step s+2 does not
+    # wait for the gather of step s.)
+    nbuf = 3 if distributed else 1
     out_b = [torch.empty((T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)]
     out_rates = torch.empty((T, S), dtype=torch.float64, device=dev) if args.want_rates else None
     gathered = [torch.empty((world * T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)] if distributed else None
@@ -404,7 +406,7 @@ def main():
                        "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
                        if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
                        "gather": ("nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the "
-                                  "next step's kernels (two result buffers); the timed region ends after the last gather")
+                                  "next steps' kernels (three result buffers); the timed region ends after the last gather")
                        if distributed else "none (1 GPU)",
                        "launches_per_step": launches // max(1, args.steps),
                        "generate_s": round(t_gen, 1), "parity_sample": parity},
