@@ -455,6 +455,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
 #ifndef GSM_RING_STAGES
 #define GSM_RING_STAGES 3
 #endif
+#ifndef GSM_SCAN_U
+#define GSM_SCAN_U 8   // leaves per thread and round of the sampled-ancestor scan
+#endif
+#ifndef GSM_PA_BATCH
+#define GSM_PA_BATCH 64   // pairs per dynamic pass A batch (two per lane and 64)
+#endif
 #ifndef GSM_PA_DYN
 #define GSM_PA_DYN 0   // 1: pass A by dynamic batches also for BLOCK >= 256
 #endif
@@ -957,11 +963,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         __syncthreads();
         const double* hrow = b.height + row;
         const int32_t* prow = b.parent + row;
-        for (int i = tid; i < L; i += BLOCK) {
-            const int32_t p = __ldg(prow + i);
-            if (static_cast<uint32_t>(p - L) < x.nL && __ldg(hrow + i) == lds_f64(x.a_hs + p * 8)) {
-                reinterpret_cast<uint8_t*>(sh_fk)[p - L4] = 1;
-                anyda = true;
+        // GSM_SCAN_U leaves per thread and round: all their global loads are issued before the first one is used
+#pragma unroll 1
+        for (int i0 = tid; i0 < L; i0 += GSM_SCAN_U * BLOCK) {
+            int32_t p[GSM_SCAN_U];
+            double h[GSM_SCAN_U];
+#pragma unroll
+            for (int u = 0; u < GSM_SCAN_U; u++) {
+                const int i = i0 + u * BLOCK;
+                p[u] = i < L ? __ldg(prow + i) : -1;
+                h[u] = i < L ? __ldg(hrow + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < GSM_SCAN_U; u++) {
+                if (static_cast<uint32_t>(p[u] - L) < x.nL && h[u] == lds_f64(x.a_hs + p[u] * 8)) {
+                    reinterpret_cast<uint8_t*>(sh_fk)[p[u] - L4] = 1;
+                    anyda = true;
+                }
             }
         }
     }
@@ -1057,12 +1075,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
 #pragma unroll 1
             for (;;) {
                 int j = 0;
-                if (lane == 0) j = atomicAdd(&sh.pa_next, 64);
+                if (lane == 0) j = atomicAdd(&sh.pa_next, GSM_PA_BATCH);
                 j = __shfl_sync(0xffffffffu, j, 0);
                 if (j >= npa) break;
                 j += lane;
-                if (j + 32 < npa) pair_aux2(j, j + 32);
-                else if (j < npa) pair_aux(j);
+#pragma unroll
+                for (int u = 0; u < GSM_PA_BATCH / 64; u++, j += 64) {
+                    if (j + 32 < npa) pair_aux2(j, j + 32);
+                    else if (j < npa) pair_aux(j);
+                }
             }
         } else {
             // the warps that did not compute Gamma table entries take all of pass A, two pairs (four nodes) at a time
