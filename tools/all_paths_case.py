@@ -20,4 +20,4 @@ for kind, T, n in (("C4", 12, 600), ("C3", 12, 300), ("C2", 24, 40), ("C4", 4, 2
     run_capi(a, b.flags, b.stub_mode, engine=eng, rates=False)
     eng.eval_dirty(**pr)
     eng.close()
-print("sanitize_case ok")
+print("all_paths_case ok")
