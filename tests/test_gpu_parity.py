@@ -204,3 +204,35 @@ def test_every_tree_of_a_large_batch_matches_oracle(kind, T, n):
                              use_spike=a["use_spike"])["out"]
     assert np.array_equal(streamed, dev, equal_nan=True)
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["C4", "C3"])
+def test_ragged_batch_mixed_tree_sizes_matches_oracle(kind):
+    """One launch over trees of very different sizes (node_count per tree): the launch configuration is picked for the
+    largest tree, the chunk / tail logic of the lean kernel sees 3 ... 1,999 nodes."""
+    sizes = [2, 3, 26, 129, 300, 513, 777, 1000]
+    per = 96
+    Nmax = 2 * max(sizes) - 1
+    parts, counts = [], []
+    for k, taxa in enumerate(sizes):
+        b = synthetic.make_batch(kind, per, taxa, seed=synthetic.SEEDS[kind] + k)
+        a = host_arrays(b)
+        n = b.n_nodes
+        pad = {}
+        for key, fill in (("height", 0.0), ("parent", -1), ("rate", 1.0), ("spike", 0.0), ("nstubs", 0)):
+            x = np.full((per, Nmax), fill, dtype=a[key].dtype)
+            x[:, :n] = a[key]
+            pad[key] = x
+        pad["params"], pad["use_spike"] = a["params"], a["use_spike"]
+        parts.append(pad)
+        counts.append(np.full(per, n, np.int32))
+    a = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    nc = np.concatenate(counts)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(nc))                      # neighbours in the grid have different sizes
+    a = {k: np.ascontiguousarray(v[perm]) for k, v in a.items()}
+    nc = np.ascontiguousarray(nc[perm])
+    F_ = synthetic.DEFAULT_FLAGS
+    ref = run_oracle(a, F_, abi.STUBS_COUNTS, node_count=nc)
+    got = run_capi(a, F_, abi.STUBS_COUNTS, node_count=nc)
+    assert_results_match(got, ref, node_count=nc, what="ragged " + kind)
