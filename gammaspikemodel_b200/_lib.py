@@ -21,9 +21,12 @@ SIGNATURES = {
     "gsm_destroy": (C.c_int, [_vp]),
     "gsm_last_error": (C.c_char_p, [_vp]),
     "gsm_set_mode": (C.c_int, [_vp, _i32, _u32]),
+    "gsm_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "gsm_upload_trees": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "gsm_upload_branch_params": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_upload_tree_params": (C.c_int, [_vp, _vp, _vp]),
+    "gsm_upload_stubs": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "gsm_bind_device_stubs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_eval": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_eval_host": (C.c_int, [_vp, _i64, _i32] + [_vp] * 11),
     "gsm_eval_dirty": (C.c_int, [_vp, _i64] + [_vp] * 10),

@@ -46,6 +46,17 @@ struct gsm_handle {
     double *d_out_rates = nullptr, *d_out_wsp = nullptr;
     int32_t *d_parent = nullptr, *d_nstubs = nullptr, *d_node_count = nullptr;
     uint8_t* d_use = nullptr;
+    // EXACT mode stub lists (gsm_upload_stubs / gsm_bind_device_stubs) and the per-branch counts derived from them
+    int64_t* d_stub_ptr = nullptr;
+    int32_t* d_stub_branch = nullptr;
+    double* d_stub_time = nullptr;
+    int64_t stub_ptr_cap = 0, stub_cap = 0;
+    const int64_t* x_stub_ptr = nullptr;      // device-bound lists (caller-owned)
+    const int32_t* x_stub_branch = nullptr;
+    const double* x_stub_time = nullptr;
+    int32_t* d_stub_counts = nullptr;         // [n_trees][stride] for device-bound batches
+    int64_t stub_counts_cap = 0;
+    bool have_stubs = false, stub_counts_valid = false;
     double* d_cdf = nullptr;  // scratch for gsm_stub_cdf
     int32_t cdf_cap = 0;
     bool have_trees = false, have_rate = false, have_spike = false, have_nstubs = false, have_params = false;
@@ -60,6 +71,8 @@ struct gsm_handle {
     int64_t prop_cap = 0;
     GsmScratch scratch;          // lean-path scratch of the handle's own stream
     int64_t scratch_trees = 0;
+    GsmLaunchCtx ctx;            // device facts, probe results, gsm_set_option overrides (nothing process-global)
+    int64_t host_chunk_mb = 256; // streaming chunk of gsm_eval_host / gsm_eval_dirty (gsm_set_option "host_chunk_mb")
     std::string err;
     int64_t launches = 0;
 };
@@ -211,6 +224,7 @@ int gsm_create(gsm_handle** out, int32_t device_id, int64_t max_trees, int32_t m
     if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = gsm_init_tables()) != cudaSuccess) return bail(e, "table upload");
+    if ((e = gsm_launch_ctx_init(h->ctx, device_id)) != cudaSuccess) return bail(e, "device attributes");
     if (max_trees > 0 && max_nodes > 0) {
         const int64_t cells = max_trees * h->max_stride;
         if ((e = dalloc(&h->d_height, cells)) != cudaSuccess) return bail(e, "alloc height");
@@ -235,6 +249,7 @@ int gsm_destroy(gsm_handle* h) {
     dfree(h->d_height); dfree(h->d_rate); dfree(h->d_spike); dfree(h->d_parent); dfree(h->d_nstubs);
     dfree(h->d_node_count); dfree(h->d_params); dfree(h->d_use); dfree(h->d_out); dfree(h->d_out_rates);
     dfree(h->d_out_wsp); dfree(h->d_cdf); dfree(h->d_prop);
+    dfree(h->d_stub_ptr); dfree(h->d_stub_branch); dfree(h->d_stub_time); dfree(h->d_stub_counts);
     free_scratch(h->scratch, h->scratch_trees);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -252,6 +267,23 @@ int gsm_set_mode(gsm_handle* h, int32_t stub_mode, uint32_t flags) {
         return fail(h, GSM_E_ARG, "gsm_set_mode: conditionOnRoot needs conditionOnSampling or conditionOnRhoSampling");
     h->stub_mode = stub_mode;
     h->flags = flags;
+    return GSM_OK;
+}
+
+int gsm_set_option(gsm_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return GSM_E_ARG;
+    if (!strcmp(name, "host_chunk_mb")) {
+        if (value < 1) return fail(h, GSM_E_ARG, "gsm_set_option: host_chunk_mb must be >= 1");
+        h->host_chunk_mb = value;
+    } else if (!strcmp(name, "force_generic")) {
+        h->ctx.force_generic = value != 0;
+    } else if (!strcmp(name, "block")) {
+        h->ctx.block = static_cast<int>(value);
+    } else if (!strcmp(name, "minb")) {
+        h->ctx.minb = static_cast<int>(value);
+    } else {
+        return fail(h, GSM_E_ARG, "gsm_set_option: unknown option '%s'", name);
+    }
     return GSM_OK;
 }
 
@@ -273,7 +305,9 @@ int gsm_upload_trees(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const doub
     h->external = false;
     h->have_trees = true;
     h->have_node_count = node_count != nullptr;
-    h->have_rate = h->have_spike = h->have_nstubs = false;  // branch arrays belong to a tree upload
+    // branch arrays and per-tree scalars belong to a tree upload: a new batch must bring its own
+    h->have_rate = h->have_spike = h->have_nstubs = h->have_params = h->have_use = false;
+    h->have_stubs = h->stub_counts_valid = false;
     h->cur = GsmBatch{};
     h->cur.n_trees = n_trees;
     h->cur.n_nodes = n_nodes;
@@ -293,6 +327,7 @@ int gsm_upload_branch_params(gsm_handle* h, const double* rate, const double* sp
     h->have_rate |= rate != nullptr;
     h->have_spike |= spike != nullptr;
     h->have_nstubs |= nstubs != nullptr;
+    if (nstubs) h->stub_counts_valid = false;   // EXACT mode: the derived counts live in the same rows
     return GSM_OK;
 }
 
@@ -310,6 +345,57 @@ int gsm_upload_tree_params(gsm_handle* h, const double* params, const uint8_t* u
     h->have_params = true;
     h->have_use = use_spike != nullptr;
     return GSM_OK;
+}
+
+int gsm_upload_stubs(gsm_handle* h, const int64_t* stub_ptr, const int32_t* stub_branch, const double* stub_time) {
+    if (!h) return GSM_E_ARG;
+    if (!h->have_trees || h->external) return fail(h, GSM_E_STATE, "gsm_upload_stubs: call gsm_upload_trees first");
+    if (!stub_ptr) return fail(h, GSM_E_ARG, "gsm_upload_stubs: stub_ptr is NULL");
+    const int64_t T = h->cur.n_trees;
+    if (stub_ptr[0] != 0) return fail(h, GSM_E_ARG, "gsm_upload_stubs: stub_ptr must start at 0");
+    for (int64_t t = 0; t < T; t++)
+        if (stub_ptr[t + 1] < stub_ptr[t]) return fail(h, GSM_E_ARG, "gsm_upload_stubs: stub_ptr decreases at tree %lld", (long long)t);
+    const int64_t S = stub_ptr[T];
+    if (S > 0 && (!stub_branch || !stub_time)) return fail(h, GSM_E_ARG, "gsm_upload_stubs: NULL stub arrays");
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    if (h->stub_ptr_cap < T + 1) {
+        dfree(h->d_stub_ptr);
+        h->stub_ptr_cap = 0;
+        GSM_CUDA(h, dalloc(&h->d_stub_ptr, T + 1));
+        h->stub_ptr_cap = T + 1;
+    }
+    if (h->stub_cap < S) {
+        dfree(h->d_stub_branch); dfree(h->d_stub_time);
+        h->stub_cap = 0;
+        GSM_CUDA(h, dalloc(&h->d_stub_branch, S));
+        GSM_CUDA(h, dalloc(&h->d_stub_time, S));
+        h->stub_cap = S;
+    }
+    GSM_CUDA(h, cudaMemcpyAsync(h->d_stub_ptr, stub_ptr, (T + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (S > 0) {
+        GSM_CUDA(h, cudaMemcpyAsync(h->d_stub_branch, stub_branch, S * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        GSM_CUDA(h, cudaMemcpyAsync(h->d_stub_time, stub_time, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_stubs = true;
+    h->stub_counts_valid = false;
+    h->have_nstubs = true;   // the counts are derived from the list (resident_batch)
+    return GSM_OK;
+}
+
+int gsm_bind_device_stubs(gsm_handle* h, const int64_t* d_stub_ptr, const int32_t* d_stub_branch, const double* d_stub_time) {
+    if (!h) return GSM_E_ARG;
+    if (!h->have_trees || !h->external) return fail(h, GSM_E_STATE, "gsm_bind_device_stubs: call gsm_bind_device first");
+    h->x_stub_ptr = d_stub_ptr;
+    h->x_stub_branch = d_stub_branch;
+    h->x_stub_time = d_stub_time;
+    h->have_stubs = d_stub_ptr != nullptr;
+    h->stub_counts_valid = false;
+    return GSM_OK;
+}
+
+static bool rj_terms_wired(const gsm_handle* h) {   // STP:219 with Stubs.getReversibleJump (STP:573-600, 639-663)
+    return h->stub_mode == GSM_STUBS_EXACT && (h->flags & GSM_F_STUBS_TO_TREE_PRIOR) && !(h->flags & GSM_F_IGNORE_STUB_PRIOR);
 }
 
 static int resident_batch(gsm_handle* h, GsmBatch* b) {
@@ -331,6 +417,41 @@ static int resident_batch(gsm_handle* h, GsmBatch* b) {
     }
     b->flags = h->flags;
     b->stub_mode = h->stub_mode;
+    b->stub_ptr = nullptr; b->stub_branch = nullptr; b->stub_time = nullptr;
+    if (h->stub_mode == GSM_STUBS_EXACT) {
+        if (h->have_stubs) {
+            // the list defines the per-branch counts (Stubs:357-364): derived on the device, once per upload
+            b->stub_ptr = h->external ? h->x_stub_ptr : h->d_stub_ptr;
+            b->stub_branch = h->external ? h->x_stub_branch : h->d_stub_branch;
+            b->stub_time = h->external ? h->x_stub_time : h->d_stub_time;
+            int32_t* counts = h->d_nstubs;
+            if (h->external) {
+                const int64_t cells = b->n_trees * b->stride;
+                if (h->stub_counts_cap < cells) {
+                    dfree(h->d_stub_counts);
+                    h->stub_counts_cap = 0;
+                    GSM_CUDA(h, cudaSetDevice(h->device));
+                    GSM_CUDA(h, dalloc(&h->d_stub_counts, cells));
+                    h->stub_counts_cap = cells;
+                    h->stub_counts_valid = false;
+                }
+                counts = h->d_stub_counts;
+            }
+            if (!counts) return fail(h, GSM_E_STATE, "EXACT mode: no room for the per-branch stub counts (handle created without capacity)");
+            if (!h->stub_counts_valid && b->n_trees > 0) {
+                GSM_CUDA(h, cudaSetDevice(h->device));
+                int nl = gsm_launch_stub_counts(*b, counts, h->stream);
+                if (nl < 0) return fail(h, GSM_E_CUDA, "stub count launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+                h->launches += nl;
+                GSM_CUDA(h, cudaStreamSynchronize(h->stream));   // evaluations may run on another stream
+                h->stub_counts_valid = true;
+            }
+            b->nstubs = counts;
+        } else if (rj_terms_wired(h)) {
+            return fail(h, GSM_E_STATE, "stub_mode is GSM_STUBS_EXACT and the stub prior is evaluated: call gsm_upload_stubs "
+                                        "(or gsm_bind_device_stubs) first");
+        }
+    }
     return check_mode(h, b->rate != nullptr, b->nstubs != nullptr);
 }
 
@@ -347,7 +468,7 @@ int gsm_eval(gsm_handle* h, double* out_tree, double* out_rates, double* out_wsp
     if (out_rates && !h->d_out_rates) GSM_CUDA(h, dalloc(&h->d_out_rates, cells));
     if (out_wspikes && !h->d_out_wsp) GSM_CUDA(h, dalloc(&h->d_out_wsp, cells));
     GSM_CUDA(h, ensure_scratch(h->scratch, h->scratch_trees, b.n_trees));
-    int nl = gsm_launch_eval(b, h->scratch, h->d_out, out_rates ? h->d_out_rates : nullptr, out_wspikes ? h->d_out_wsp : nullptr, h->stream);
+    int nl = gsm_launch_eval(h->ctx, b, h->scratch, h->d_out, out_rates ? h->d_out_rates : nullptr, out_wspikes ? h->d_out_wsp : nullptr, h->stream);
     if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
     h->launches += nl;
     GSM_CUDA(h, cudaMemcpyAsync(out_tree, h->d_out, b.n_trees * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -392,13 +513,15 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
     if (n_nodes > GSM_MAX_NODES) return fail(h, GSM_E_UNSUPPORTED, "gsm_eval_host: n_nodes %d exceeds GSM_MAX_NODES", n_nodes);
     if (n_trees == 0 || n_nodes == 0) return GSM_OK;
     if (!height || !parent || !spike || !params || !out_tree) return fail(h, GSM_E_ARG, "gsm_eval_host: NULL required array");
+    if (rj_terms_wired(h))
+        return fail(h, GSM_E_UNSUPPORTED, "gsm_eval_host: EXACT mode with the stub prior evaluated needs the stub lists; use "
+                                          "gsm_upload_trees / gsm_upload_stubs / gsm_eval");
     int rc = check_mode(h, rate != nullptr, nstubs != nullptr);
     if (rc != GSM_OK) return rc;
     GSM_CUDA(h, cudaSetDevice(h->device));
     const int64_t stride = gsm_device_stride(n_nodes);
     // ~256 MB of inputs per slot: long enough transfers for full PCIe rate, short enough to overlap
-    int64_t chunk_mb = 256;
-    if (const char* env = getenv("GSM_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));   // test hook: force small chunks
+    const int64_t chunk_mb = h->host_chunk_mb;
     int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (stride * 32));
     chunk = std::min(chunk, n_trees);
     rc = ensure_slots(h, chunk, stride, out_rates != nullptr, out_wspikes != nullptr);
@@ -424,7 +547,7 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
         b.rate = rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = nstubs ? s.nstubs : nullptr;
         b.params = s.params; b.use_spike = use_spike ? s.use_spike : nullptr;
         b.flags = h->flags; b.stub_mode = h->stub_mode;
-        int nl = gsm_launch_eval(b, s.scratch, s.out, out_rates ? s.out_rates : nullptr, out_wspikes ? s.out_wsp : nullptr, s.stream);
+        int nl = gsm_launch_eval(h->ctx, b, s.scratch, s.out, out_rates ? s.out_rates : nullptr, out_wspikes ? s.out_wsp : nullptr, s.stream);
         if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_host launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
         h->launches += nl;
         GSM_CUDA(h, cudaMemcpyAsync(out_tree + t0 * GSM_NOUT, s.out, T * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -447,6 +570,9 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
     if (n_props < 0) return fail(h, GSM_E_ARG, "gsm_eval_dirty: negative n_props");
     if (n_props == 0) return GSM_OK;
     if (!tree_of_prop || !dirty_ptr || !out_tree) return fail(h, GSM_E_ARG, "gsm_eval_dirty: NULL required array");
+    if (rj_terms_wired(h))
+        return fail(h, GSM_E_UNSUPPORTED, "gsm_eval_dirty: reversible-jump moves change the stub list itself; upload the "
+                                          "proposed state (gsm_upload_stubs) and call gsm_eval");
     GsmBatch src;
     int rc = resident_batch(h, &src);
     if (rc != GSM_OK) return rc;
@@ -500,8 +626,7 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
     pr.new_params = new_params ? reinterpret_cast<const double*>(base + o_par) : nullptr;
     pr.new_use_spike = new_use_spike ? reinterpret_cast<const uint8_t*>(base + o_use) : nullptr;
     // ---- proposed states, chunk by chunk, through the two staging slots ----
-    int64_t chunk_mb = 256;
-    if (const char* env = getenv("GSM_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));   // test hook: force small chunks
+    const int64_t chunk_mb = h->host_chunk_mb;
     int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (src.stride * 32));
     chunk = std::min(chunk, n_props);
     rc = ensure_slots(h, chunk, src.stride, false, false);
@@ -521,7 +646,7 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
         b.height = s.height; b.parent = s.parent; b.node_count = s.node_count;
         b.rate = src.rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = src.nstubs ? s.nstubs : nullptr;
         b.params = s.params; b.use_spike = s.use_spike;
-        nl = gsm_launch_eval(b, s.scratch, s.out, nullptr, nullptr, s.stream);
+        nl = gsm_launch_eval(h->ctx, b, s.scratch, s.out, nullptr, nullptr, s.stream);
         if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
         h->launches += nl;
         GSM_CUDA(h, cudaMemcpyAsync(out_tree + p0 * GSM_NOUT, s.out, P * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -555,7 +680,8 @@ int gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t
     int32_t n = 0;
     GSM_CUDA(h, cudaMemcpyAsync(&n, d_len, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     GSM_CUDA(h, cudaStreamSynchronize(h->stream));
-    GSM_CUDA(h, cudaMemcpy(cdf, h->d_cdf, sizeof(double) * std::min(n, cap), cudaMemcpyDeviceToHost));
+    GSM_CUDA(h, cudaMemcpyAsync(cdf, h->d_cdf, sizeof(double) * std::min(n, cap), cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
     *len = n;
     return GSM_OK;
 }
@@ -583,10 +709,14 @@ int gsm_bind_device(gsm_handle* h, int64_t n_trees, int32_t n_nodes, int64_t str
     if (n_nodes > GSM_MAX_NODES) return fail(h, GSM_E_UNSUPPORTED, "gsm_bind_device: n_nodes %d exceeds GSM_MAX_NODES", n_nodes);
     if (stride < n_nodes || (stride % 32) != 0) return fail(h, GSM_E_ARG, "gsm_bind_device: stride must be >= n_nodes and a multiple of 32");
     if (n_trees > 0 && (!d_height || !d_parent || !d_spike || !d_params)) return fail(h, GSM_E_ARG, "gsm_bind_device: NULL required array");
-    if ((reinterpret_cast<uintptr_t>(d_height) | reinterpret_cast<uintptr_t>(d_parent)) & 15u)
-        return fail(h, GSM_E_ARG, "gsm_bind_device: height/parent must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(d_height) | reinterpret_cast<uintptr_t>(d_parent) | reinterpret_cast<uintptr_t>(d_rate) |
+         reinterpret_cast<uintptr_t>(d_spike) | reinterpret_cast<uintptr_t>(d_nstubs)) & 15u)
+        return fail(h, GSM_E_ARG, "gsm_bind_device: height / parent / rate / spike / nstubs must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_params) & 7u) return fail(h, GSM_E_ARG, "gsm_bind_device: params must be 8-byte aligned");
     h->external = true;
     h->have_trees = true;
+    h->have_stubs = h->stub_counts_valid = false;
+    h->x_stub_ptr = nullptr; h->x_stub_branch = nullptr; h->x_stub_time = nullptr;
     GsmBatch b{};
     b.n_trees = n_trees; b.n_nodes = n_nodes; b.stride = stride;
     b.height = d_height; b.parent = d_parent; b.node_count = d_node_count;
@@ -605,7 +735,7 @@ int gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, doub
     GSM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
     GSM_CUDA(h, ensure_scratch(h->scratch, h->scratch_trees, b.n_trees));
-    int nl = gsm_launch_eval(b, h->scratch, d_out_tree, d_out_rates, d_out_wspikes, st);
+    int nl = gsm_launch_eval(h->ctx, b, h->scratch, d_out_tree, d_out_rates, d_out_wspikes, st);
     if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_device launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
     h->launches += nl;
     return GSM_OK;

@@ -194,8 +194,9 @@ struct GsmGenericShared {
     int32_t redi[5][16];
 };
 
+// Returns true when the tree went through the bulk-copy phase of sh.mbar (the caller flips its parity bit then).
 template <int BLOCK, bool WANT_RATES>
-static __device__ void gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t parity, unsigned char* smem_raw,
+static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t parity, unsigned char* smem_raw,
                                         GsmGenericShared& sh, double* __restrict__ out_tree, double* __restrict__ out_rates,
                                         double* __restrict__ out_wspikes) {
     constexpr int NWARP = BLOCK / 32;
@@ -215,7 +216,7 @@ static __device__ void gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
     double* orow = out_tree + t * GSM_NOUT;
     if (n <= 0) {
         if (tid < GSM_NOUT) orow[tid] = NAN;
-        return;
+        return false;
     }
     const int64_t row = t * S;
 
@@ -326,6 +327,21 @@ static __device__ void gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
         i = inext;
     }
 
+    // ---- phase 3b: EXACT mode, the listed stubs of this tree (STP:573-592 / 639-655) ----
+    if (b.stub_ptr != nullptr && K.stub_term && K.stub_mode == GSM_STUBS_EXACT) {
+        const int64_t s0 = b.stub_ptr[t], s1 = b.stub_ptr[t + 1];
+        for (int64_t j = s0 + tid; j < s1; j += BLOCK) {
+            const int32_t br = __ldg(b.stub_branch + j);
+            if (static_cast<uint32_t>(br) >= static_cast<uint32_t>(n)) continue;   // matches no branchNr of STP:243-253
+            const int32_t p = sh_par[br];
+            const double h = sh_h[br];
+            const bool root = p < 0;
+            const double hp = root ? h : sh_h[p];
+            const bool da = !root && !sh_nonleaf[br] && hp == h;
+            gsm_stub_term(K, A, root, da, h, hp, __ldg(b.stub_time + j));
+        }
+    }
+
     // ---- phase 4: reductions (fixed order) + epilogue ----
     double v0 = warp_sum(A.tree), v1 = warp_sum(A.stub), v2 = warp_sum(A.spike), v3 = warp_sum(A.rate),
            v4 = warp_sum(A.burst), v5 = warp_sum(A.dist);
@@ -360,6 +376,7 @@ static __device__ void gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
 #pragma unroll
         for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
     }
+    return true;
 }
 
 // One CTA per tree (wirings outside the lean family).
@@ -428,8 +445,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_post_kernel(const GsmBatch b,
     __syncthreads();
     uint32_t parity = 0;
     for (int32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
-        gsm_generic_tree<BLOCK, WANT_RATES>(b, redo_list[k], parity, smem_raw, sh, out_tree, out_rates, out_wspikes);
-        parity ^= 1u;
+        if (gsm_generic_tree<BLOCK, WANT_RATES>(b, redo_list[k], parity, smem_raw, sh, out_tree, out_rates, out_wspikes)) parity ^= 1u;
         __syncthreads();
     }
 }
@@ -817,7 +833,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     uint32_t dyn_bytes;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
     if (lay.total > dyn_bytes) n = 0;   // the launch did not provide this layout (cannot happen with launch_lean): generic path
-    if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) {   // not a binary BEAST tree the lean path covers
+    if (!((n & 1) && n >= 3 && n <= GSM_LEAN_MAX_NODES)) {   // not a binary BEAST tree the lean path covers (incl. n <= 0)
         if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
         return;
     }
@@ -936,7 +952,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     x.nL = static_cast<uint32_t>(n - L);
 
     // ---- phase 1: Gamma tables (64 lanes), fake flags ----
-    const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);   // sampled ancestors are possible
+    // Sampled ancestors are expected where the tree prior generates them (psi > 0, origin / root conditioning): those trees
+    // are scanned.  Elsewhere a zero-length leaf is caught by the length check of the CLEAN bodies or, in a GENERAL body
+    // (root not last, tail nodes), by c.sa_unscanned, and the tree goes to the generic path.
+    const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);
+    c.sa_unscanned = !detect;
     if (tid < GSM_LEAN_MTAB_N - 1) {
         // mtab[m] = {shape m - 1, log shape - logGamma(shape m)}, ntab[m - 1] = {log shape - logGamma(shape m), -log((m - 1)!)}
         // (BSP:97-99 with the Lanczos logGamma of commons-math; STP:567)
@@ -1296,25 +1316,52 @@ static size_t lean_smem_bytes(int32_t n_nodes, int a_dyn, int pairs_per_chunk, i
     return gsm_lean_layout(static_cast<uint32_t>(a_dyn), gsm_lean_si(n_nodes), static_cast<uint32_t>(stages) * pairs_per_chunk * 64u).total;
 }
 
+// Kernel attributes are set once per handle and kernel, to values that do not depend on the batch (the device's opt-in
+// maximum): concurrent handles that race here write the same values.
 template <typename KERN>
-static cudaError_t prep(KERN kern, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+static cudaError_t prep(GsmLaunchCtx& ctx, KERN kern, size_t smem) {
+    if (smem > ctx.smem_optin) return cudaErrorInvalidConfiguration;
+    const void* key = reinterpret_cast<const void*>(kern);
+    for (int k = 0; k < ctx.n_prepared; k++)
+        if (ctx.prepared[k] == key) return cudaSuccess;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (smem + fa.sharedSizeBytes > ctx.smem_optin) return cudaErrorInvalidConfiguration;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx.smem_optin - fa.sharedSizeBytes));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (ctx.n_prepared < GSM_CTX_MAX_KERNELS) ctx.prepared[ctx.n_prepared++] = key;
+    return cudaSuccess;
+}
+
+cudaError_t gsm_launch_ctx_init(GsmLaunchCtx& ctx, int device) {
+    ctx = GsmLaunchCtx{};
+    ctx.device = device;
+    int v = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    ctx.sm_count = v > 0 ? v : 148;
+    if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device)) != cudaSuccess) return e;
+    ctx.smem_per_sm = v > 0 ? static_cast<size_t>(v) : 233472u;
+    if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return e;
+    ctx.smem_optin = v > 0 ? static_cast<size_t>(v) : 232448u;
+    return cudaSuccess;
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_generic(const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
+static cudaError_t launch_generic(GsmLaunchCtx& ctx, const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
     const size_t smem = generic_smem_bytes(b.stride);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     cudaError_t e;
     if (r || w) {
         auto kern = gsm_eval_kernel<BLOCK, MINB, true>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     } else {
         auto kern = gsm_eval_kernel<BLOCK, MINB, false>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
     }
     return cudaGetLastError();
@@ -1334,9 +1381,12 @@ static cudaError_t lean_probe(KERN kern, int block, const GsmBatch& b, const Gsm
 }
 
 // dynamic + static + driver-reserved shared memory one CTA of the lean kernel <BLOCK, MINB> takes for this batch
+// index of a compiled-in lean configuration in GsmLaunchCtx::a_dyn
+constexpr int gsm_lean_cfg_index(int block, int minb) { return block == 128 ? (minb == 4 ? 0 : (minb == 3 ? 1 : 3)) : 2; }
 template <int BLOCK, int MINB>
-static cudaError_t lean_cta_bytes(const GsmBatch& b, const GsmScratch& sc, bool rates, cudaStream_t st, size_t* dyn, size_t* all) {
-    static int a_dyn[2] = {-1, -1};
+static cudaError_t lean_cta_bytes(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, bool rates, cudaStream_t st, size_t* dyn,
+                                  size_t* all) {
+    int* a_dyn = ctx.a_dyn + 2 * gsm_lean_cfg_index(BLOCK, MINB);
     constexpr int HB = BLOCK * gsm_lean_pairs(BLOCK, MINB), NST = gsm_lean_stages(BLOCK, MINB);
     const int k = rates ? 1 : 0;
     if (a_dyn[k] < 0) {
@@ -1352,7 +1402,7 @@ static cudaError_t lean_cta_bytes(const GsmBatch& b, const GsmScratch& sc, bool 
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
+static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
     int32_t* cnt = sc.redo + (sc.epoch & 1);
@@ -1360,22 +1410,23 @@ static cudaError_t launch_lean(const GsmBatch& b, const GsmScratch& sc, double* 
     int32_t* list = sc.redo + 4;
     cudaError_t e;
     size_t smem = 0, all = 0;
-    if ((e = lean_cta_bytes<BLOCK, MINB>(b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
+    if ((e = lean_cta_bytes<BLOCK, MINB>(ctx, b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
     if (r || w) {
         auto kern = gsm_lean_kernel<BLOCK, MINB, true>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     } else {
         auto kern = gsm_lean_kernel<BLOCK, MINB, false>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
     }
     return cudaGetLastError();
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* o, double* r, double* w, int sm_count,
+static cudaError_t launch_post(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* o, double* r, double* w,
                                cudaStream_t st) {
+    const int sm_count = ctx.sm_count;
     const size_t smem = generic_smem_bytes(b.stride);
     int64_t g = (b.n_trees + BLOCK - 1) / BLOCK;
     const int64_t cap = static_cast<int64_t>(sm_count) * MINB;
@@ -1389,18 +1440,15 @@ static cudaError_t launch_post(const GsmBatch& b, const GsmScratch& sc, double* 
     cudaError_t e;
     if (r || w) {
         auto kern = gsm_post_kernel<BLOCK, MINB, true>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, list, o, r, w);
     } else {
         auto kern = gsm_post_kernel<BLOCK, MINB, false>;
-        if ((e = prep(kern, smem)) != cudaSuccess) return e;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
         kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, list, o, r, w);
     }
     return cudaGetLastError();
 }
-
-static int g_sm_count = 0;
-static size_t g_smem_per_sm = 0;
 
 // launch configurations of the lean kernel that are compiled in
 #ifdef GSM_DEV_BUILD
@@ -1411,24 +1459,18 @@ static size_t g_smem_per_sm = 0;
 
 // Launch configuration: one CTA per tree.  The shared-memory footprint per node (18 B lean, 22 B generic) bounds
 // the number of resident trees per SM; BLOCK and the register budget (MINB) are picked from the measured sweeps in
-// profiles/.  GSM_BLOCK / GSM_MINB / GSM_GENERIC override the choice for tuning runs.
-int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
-                    cudaStream_t stream) {
+// profiles/.  gsm_set_option("block" / "minb" / "force_generic") overrides the choice for tuning runs.
+int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double* d_out_tree, double* d_out_rates,
+                    double* d_out_wspikes, cudaStream_t stream) {
     if (b.n_trees <= 0) return 0;
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        g_sm_count = n > 0 ? n : 148;
-        int sm_bytes = 0;
-        cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        g_smem_per_sm = sm_bytes > 0 ? static_cast<size_t>(sm_bytes) : 233472u;
-    }
+    if (ctx.sm_count <= 0) return -static_cast<int>(cudaErrorInvalidValue);
+    // the lean kernel moves rows with 16-byte bulk copies and writes rates / weighted spikes as double2
     const bool aligned = ((reinterpret_cast<uintptr_t>(b.rate) | reinterpret_cast<uintptr_t>(b.spike) |
                            reinterpret_cast<uintptr_t>(b.nstubs) | reinterpret_cast<uintptr_t>(b.height) |
-                           reinterpret_cast<uintptr_t>(b.parent)) & 15u) == 0 && (b.stride % 32) == 0;
+                           reinterpret_cast<uintptr_t>(b.parent) | reinterpret_cast<uintptr_t>(d_out_rates) |
+                           reinterpret_cast<uintptr_t>(d_out_wspikes)) & 15u) == 0 && (b.stride % 32) == 0;
     const bool lean = gsm_lean_wiring_ok(b.flags, b.stub_mode) && b.rate != nullptr && sc.rows != nullptr && sc.redo != nullptr &&
-                      aligned && (b.stub_mode == GSM_STUBS_NOSTUB || b.nstubs != nullptr) && !getenv("GSM_GENERIC");
+                      aligned && (b.stub_mode == GSM_STUBS_NOSTUB || b.nstubs != nullptr) && !ctx.force_generic;
     cudaError_t e = cudaErrorInvalidConfiguration;
     int launches = 0;
     if (lean) {
@@ -1439,34 +1481,34 @@ int gsm_launch_eval(const GsmBatch& b, GsmScratch& sc, double* d_out_tree, doubl
         int block = 128, minb = 4;
         if (b.n_nodes > 512) {
             size_t dyn = 0, all = 0;
-            cudaError_t pe = lean_cta_bytes<128, 3>(b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
+            cudaError_t pe = lean_cta_bytes<128, 3>(ctx, b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
             if (pe != cudaSuccess) return -static_cast<int>(pe);
-            if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) <= g_smem_per_sm) {
+            if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) <= ctx.smem_per_sm) {
                 minb = 3;
             } else {
                 block = 256;
                 minb = 2;
             }
         }
-        if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
-        if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
+        if (ctx.block > 0) block = ctx.block;
+        if (ctx.minb > 0) minb = ctx.minb;
 #define GSM_CFG(B, M) \
-    if (block == B && minb == M) e = launch_lean<B, M>(b, sc, d_out_rates, d_out_wspikes, stream);
+    if (block == B && minb == M) e = launch_lean<B, M>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         GSM_LEAN_CFGS
 #undef GSM_CFG
         if (e != cudaSuccess) return -static_cast<int>(e);
-        if (b.n_nodes <= 2048) e = launch_post<256, 3>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);
-        else e = launch_post<384, 2>(b, sc, d_out_tree, d_out_rates, d_out_wspikes, g_sm_count, stream);
+        if (b.n_nodes <= 2048) e = launch_post<256, 3>(ctx, b, sc, d_out_tree, d_out_rates, d_out_wspikes, stream);
+        else e = launch_post<384, 2>(ctx, b, sc, d_out_tree, d_out_rates, d_out_wspikes, stream);
         if (e != cudaSuccess) return -static_cast<int>(e);
         sc.epoch++;
         launches = 2;
     } else {
         int block = b.n_nodes <= 512 ? 128 : (b.n_nodes <= 2048 ? 256 : 384);
         int minb = b.n_nodes <= 512 ? 6 : (b.n_nodes <= 2048 ? 3 : 2);
-        if (const char* env = getenv("GSM_BLOCK")) block = atoi(env);
-        if (const char* env = getenv("GSM_MINB")) minb = atoi(env);
+        if (ctx.block > 0) block = ctx.block;
+        if (ctx.minb > 0) minb = ctx.minb;
 #define GSM_CFG(B, M) \
-    if (block == B && minb == M) e = launch_generic<B, M>(b, d_out_tree, d_out_rates, d_out_wspikes, stream);
+    if (block == B && minb == M) e = launch_generic<B, M>(ctx, b, d_out_tree, d_out_rates, d_out_wspikes, stream);
         GSM_CFG(128, 8) GSM_CFG(128, 6) GSM_CFG(128, 4)
         GSM_CFG(256, 4) GSM_CFG(256, 3) GSM_CFG(256, 2)
         GSM_CFG(384, 2) GSM_CFG(512, 2) GSM_CFG(512, 1)
@@ -1531,6 +1573,29 @@ int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, in
                      cudaStream_t stream) {
     if (count <= 0) return 0;
     gsm_patch_kernel<<<static_cast<unsigned>(count), 256, 0, stream>>>(src, pr, p0, dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}
+
+// EXACT mode: per-branch stub counts of every tree from its stub list (Stubs.getNStubsOnBranch, Stubs:357-364)
+__global__ void __launch_bounds__(256) gsm_stub_counts_kernel(const GsmBatch b, int32_t* __restrict__ counts) {
+    const int64_t t = blockIdx.x;
+    int32_t* row = counts + t * b.stride;
+    for (int64_t i = threadIdx.x; i < b.stride; i += blockDim.x) row[i] = 0;
+    __syncthreads();
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    const int64_t s0 = b.stub_ptr[t], s1 = b.stub_ptr[t + 1];
+    for (int64_t j = s0 + threadIdx.x; j < s1; j += blockDim.x) {
+        const int32_t br = b.stub_branch[j];
+        if (static_cast<uint32_t>(br) < static_cast<uint32_t>(n)) atomicAdd(row + br, 1);
+    }
+}
+
+int gsm_launch_stub_counts(const GsmBatch& b, int32_t* d_counts, cudaStream_t stream) {
+    if (b.n_trees <= 0) return 0;
+    gsm_stub_counts_kernel<<<static_cast<unsigned>(b.n_trees), 256, 0, stream>>>(b, d_counts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     return 1;

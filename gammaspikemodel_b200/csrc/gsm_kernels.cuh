@@ -22,6 +22,10 @@ struct GsmBatch {
     const uint8_t* use_spike;   // [T] or nullptr
     uint32_t flags;
     int32_t stub_mode;
+    // EXACT mode (gsm_upload_stubs): stub lists, CSR by tree; nullptr otherwise.  nstubs then holds the derived counts.
+    const int64_t* stub_ptr;     // [T + 1]
+    const int32_t* stub_branch;  // [S]
+    const double* stub_time;     // [S] relative position along the branch
 };
 
 // Device scratch of the lean path, owned by whoever owns the stream the evaluation runs on (one per handle slot):
@@ -36,11 +40,27 @@ struct GsmScratch {
 };
 size_t gsm_scratch_row_bytes();
 
+// Per-handle launch context: device facts, probe results and tuning overrides.  Owned by one gsm_handle (calls on a handle
+// are serialised by its caller), so nothing here is process-global: two handles on two threads or two devices never share it.
+#define GSM_CTX_MAX_KERNELS 48
+struct GsmLaunchCtx {
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_per_sm = 0;      // cudaDevAttrMaxSharedMemoryPerMultiprocessor
+    size_t smem_optin = 0;       // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int a_dyn[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // shared-window address of the dynamic segment per (lean config, rates)
+    const void* prepared[GSM_CTX_MAX_KERNELS] = {};    // kernels whose attributes were set on this handle's device
+    int n_prepared = 0;
+    // gsm_set_option (tuning / tests; 0 = automatic)
+    int force_generic = 0, block = 0, minb = 0;
+};
+cudaError_t gsm_launch_ctx_init(GsmLaunchCtx& ctx, int device);
+
 // Evaluate the whole batch: one result row per tree, optional per-branch rates / weighted spikes
 // (pitch = stride).  Returns the number of kernels launched (>=1) or a negative cudaError_t.
 // Without scratch (rows == nullptr) every wiring runs the generic kernel.
-int gsm_launch_eval(const GsmBatch& b, GsmScratch& scratch, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
-                    cudaStream_t stream);
+int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& scratch, double* d_out_tree, double* d_out_rates,
+                    double* d_out_wspikes, cudaStream_t stream);
 
 // Proposal batch (gsm_eval_dirty): dst rows [p] = src rows [tree_of_prop[p0 + p]] with the CSR edits of proposal p0 + p
 // applied; dst has the same n_nodes / stride as src.  Device pointers throughout; a null edit array = unchanged.
@@ -61,6 +81,10 @@ struct GsmBatchMut {   // writable twin of GsmBatch's arrays
 };
 int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, int64_t count, const GsmBatchMut& dst,
                      cudaStream_t stream);
+
+// EXACT mode: counts[t][i] = number of listed stubs of tree t on branch i (Stubs.getNStubsOnBranch, Stubs:357-364);
+// rows of `stride` int32, every entry of a row is written.
+int gsm_launch_stub_counts(const GsmBatch& b, int32_t* d_counts, cudaStream_t stream);
 
 // Fills the device-side sum_{i=2..n} log(i) table of the current device (idempotent).
 cudaError_t gsm_init_tables();

@@ -65,7 +65,9 @@ inline void gsm_lean_blob_fill(GsmLeanBlob& b) {
 GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
     const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
     const bool known_n = !stubs_spike || stub_mode != GSM_STUBS_NOSTUB;          // BSP:77
-    return known_n && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
+    // reversible-jump placement terms (STP:573-600, 639-663) are evaluated by the generic path only
+    const bool rj_terms = stub_mode == GSM_STUBS_EXACT && (flags & GSM_F_STUBS_TO_TREE_PRIOR) && !(flags & GSM_F_IGNORE_STUB_PRIOR);
+    return known_n && !rj_terms && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
 }
 
 // fp64 constants that do not fit an instruction immediate live in constant memory on the device, so that the hot
@@ -225,6 +227,8 @@ struct GsmLeanC {
     bool s2p, s2c;             // stubs wired to the spike prior (BSP:81) / the clock model (PRCM:192-195)
     bool stub_term;            // STP:219 && count mode
     bool use_rate;             // relaxed clock (PRCM:216)
+    bool sa_unscanned;         // the tree was not scanned for sampled ancestors (no fake flags): a direct-ancestor leaf met by
+                               // a GENERAL body sends the tree to the generic path
 };
 
 // true when the per-tree constants allow the lean path at all (everything else goes to the generic kernel)
@@ -249,6 +253,7 @@ GSM_HD void gsm_lean_consts(const GsmTreeConsts& K, GsmLeanC& c, int32_t n) {
     c.s2c = (K.flags & GSM_F_STUBS_TO_CLOCK) != 0;
     c.stub_term = K.stub_term && K.stub_counts;
     c.use_rate = !(K.flags & GSM_F_RELAXED_FALSE);
+    c.sa_unscanned = false;
 }
 
 // ---- pass A: aux(h) = log G(h) for every node; extinct-leaf terms of the psi > 0 densities -----------------------
@@ -386,6 +391,7 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
         pf = parent_fake && !root;                                                      // parent isFake
         m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
         if (!(have_len || zero)) S.chk = 0xffffffffu;                                   // negative / NaN length
+        if (da && c.sa_unscanned) S.chk = 0xffffffffu;                                  // its sibling's parent_fake is unknown here
         if (m == 0 && spike != 0.0) S.chk = 0xffffffffu;                                // BSP:86-95 -> -inf
         if (stub_term && !have_len && nst != 0) S.chk = 0xffffffffu;                    // STP:232-240, 558-561
     } else {

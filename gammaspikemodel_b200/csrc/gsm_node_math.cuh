@@ -98,6 +98,7 @@ struct GsmAcc {
 #define GSM_BAD_NEG_SPIKE 1   // BSP:72-75
 #define GSM_BAD_NEG_RATE  2   // BRP:47-50
 #define GSM_BAD_SA_STUBS  4   // STP:232-240
+#define GSM_BAD_THROWS    8   // the Java throws inside calculateTreeLogLikelihood (Stubs:631-634) -> -inf (STP:258-265)
 
 GSM_HD double gsm_neg_inf() { return -INFINITY; }
 
@@ -436,8 +437,10 @@ GSM_HD void gsm_node_pass_b(const GsmTreeConsts& K, const double* __restrict__ l
 
     // expected number of stubs on this branch (STP:749-769), where some term needs it
     const bool have_len = hp > h && !root;                                   // STP:558 / 878 (h0 <= h1 -> no stubs)
+    const bool rj = K.stub_mode == GSM_STUBS_EXACT;                          // Stubs.getReversibleJump
     double E = 0.0;
-    if (K.need_E && have_len) E = fma(len, K.kE, 2 * (aux - auxp));
+    // the reversible-jump branch of the Java has no h0 <= h1 rule: E is whatever STP:749-769 give (0 for the root)
+    if (K.need_E && (have_len || (rj && !root))) E = fma(len, K.kE, 2 * (aux - auxp));
 
     // ---- BranchSpikePrior BSP:69-174 (all N entries incl. root) ----
     if (spike < 0) A.bad |= GSM_BAD_NEG_SPIKE;                               // BSP:72-75
@@ -457,7 +460,11 @@ GSM_HD void gsm_node_pass_b(const GsmTreeConsts& K, const double* __restrict__ l
     // ---- stub density, count mode: STP:555-571 / 621-637 ----
     if (K.stub_term) {
         if (da && nst > 0) A.bad |= GSM_BAD_SA_STUBS;                        // STP:232-240
-        if (K.stub_counts && !root) {
+        if (rj) {
+            // per-branch part of STP:573-600 / 639-663: -E - sum_{i=2..count} log i (every node, the root with E = 0);
+            // the per-stub birth-rate terms are added by gsm_stub_term
+            A.stub += -E - gsm_logfact(logfact, nst);
+        } else if (K.stub_counts && !root) {
             if (!have_len) {
                 if (nst != 0) A.stub += gsm_neg_inf();                       // STP:558-561
             } else {
@@ -471,6 +478,28 @@ GSM_HD void gsm_node_pass_b(const GsmTreeConsts& K, const double* __restrict__ l
     // ---- psi = 0, rho = 1 tree density: the branch integral of STP:398-416 ----
     // B(h_i) - B(h_parent) = Lb(h_parent) - Lb(h_i), Lb = aux - lb_shift + (l-m)h  =>  -(integral) = (aux - auxp) - (l-m) len
     if (K.tree_variant == GSM_TV_COMPLETE_RHO && !root) A.tree += (aux - auxp) - K.lmm * len;
+}
+
+// ---- one listed stub of EXACT mode: STP:573-592 / 639-655 with Stubs.getAbsoluteTimeOfStub (Stubs:625-640) ----
+// h / hp: heights of the stub's branch node and of its parent; leaf_da: the node isDirectAncestor.
+GSM_HD void gsm_stub_term(const GsmTreeConsts& K, GsmAcc& A, bool root, bool leaf_da, double h, double hp, double rel_time) {
+    if (root) {                                                              // Stubs:631-634 throws -> STP:258-265
+        A.bad |= GSM_BAD_THROWS;
+        return;
+    }
+    const double t = h + rel_time * (hp - h);                                // Stubs:636
+    if (t < h || t > hp) { A.stub += gsm_neg_inf(); return; }                // STP:580-582 / 647-649
+    double log_qt;
+    if (K.stub_nosampling) {                                                 // STP:826-831
+        const double e = gsm_exp(K.lmm * t);
+        log_qt = gsm_log(K.mu * (e - 1)) - gsm_log(K.lambda * e - K.mu);
+    } else {                                                                 // STP:813-820
+        if (leaf_da) { A.stub += gsm_neg_inf(); return; }                    // STP:583-585
+        const double e = gsm_exp(-K.c1 * t);
+        const double top = e * K.omc2 - K.opc2, btm = e * K.omc2 + K.opc2;
+        log_qt = gsm_log(K.kS + K.c1 * top / btm) - K.log_2lambda;
+    }
+    A.stub += 0.69314718055994530942 + K.log_lambda + log_qt;                // STP:796-806
 }
 
 // ---- per-tree epilogue: combine reduced sums into the result row (GSM_O_*) ----
@@ -548,7 +577,7 @@ GSM_HD void gsm_finalize(const GsmTreeConsts& K, const GsmAcc& A, int32_t n, boo
         return;
     }
     if (K.stub_term) {
-        if (A.bad & GSM_BAD_SA_STUBS) {                                                     // STP:232-240
+        if (A.bad & (GSM_BAD_SA_STUBS | GSM_BAD_THROWS)) {                                  // STP:232-240, 258-265
             out[GSM_O_STP_LOGP] = gsm_neg_inf();
             out[GSM_O_TREE_LOGP] = tree;
             out[GSM_O_STUB_LOGP] = gsm_neg_inf();

@@ -63,6 +63,9 @@ class GsmEngine:
     def set_mode(self, stub_mode, flags):
         self._ck(self._lib.gsm_set_mode(self._h, int(stub_mode), int(flags)))
 
+    def set_option(self, name, value):
+        self._ck(self._lib.gsm_set_option(self._h, name.encode(), int(value)))
+
     # ---- host-buffer path ----
     def upload_trees(self, height, parent, node_count=None):
         height = _np(height, np.float64)
@@ -81,6 +84,19 @@ class GsmEngine:
         params = _np(params, np.float64, (self.n_trees, abi.NPARAM))
         use_spike = _np(use_spike, np.uint8, (self.n_trees,))
         self._ck(self._lib.gsm_upload_tree_params(self._h, _p(params), _p(use_spike)))
+
+    def upload_stubs(self, stub_ptr, stub_branch, stub_time):
+        """EXACT mode stub lists, CSR by tree (gsm_upload_stubs)."""
+        stub_ptr = _np(stub_ptr, np.int64, (self.n_trees + 1,))
+        S = int(stub_ptr[-1])
+        stub_branch = _np(stub_branch, np.int32, (S,))
+        stub_time = _np(stub_time, np.float64, (S,))
+        self._ck(self._lib.gsm_upload_stubs(self._h, _p(stub_ptr), _p(stub_branch), _p(stub_time)))
+
+    def bind_stubs(self, stub_ptr, stub_branch, stub_time):
+        """device tensors (int64 / int32 / float64) of the stub lists; kept alive by the engine"""
+        self._keep_stubs = (stub_ptr, stub_branch, stub_time)
+        self._ck(self._lib.gsm_bind_device_stubs(self._h, _dp(stub_ptr), _dp(stub_branch), _dp(stub_time)))
 
     def eval(self, want_rates=False, want_wspikes=False):
         T, N = self.n_trees, self.n_nodes

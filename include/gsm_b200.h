@@ -68,7 +68,8 @@ extern "C" {
 /* ---- Stubs.StubMode (Stubs:36-40) ---- */
 #define GSM_STUBS_NOSTUB  0   /* integrate over stub counts: getNStubsOnBranch == -1 (Stubs:348-350) */
 #define GSM_STUBS_COUNTS  1   /* stubsPerBranch, dimension N-1 (Stubs:200, 352-355) */
-#define GSM_STUBS_EXACT   2   /* RJ placement; evaluated through per-branch counts (Stubs:357-364) */
+#define GSM_STUBS_EXACT   2   /* reversible-jump placement (Stubs:42-54): the stub list of gsm_upload_stubs defines the
+                                 per-branch counts (Stubs:357-364) and the point-process density STP:573-600 / 639-663 */
 
 /* ---- per-tree parameter row: params[t * GSM_NPARAM + k] ---- */
 #define GSM_NPARAM 9
@@ -109,6 +110,12 @@ const char* gsm_last_error(const gsm_handle* h);   /* h may be NULL: error of th
  * PRCM:181,185,192-195,213-216; BSP:77; STP:174,179,219 and Stubs.initAndValidate mode selection Stubs:138-245). */
 int  gsm_set_mode(gsm_handle* h, int32_t stub_mode, uint32_t flags);
 
+/* Tuning / test options of one handle; never needed for correct results.  Names: "host_chunk_mb" (MB of inputs per
+ * streaming chunk of gsm_eval_host / gsm_eval_dirty, default 256), "force_generic" (1: every wiring runs the
+ * statement-by-statement kernel), "block" / "minb" (launch configuration override, 0 = automatic).  Stored in the
+ * handle: the library reads no environment variables and keeps no process-global mutable state. */
+int  gsm_set_option(gsm_handle* h, const char* name, int64_t value);
+
 /* ---- host-buffer path (what the Java plugin calls) ---------------------------------------------
  * All host arrays are caller-owned and are copied before the call returns. */
 
@@ -122,6 +129,22 @@ int  gsm_upload_trees(gsm_handle* h, int64_t n_trees, int32_t n_nodes,
 int  gsm_upload_branch_params(gsm_handle* h, const double* rate, const double* spike, const int32_t* nstubs);
 /* Per-tree scalars (GSM_P_*) and the GSMuseSpikeModel indicator (NULL => true for every tree). */
 int  gsm_upload_tree_params(gsm_handle* h, const double* params, const uint8_t* use_spike);
+
+/* Stubs in exact (reversible-jump) mode: the stub list of every tree of the resident batch, CSR by tree (entries
+ * [stub_ptr[t], stub_ptr[t+1]) belong to tree t; stub_ptr has n_trees + 1 entries).  stub_branch[j] / stub_time[j] are
+ * Stubs.branchNr / Stubs.time (relative position along the branch, Stubs:625-640) of the Java entries 1 .. dim-1; the
+ * dummy at index 0, which Stubs.includeStub always rejects (Stubs:285-287), is not passed.  On the device the list
+ * replaces the O(S) scans of Stubs.getNStubsOnBranch (Stubs:357-364; used by PRCM:195, BSP:81, STP:232-240) and of
+ * getStubLogPForBranchWith/WithoutSampling (STP:573-600, 639-663): per stub log 2 + log lambda + logQt(height)
+ * (STP:796-831), per branch -E - log(count!); a stub outside its branch, or on a sampled ancestor when psi > 0 or
+ * rho < 1, gives -inf; a stub on the root makes the Java throw (Stubs:631-634, caught at STP:258-265) and the state
+ * -inf.  Stubs whose branch is outside [0, n) match no branch in the reference and are ignored.
+ * Call after gsm_upload_trees; needed (GSM_E_STATE otherwise) whenever stub_mode is GSM_STUBS_EXACT and the stub prior
+ * is evaluated (GSM_F_STUBS_TO_TREE_PRIOR without GSM_F_IGNORE_STUB_PRIOR).  Without a stub list, EXACT mode takes the
+ * per-branch counts from the nstubs array of gsm_upload_branch_params (all n entries), which is enough for PRCM / BSP.
+ * gsm_eval_host and gsm_eval_dirty do not take stub lists: in EXACT mode with the stub prior evaluated they return
+ * GSM_E_UNSUPPORTED (reversible-jump moves change the list itself; upload the proposed state instead). */
+int  gsm_upload_stubs(gsm_handle* h, const int64_t* stub_ptr, const int32_t* stub_branch, const double* stub_time);
 
 /* Evaluate the resident batch.  out_tree [T][GSM_NOUT] is required.  out_rates [T][n_nodes] (optional)
  * receives PRCM.getRatesArray() (PRCM:267-276; getRateForBranch PRCM:225-242); out_wspikes [T][n_nodes]
@@ -172,6 +195,9 @@ int  gsm_bind_device(gsm_handle* h, int64_t n_trees, int32_t n_nodes, int64_t st
                      const double* d_height, const int32_t* d_parent, const int32_t* d_node_count,
                      const double* d_rate, const double* d_spike, const int32_t* d_nstubs,
                      const double* d_params, const uint8_t* d_use_spike);
+/* Device-resident stub lists of EXACT mode (see gsm_upload_stubs); call after gsm_bind_device.  The handle allocates the
+ * derived per-branch count rows itself.  NULL stub_ptr removes the list. */
+int  gsm_bind_device_stubs(gsm_handle* h, const int64_t* d_stub_ptr, const int32_t* d_stub_branch, const double* d_stub_time);
 /* Launch on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) and return without
  * synchronising.  d_out_rates / d_out_wspikes have pitch `stride` and may be NULL. */
 int  gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,

@@ -187,15 +187,20 @@ static inline int parent_is_fake(const gsmo_tree* t, const node_info* ni, int32_
 }
 
 /* Stubs.getNStubsOnBranch Stubs:344-370 (nostub -> -1; branchCounts -> nr>=dim ? 0 : value[nr],
- * dim = nodeCount-1 per Stubs:200).  EXACT mode takes per-branch counts precomputed by the caller
- * (count of stubs whose branch == nr, Stubs:357-364) over all n entries. */
+ * dim = nodeCount-1 per Stubs:200; exact -> number of listed stubs whose branch == nr, Stubs:357-364:
+ * the O(S) scan of the Java, index 0 excluded by includeStub Stubs:285-287). */
 static int32_t nstubs_on_branch(const gsmo_config* cfg, const gsmo_tree* t, int32_t nr) {
     switch (cfg->stub_mode) {
         case GSMO_STUBS_NOSTUB: return -1;
         case GSMO_STUBS_COUNTS:
             if (nr >= t->n - 1) return 0;
             return t->nstubs[nr];
-        case GSMO_STUBS_EXACT: return t->nstubs[nr];
+        case GSMO_STUBS_EXACT: {
+            int32_t nstubs = 0;
+            for (int32_t i = 0; i < t->n_stub_entries; i++)
+                if (t->stub_branch[i] == nr) nstubs++;
+            return nstubs;
+        }
     }
     return -1;
 }
@@ -489,15 +494,47 @@ static double tree_logp_conditioned(const gsmo_config* cfg, const gsmo_tree* t, 
     return treeLogP;
 }
 
-/* count-mode branch of getStubLogPForBranchWithSampling STP:539-571 / ...WithoutSampling STP:605-637 */
+/* getStubLogBirthRate STP:796-806 */
+double gsmo_stub_log_birth_rate_sampling(double t, double lambda, double mu, double psi, double rho) { /* STP:796-800 */
+    double logQt = gsmo_log_qt_sampling(t, lambda, mu, psi, rho);
+    return log(2) + log(lambda) + logQt;
+}
+double gsmo_stub_log_birth_rate_nosampling(double t, double lambda, double mu) { /* STP:802-806 */
+    double logQt = gsmo_log_qt_nosampling(t, lambda, mu);
+    return log(2) + log(lambda) + logQt;
+}
+
+/* getStubLogPForBranchWithSampling STP:539-601 / getStubLogPForBranchWithoutSampling STP:605-665.
+ * *threw is set where the Java throws (Stubs.getAbsoluteTimeOfStub on the root, Stubs:631-634; the exception is caught
+ * at STP:258-265 and calculateTreeLogLikelihood returns -inf). */
 static double stub_logp_branch(const gsmo_config* cfg, const gsmo_tree* t, const node_info* ni, int32_t nr,
-                               double lambda, double mu, double psi, double rho, int with_sampling) {
+                               double lambda, double mu, double psi, double rho, int with_sampling, int* threw) {
     if (!estimate_stubs(cfg)) return 0;                                                  /* STP:547 / 613 */
     double tree_h = t->height[ni->root];
     double h0 = is_root(t, nr) ? tree_h : t->height[t->parent[nr]];                      /* STP:550 / 616 */
     double h1 = t->height[nr];
-    /* reversible-jump placement terms (STP:573-600 / 639-663) need the stub time list: not part of
-     * the batched path; EXACT mode is evaluated through its per-branch counts like branchCounts. */
+    if (cfg->stub_mode == GSMO_STUBS_EXACT) {                                            /* STP:573-600 / 639-663 */
+        double stubLogP = 0;
+        int stubCount = 0;
+        for (int32_t s = 0; s < t->n_stub_entries; s++) {                                /* includeStub: index 0 never listed */
+            if (t->stub_branch[s] != nr) continue;
+            /* Stubs.getAbsoluteTimeOfStub Stubs:625-640 */
+            if (is_root(t, nr)) { *threw = 1; return NEG_INF; }                          /* Stubs:631-634 throws */
+            double parent_h = t->height[t->parent[nr]];
+            double stubHeight = h1 + t->stub_time[s] * (parent_h - h1);                  /* Stubs:636 */
+            if (stubHeight < h1 || stubHeight > parent_h) return NEG_INF;                /* STP:580-582 / 647-649 */
+            if (with_sampling && ni->da[nr]) return NEG_INF;                             /* STP:583-585 (sampling variant only) */
+            double logRate = with_sampling ? gsmo_stub_log_birth_rate_sampling(stubHeight, lambda, mu, psi, rho)
+                                           : gsmo_stub_log_birth_rate_nosampling(stubHeight, lambda, mu);
+            stubLogP += logRate;                                                         /* STP:587-589 / 651-653 */
+            stubCount++;
+        }
+        double E = with_sampling ? gsmo_expected_stubs_sampling(h1, h0, lambda, mu, psi, rho)   /* STP:594 */
+                                 : gsmo_expected_stubs_nosampling(h1, h0, lambda, mu, tree_h);  /* STP:658 */
+        stubLogP += -E;                                                                  /* STP:596 / 659 */
+        for (int i = 2; i <= stubCount; i++) stubLogP += -log((double)i);                /* STP:597 / 660 */
+        return stubLogP;
+    }
     if (is_root(t, nr)) return 0;                                                        /* STP:556 / 622 */
     int32_t cnt = nstubs_on_branch(cfg, t, nr);
     if (h0 <= h1) {                                                                      /* STP:558-561 */
@@ -545,8 +582,10 @@ static void stumped_tree_prior(const gsmo_config* cfg, const gsmo_tree* t, const
             }
         }
         int with_sampling = !((psi == 0) && (rho == 1));                                 /* STP:243-253 */
-        for (int32_t nr = 0; nr < t->n; nr++)
-            stubLogP += stub_logp_branch(cfg, t, ni, nr, lambda, mu, psi, rho, with_sampling);
+        int threw = 0;
+        for (int32_t nr = 0; nr < t->n && !threw; nr++)
+            stubLogP += stub_logp_branch(cfg, t, ni, nr, lambda, mu, psi, rho, with_sampling, &threw);
+        if (threw) { *stp = NEG_INF; *stub_lp = NEG_INF; return; }                       /* STP:258-265 */
     }
     *stub_lp = stubLogP;
     *stp = treeLogP + stubLogP;                                                          /* STP:280 */
@@ -601,7 +640,18 @@ int gsmo_eval_batch(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, in
                     const int32_t* nstubs, const double* params, const uint8_t* use_spike,
                     const int32_t* node_count, double* out_tree, double* out_rates, double* out_wspikes,
                     int n_threads) {
+    return gsmo_eval_batch_stubs(cfg, n_trees, n_nodes, stride, height, parent, rate, spike, nstubs, params, use_spike,
+                                 node_count, NULL, NULL, NULL, out_tree, out_rates, out_wspikes, n_threads);
+}
+
+int gsmo_eval_batch_stubs(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, int64_t stride,
+                          const double* height, const int32_t* parent, const double* rate, const double* spike,
+                          const int32_t* nstubs, const double* params, const uint8_t* use_spike,
+                          const int32_t* node_count, const int64_t* stub_ptr, const int32_t* stub_branch,
+                          const double* stub_time, double* out_tree, double* out_rates, double* out_wspikes,
+                          int n_threads) {
     if (n_trees < 0 || n_nodes < 0 || stride < n_nodes) return 1;
+    if (cfg->stub_mode == GSMO_STUBS_EXACT && !stub_ptr) return 2;   /* exact mode is defined by its stub list */
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
@@ -618,6 +668,9 @@ int gsmo_eval_batch(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, in
         t.nstubs = nstubs ? nstubs + ti * stride : NULL;
         t.params = params + ti * GSMO_NPARAM;
         t.use_spike = use_spike ? use_spike[ti] : 1;
+        t.n_stub_entries = stub_ptr ? (int32_t)(stub_ptr[ti + 1] - stub_ptr[ti]) : 0;
+        t.stub_branch = stub_ptr ? stub_branch + stub_ptr[ti] : NULL;
+        t.stub_time = stub_ptr ? stub_time + stub_ptr[ti] : NULL;
         gsmo_eval_tree(cfg, &t, out_tree + ti * GSMO_NOUT, out_rates ? out_rates + ti * stride : NULL,
                        out_wspikes ? out_wspikes + ti * stride : NULL);
     }

@@ -104,9 +104,15 @@ typedef struct gsmo_tree {
     const int32_t* parent;     /* [n], -1 for the root */
     const double*  rate;       /* [n] or NULL when rates are not wired */
     const double*  spike;      /* [n] */
-    const int32_t* nstubs;     /* [n]; entry i >= n-1 is ignored (Stubs.java:200,354); NULL if no counts */
+    const int32_t* nstubs;     /* [n]; entry i >= n-1 is ignored (Stubs.java:200,354); NULL if no counts.  Not used in
+                                  EXACT mode: there the counts come from the stub list (Stubs.java:357-364) */
     const double*  params;     /* [GSMO_NPARAM] */
     int32_t use_spike;         /* value of the indicator (GSMuseSpikeModel) */
+    /* EXACT (reversible-jump) mode, Stubs.java:42-54: entries 1 .. dim-1 of Stubs.branchNr / Stubs.time (index 0 is the
+     * dummy that Stubs.includeStub always rejects, Stubs.java:285-287) */
+    int32_t n_stub_entries;
+    const int32_t* stub_branch;  /* [n_stub_entries] branch (node number) the stub sits on */
+    const double*  stub_time;    /* [n_stub_entries] relative position along the branch, Stubs.java:625-640 */
 } gsmo_tree;
 
 /* Evaluate everything for one tree.  out[GSMO_NOUT]; out_rates / out_wspikes are [n] or NULL
@@ -124,6 +130,15 @@ int gsmo_eval_batch(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, in
                     const int32_t* nstubs, const double* params, const uint8_t* use_spike,
                     const int32_t* node_count /* NULL => n_nodes for every tree */,
                     double* out_tree, double* out_rates, double* out_wspikes, int n_threads);
+/* ... with the stub lists of EXACT mode, CSR by tree: entries [stub_ptr[t], stub_ptr[t+1]) belong to tree t */
+int gsmo_eval_batch_stubs(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, int64_t stride,
+                          const double* height, const int32_t* parent, const double* rate, const double* spike,
+                          const int32_t* nstubs, const double* params, const uint8_t* use_spike,
+                          const int32_t* node_count, const int64_t* stub_ptr, const int32_t* stub_branch,
+                          const double* stub_time, double* out_tree, double* out_rates, double* out_wspikes, int n_threads);
+/* getStubLogBirthRate STP:796-806 (log 2 + log lambda + logQt) */
+double gsmo_stub_log_birth_rate_sampling(double t, double lambda, double mu, double psi, double rho);
+double gsmo_stub_log_birth_rate_nosampling(double t, double lambda, double mu);
 
 int gsmo_max_threads(void);
 

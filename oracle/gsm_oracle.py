@@ -68,6 +68,12 @@ def lib():
         L.gsmo_cumulative_probs.argtypes = [d, d, d, C.c_int, C.POINTER(d), C.c_int32]
         L.gsmo_eval_batch.restype = C.c_int
         L.gsmo_eval_batch.argtypes = [C.POINTER(_Config), C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int]
+        L.gsmo_eval_batch_stubs.restype = C.c_int
+        L.gsmo_eval_batch_stubs.argtypes = [C.POINTER(_Config), C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 14 + [C.c_int]
+        for name, nargs in [("gsmo_stub_log_birth_rate_sampling", 5), ("gsmo_stub_log_birth_rate_nosampling", 3)]:
+            f = getattr(L, name)
+            f.restype = d
+            f.argtypes = [d] * nargs
         L.gsmo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -87,8 +93,9 @@ def _arr(a, dtype, shape=None):
 
 
 def eval_batch(flags, stub_mode, height, parent, rate, spike, nstubs, params, use_spike=None, node_count=None,
-               want_rates=False, want_wspikes=False, n_threads=1):
-    """Evaluate a [T][stride] batch.  Returns dict(out=[T][8], rates=[T][stride]|None, wspikes=...)."""
+               want_rates=False, want_wspikes=False, n_threads=1, stubs=None):
+    """Evaluate a [T][stride] batch.  Returns dict(out=[T][8], rates=[T][stride]|None, wspikes=...).
+    stubs = (stub_ptr [T+1] int64, stub_branch [S] int32, stub_time [S] float64): the stub lists of EXACT mode."""
     height = _arr(height, np.float64)
     T, stride = height.shape
     parent = _arr(parent, np.int32, (T, stride))
@@ -102,9 +109,14 @@ def eval_batch(flags, stub_mode, height, parent, rate, spike, nstubs, params, us
     rates = np.full((T, stride), np.nan) if want_rates else None
     wsp = np.full((T, stride), np.nan) if want_wspikes else None
     cfg = _Config(int(flags), int(stub_mode))
-    rc = lib().gsmo_eval_batch(C.byref(cfg), T, stride, stride, _ptr(height), _ptr(parent), _ptr(rate), _ptr(spike),
-                               _ptr(nstubs), _ptr(params), _ptr(use_spike), _ptr(node_count), _ptr(out), _ptr(rates),
-                               _ptr(wsp), int(n_threads))
+    sp = sb = st = None
+    if stubs is not None:
+        sp = _arr(stubs[0], np.int64, (T + 1,))
+        sb = _arr(stubs[1], np.int32, (int(sp[-1]),))
+        st = _arr(stubs[2], np.float64, (int(sp[-1]),))
+    rc = lib().gsmo_eval_batch_stubs(C.byref(cfg), T, stride, stride, _ptr(height), _ptr(parent), _ptr(rate), _ptr(spike),
+                                     _ptr(nstubs), _ptr(params), _ptr(use_spike), _ptr(node_count), _ptr(sp), _ptr(sb),
+                                     _ptr(st), _ptr(out), _ptr(rates), _ptr(wsp), int(n_threads))
     if rc != 0:
         raise RuntimeError("gsmo_eval_batch failed: %d" % rc)
     return {"out": out, "rates": rates, "wspikes": wsp}

@@ -3,7 +3,7 @@
 import numpy as np
 
 from gammaspikemodel_b200 import abi, synthetic
-from helpers import host_arrays, variant
+from helpers import host_arrays, stubs_from_counts, variant
 
 F = synthetic.DEFAULT_FLAGS
 NOSTUBS = abi.F_HAS_INDICATOR | abi.F_HAS_RATES
@@ -12,6 +12,18 @@ NOSTUBS = abi.F_HAS_INDICATOR | abi.F_HAS_RATES
 def _base(kind, T, n, seed=None):
     b = synthetic.make_batch(kind, T, n, seed=seed)
     return host_arrays(b)
+
+
+def swap_labels(a, t, i, j):
+    """renumber nodes i <-> j of tree t (same tree, different Node.getNr())"""
+    for k in ("height", "rate", "spike", "nstubs"):
+        a[k][t, [i, j]] = a[k][t, [j, i]]
+    p = a["parent"][t].copy()
+    p[[i, j]] = p[[j, i]]
+    q = p.copy()
+    q[p == i] = j
+    q[p == j] = i
+    a["parent"][t] = q
 
 
 def build_cases():
@@ -29,7 +41,55 @@ def build_cases():
     add("c3-nostub-mixture", c3, F, abi.STUBS_NOSTUB)                      # BSP:102-172, quirk 2 of SURVEY §8a
     add("c2-nostub-mixture", c2, F, abi.STUBS_NOSTUB)
     add("c4-nostub-mixture", c4, F, abi.STUBS_NOSTUB)
-    add("c3-exact-counts", c3, F, abi.STUBS_EXACT)
+    # ---- Stubs exact (reversible-jump) mode: stub lists, STP:573-600 / 639-663 ----
+    def exact(a, seed):
+        b = {k: v.copy() for k, v in a.items()}
+        b["stubs"] = stubs_from_counts(b, seed)
+        b["nstubs"] = np.zeros_like(b["nstubs"])      # not used in exact mode: the list defines the counts
+        return b
+    x3, x2, x4 = exact(c3, 1), exact(c2, 2), exact(c4, 3)
+    add("c3-exact", x3, F, abi.STUBS_EXACT)                                # psi > 0: getLogQt(t, l, m, psi, rho)
+    add("c2-exact", x2, F, abi.STUBS_EXACT)                                # psi == 0, rho == 1: getLogQt(t, l, m)
+    add("c4-exact", x4, F, abi.STUBS_EXACT)
+    add("c3-exact-ignore-stub-prior", x3, F | abi.F_IGNORE_STUB_PRIOR, abi.STUBS_EXACT)   # counts only: PRCM:195, BSP:81
+    add("c3-exact-origin", variant(x3, F, origin=1e3), F | abi.F_ORIGIN, abi.STUBS_EXACT)
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in x3.items()}
+    ptr, br, tm = (v.copy() for v in b["stubs"])
+    for t in range(0, len(ptr) - 1, 3):                                    # a stub outside its branch -> -inf (STP:580-582)
+        if ptr[t + 1] > ptr[t]:
+            tm[ptr[t]] = 1.5 if t % 2 else -0.25
+    b["stubs"] = (ptr, br, tm)
+    add("c3-exact-stub-outside-branch", b, F, abi.STUBS_EXACT)
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in x3.items()}
+    ptr, br, tm = (v.copy() for v in b["stubs"])
+    n3x = b["height"].shape[1]
+    for t in range(0, len(ptr) - 1, 2):                                    # a stub on the root: the Java throws (Stubs:631-634)
+        if ptr[t + 1] > ptr[t]:
+            br[ptr[t + 1] - 1] = n3x - 1
+    b["stubs"] = (ptr, br, tm)
+    add("c3-exact-stub-on-root", b, F, abi.STUBS_EXACT)
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in x3.items()}
+    ptr, br, tm = (v.copy() for v in b["stubs"])
+    for t in range(len(ptr) - 1):                                          # a stub on a sampled ancestor (STP:232-240, 583-585)
+        h, p = b["height"][t], b["parent"][t]
+        sa = [i for i in range((n3x + 1) // 2) if p[i] >= 0 and h[p[i]] == h[i]]
+        if sa and ptr[t + 1] > ptr[t] and t % 2 == 0:
+            br[ptr[t]] = sa[0]
+    b["stubs"] = (ptr, br, tm)
+    add("c3-exact-stub-on-sampled-ancestor", b, F, abi.STUBS_EXACT)
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in x2.items()}
+    ptr, br, tm = (v.copy() for v in b["stubs"])
+    br[::5] = 10_000                                                       # branch numbers that match no node: ignored
+    br[1::7] = -3
+    b["stubs"] = (ptr, br, tm)
+    add("c2-exact-unmatched-branches", b, F, abi.STUBS_EXACT)
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in x2.items()}
+    nl2 = (b["height"].shape[1] + 1) // 2
+    for t in range(0, b["height"].shape[0], 3):                            # zero-length internal branch carrying stubs:
+        i = nl2 + 1                                                        # no h0 <= h1 rule in the RJ branch, E = 0
+        b["height"][t, i] = b["height"][t, b["parent"][t, i]]
+    add("c2-exact-zero-length-branches", b, F, abi.STUBS_EXACT)
+    add("c2-exact-mu-zero", variant(x2, F, mu=0.0), F, abi.STUBS_EXACT)    # log(mu (e - 1)) = -inf (STP:826-831)
     add("c3-strict-clock", c3, F | abi.F_RELAXED_FALSE)                    # PRCM:216-220
     add("c3-no-rates", c3, F & ~abi.F_HAS_RATES)                           # PRCM:213
     add("c3-no-indicator", c3, F & ~abi.F_HAS_INDICATOR)
@@ -90,6 +150,26 @@ def build_cases():
     a = variant(c2, F, lam=40.0, mu=1.0)                                   # exp(lambda*T) overflow -> NaN tree term (STP:420)
     a["height"] *= 30.0
     add("c2-exp-lambda-T-overflow", a)
+    # sampled ancestors where the tree prior does not generate them (psi == 0): the lean kernel does not scan such trees
+    # for fake parents, so every flavour of its bodies has to hand them to the generic path
+    a = variant(c3, F, psi=0.0, rho=1.0)
+    n3 = a["height"].shape[1]
+    for t in range(a["height"].shape[0]):                                  # (a) root is not node n-1
+        swap_labels(a, t, n3 - 1, n3 - 2 - (t % 5))
+    add("c3-psi0-sa-root-not-last", a)
+    odd = _base("C3", 24, 61)                                              # (b) L odd and the tail leaf L-1 is a sampled ancestor
+    Lo = 61
+    for t in range(odd["height"].shape[0]):
+        odd["height"][t, Lo - 1] = odd["height"][t, odd["parent"][t, Lo - 1]]
+        odd["spike"][t, Lo - 1] = 0.0
+        odd["nstubs"][t, Lo - 1] = 0
+    add("c3-psi0-sa-tail-leaf", variant(odd, F, psi=0.0, rho=1.0))
+    add("c3-psi0-rho-lt1-sa-tail-leaf", variant(odd, F, psi=0.0, rho=0.4))
+    add("c3-sa-tail-leaf", odd)                                            # same trees under psi > 0 (scanned)
+    a = {k: v.copy() for k, v in c3.items()}
+    for t in range(a["height"].shape[0]):
+        swap_labels(a, t, n3 - 1, n3 - 2 - (t % 7))
+    add("c3-root-not-last", a)                                             # GENERAL flavour with the scan
     # ---- shapes ----
     add("two-taxa", _base("C3", 40, 2))
     add("single-node-trees", _base("C2", 7, 1))

@@ -27,8 +27,17 @@ static void init_tables() {
 
 template <bool WANT>
 static void eval_tree(uint32_t flags, int32_t stub_mode, int32_t n, const double* h, const int32_t* par_in,
-                      const double* rate, const double* spike, const int32_t* nstubs, const double* params,
-                      int32_t use_spike, double* out, double* out_rates, double* out_wsp) {
+                      const double* rate, const double* spike, const int32_t* nstubs_in, const double* params,
+                      int32_t use_spike, double* out, double* out_rates, double* out_wsp, int64_t n_stub = 0,
+                      const int32_t* stub_branch = nullptr, const double* stub_time = nullptr) {
+    std::vector<int32_t> counts;
+    const int32_t* nstubs = nstubs_in;
+    if (stub_mode == GSM_STUBS_EXACT && stub_branch) {   // gsm_stub_counts_kernel
+        counts.assign(n > 0 ? n : 1, 0);
+        for (int64_t j = 0; j < n_stub; j++)
+            if ((uint32_t)stub_branch[j] < (uint32_t)n) counts[stub_branch[j]]++;
+        nstubs = counts.data();
+    }
     if (n <= 0) {
         for (int k = 0; k < GSM_NOUT; k++) out[k] = NAN;
         return;
@@ -82,12 +91,42 @@ static void eval_tree(uint32_t flags, int32_t stub_mode, int32_t n, const double
         gsm_node_pass_b<WANT>(K, g_logfact_host, A, i, n, nf, h[i], hp, aux[i], auxp, rate ? rate[i] : 1.0, spike[i],
                               nstubs ? nstubs[i] : 0, out_rates ? out_rates + i : nullptr, out_wsp ? out_wsp + i : nullptr);
     }
+    if (stub_branch && K.stub_term && K.stub_mode == GSM_STUBS_EXACT) {   // phase 3b
+        for (int64_t j = 0; j < n_stub; j++) {
+            const int32_t br = stub_branch[j];
+            if ((uint32_t)br >= (uint32_t)n) continue;
+            const int32_t p = par[br];
+            const bool rt = p < 0;
+            const double hp = rt ? h[br] : h[p];
+            const bool da = !rt && !nonleaf[br] && hp == h[br];
+            gsm_stub_term(K, A, rt, da, h[br], hp, stub_time[j]);
+        }
+    }
     if (root < 0) {
         for (int k = 0; k < GSM_NOUT; k++) out[k] = NAN;
         return;
     }
     gsm_finish_consts(K, h[root]);
     gsm_finalize(K, A, n, fake[root] != 0, out);
+}
+
+// EXACT mode with stub lists (CSR by tree): the generic walk, as gsm_eval_kernel + gsm_stub_counts_kernel do it
+extern "C" int gsm_emu_eval_batch_stubs(uint32_t flags, int32_t stub_mode, int64_t n_trees, int32_t n_nodes, int64_t stride,
+                                        const double* height, const int32_t* parent, const double* rate, const double* spike,
+                                        const int32_t* nstubs, const double* params, const uint8_t* use_spike,
+                                        const int32_t* node_count, const int64_t* stub_ptr, const int32_t* stub_branch,
+                                        const double* stub_time, double* out_tree, double* out_rates, double* out_wsp) {
+    init_tables();
+    for (int64_t t = 0; t < n_trees; t++) {
+        int32_t n = node_count ? node_count[t] : n_nodes;
+        const int64_t r = t * stride;
+        const int64_t s0 = stub_ptr ? stub_ptr[t] : 0, s1 = stub_ptr ? stub_ptr[t + 1] : 0;
+        eval_tree<true>(flags, stub_mode, n, height + r, parent + r, rate ? rate + r : nullptr, spike + r,
+                        nstubs ? nstubs + r : nullptr, params + t * GSM_NPARAM, use_spike ? use_spike[t] : 1,
+                        out_tree + t * GSM_NOUT, out_rates ? out_rates + r : nullptr, out_wsp ? out_wsp + r : nullptr, s1 - s0,
+                        stub_ptr ? stub_branch + s0 : nullptr, stub_ptr ? stub_time + s0 : nullptr);
+    }
+    return 0;
 }
 
 extern "C" int gsm_emu_eval_batch(uint32_t flags, int32_t stub_mode, int64_t n_trees, int32_t n_nodes, int64_t stride,
@@ -201,6 +240,7 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     const uint32_t nL = (uint32_t)(n - L);
     // phase 1: sampled-ancestor scan (only where they can occur)
     const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);
+    c.sa_unscanned = !detect;
     std::vector<uint8_t> fk(n - L4 + 8, 0);
     bool anyda = false;
     if (detect)

@@ -22,6 +22,8 @@ def emu():
         _emu.gsm_emu_eval_batch.restype = C.c_int
         _emu.gsm_emu_eval_batch_lean.argtypes = _emu.gsm_emu_eval_batch.argtypes + [C.c_void_p]
         _emu.gsm_emu_eval_batch_lean.restype = C.c_int
+        _emu.gsm_emu_eval_batch_stubs.argtypes = [C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 14
+        _emu.gsm_emu_eval_batch_stubs.restype = C.c_int
     return _emu
 
 
@@ -37,8 +39,31 @@ def host_arrays(b):
 
 def run_oracle(a, flags, mode, node_count=None, rates=True, threads=0):
     r = oracle.eval_batch(flags, mode, a["height"], a["parent"], a["rate"], a["spike"], a["nstubs"], a["params"],
-                          a["use_spike"], node_count=node_count, want_rates=rates, want_wspikes=rates, n_threads=threads)
+                          a["use_spike"], node_count=node_count, want_rates=rates, want_wspikes=rates, n_threads=threads,
+                          stubs=a.get("stubs"))
     return r
+
+
+def stubs_from_counts(a, seed=0, n_nodes=None):
+    """EXACT-mode stub lists (CSR by tree) that realise the per-branch counts of a["nstubs"] (entries 0 .. n-2; the root
+    carries no stub): uniform relative times along each branch."""
+    rng = np.random.default_rng(seed)
+    T, N = a["nstubs"].shape
+    cnt = a["nstubs"].copy()
+    cnt[:, N - 1:] = 0
+    if n_nodes is not None:
+        for t in range(T):
+            cnt[t, n_nodes[t] - 1:] = 0
+    cnt = np.maximum(cnt, 0)
+    ptr = np.zeros(T + 1, np.int64)
+    ptr[1:] = np.cumsum(cnt.sum(axis=1))
+    branch = np.repeat(np.tile(np.arange(N, dtype=np.int32), T), cnt.ravel())
+    time = rng.random(branch.shape[0])
+    # shuffle inside each tree: the list is unordered in the reference
+    for t in range(T):
+        perm = rng.permutation(ptr[t + 1] - ptr[t]) + ptr[t]
+        branch[ptr[t]:ptr[t + 1]] = branch[perm]
+    return ptr, branch.astype(np.int32), time
 
 
 def run_emu(a, flags, mode, node_count=None, rates=True):
@@ -47,6 +72,14 @@ def run_emu(a, flags, mode, node_count=None, rates=True):
     r = np.full((T, N), np.nan) if rates else None
     w = np.full((T, N), np.nan) if rates else None
     nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
+    if a.get("stubs") is not None:
+        sp, sb, st = (np.ascontiguousarray(x, d) for x, d in zip(a["stubs"], (np.int64, np.int32, np.float64)))
+        r = np.full((T, N), np.nan)
+        w = np.full((T, N), np.nan)
+        emu().gsm_emu_eval_batch_stubs(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
+                                       _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(sp), _p(sb), _p(st),
+                                       _p(out), _p(r), _p(w))
+        return {"out": out, "rates": r if rates else None, "wspikes": w if rates else None}
     emu().gsm_emu_eval_batch(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
                              _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w))
     return {"out": out, "rates": r, "wspikes": w}
@@ -61,6 +94,10 @@ def run_emu_lean(a, flags, mode, node_count=None, rates=True):
     w = np.full((T, N), np.nan) if rates else None
     nc = None if node_count is None else np.ascontiguousarray(node_count, np.int32)
     n_lean = np.zeros(1, np.int64)
+    if a.get("stubs") is not None and not (flags & abi.F_IGNORE_STUB_PRIOR) and (flags & abi.F_STUBS_TO_TREE_PRIOR):
+        return None   # reversible-jump placement terms: generic path only (gsm_lean_wiring_ok)
+    if a.get("stubs") is not None:
+        return None   # the emulated lean walk takes counts, not lists
     rc = emu().gsm_emu_eval_batch_lean(flags, mode, T, N, N, _p(a["height"]), _p(a["parent"]), _p(a["rate"]), _p(a["spike"]),
                                        _p(a["nstubs"]), _p(a["params"]), _p(a["use_spike"]), _p(nc), _p(out), _p(r), _p(w),
                                        _p(n_lean))
@@ -77,6 +114,8 @@ def run_capi(a, flags, mode, node_count=None, rates=True, engine=None):
     eng.upload_trees(a["height"], a["parent"], node_count)
     eng.upload_branch_params(a["rate"], a["spike"], a["nstubs"])
     eng.upload_tree_params(a["params"], a["use_spike"])
+    if a.get("stubs") is not None:
+        eng.upload_stubs(*a["stubs"])
     r = eng.eval(want_rates=rates, want_wspikes=rates)
     if engine is None:
         eng.close()
@@ -120,7 +159,7 @@ def assert_results_match(got, ref, n_nodes=None, node_count=None, what=""):
 
 def variant(a, flags, **edits):
     """copy of the host arrays with per-tree parameter edits, e.g. psi=0.0, rho=1.0"""
-    b = {k: v.copy() for k, v in a.items()}
+    b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in a.items()}
     idx = dict(clock_rate=abi.P_CLOCK_RATE, spike_mean=abi.P_SPIKE_MEAN, shape=abi.P_SPIKE_SHAPE, sigma=abi.P_CLOCK_SD,
                lam=abi.P_LAMBDA, mu=abi.P_MU, psi=abi.P_PSI, rho=abi.P_RHO, origin=abi.P_ORIGIN)
     for k, v in edits.items():

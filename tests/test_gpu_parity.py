@@ -84,12 +84,12 @@ def test_state_updates_between_evals():
 
 
 @pytest.mark.parametrize("kind,T,n", [("C3", 700, 150), ("C4", 37, 1200)])
-def test_streaming_host_path_equals_resident_path(kind, T, n, monkeypatch):
+def test_streaming_host_path_equals_resident_path(kind, T, n):
     """gsm_eval_host (chunked, double-buffered) must return bit-identical rows to upload + gsm_eval."""
-    monkeypatch.setenv("GSM_HOST_CHUNK_MB", "1")        # force many chunks
     b = synthetic.make_batch(kind, T, n)
     a = host_arrays(b)
     eng = GsmEngine(max_trees=T, max_nodes=b.n_nodes)
+    eng.set_option("host_chunk_mb", 1)                   # force many chunks
     resident = run_capi(a, b.flags, b.stub_mode, engine=eng)
     eng.set_mode(b.stub_mode, b.flags)
     streamed = eng.eval_host(a["height"], a["parent"], a["spike"], a["params"], rate=a["rate"], nstubs=a["nstubs"],
@@ -236,3 +236,119 @@ def test_ragged_batch_mixed_tree_sizes_matches_oracle(kind):
     ref = run_oracle(a, F_, abi.STUBS_COUNTS, node_count=nc)
     got = run_capi(a, F_, abi.STUBS_COUNTS, node_count=nc)
     assert_results_match(got, ref, node_count=nc, what="ragged " + kind)
+
+
+def test_exact_mode_needs_the_stub_list_where_the_reference_uses_it():
+    """GSM_STUBS_EXACT: the point-process stub density (STP:573-600 / 639-663) is defined by the stub list; without it the
+    call fails instead of returning the count-mode density (round-1 parity hole)."""
+    from helpers import stubs_from_counts
+    b = synthetic.make_batch("C3", 16, 40)
+    a = host_arrays(b)
+    eng = GsmEngine(max_trees=16, max_nodes=b.n_nodes)
+    eng.set_mode(abi.STUBS_EXACT, F)
+    eng.upload_trees(a["height"], a["parent"])
+    eng.upload_branch_params(a["rate"], a["spike"], a["nstubs"])
+    eng.upload_tree_params(a["params"], a["use_spike"])
+    with pytest.raises(GsmError) as ei:
+        eng.eval()
+    assert ei.value.code == abi.E_STATE
+    with pytest.raises(GsmError) as ei:
+        eng.eval_host(a["height"], a["parent"], a["spike"], a["params"], rate=a["rate"], nstubs=a["nstubs"], use_spike=a["use_spike"])
+    assert ei.value.code == abi.E_UNSUPPORTED
+    with pytest.raises(GsmError) as ei:
+        eng.eval_dirty(np.array([0], np.int32), np.array([0, 0], np.int64), np.zeros(0, np.int32))
+    assert ei.value.code == abi.E_UNSUPPORTED
+    # stub prior not evaluated: the per-branch counts are all PRCM / BSP need, with or without the list
+    eng.set_mode(abi.STUBS_EXACT, F | abi.F_IGNORE_STUB_PRIOR)
+    by_counts = eng.eval(want_rates=True, want_wspikes=True)
+    ax = dict(a)
+    ax["stubs"] = stubs_from_counts(a, 3)
+    ref = run_oracle(ax, F | abi.F_IGNORE_STUB_PRIOR, abi.STUBS_EXACT)
+    assert_results_match(by_counts, ref, what="exact mode, caller-supplied counts")
+    eng.upload_stubs(*ax["stubs"])
+    by_list = eng.eval(want_rates=True, want_wspikes=True)
+    for k in ("out", "rates", "wspikes"):
+        assert np.array_equal(by_counts[k], by_list[k], equal_nan=True), k
+    # ... and with the list the full density is available
+    eng.set_mode(abi.STUBS_EXACT, F)
+    assert_results_match(eng.eval(want_rates=True, want_wspikes=True), run_oracle(ax, F, abi.STUBS_EXACT), what="exact mode")
+    eng.close()
+
+
+def test_exact_mode_device_bound_lists():
+    import torch
+    from helpers import stubs_from_counts
+    b = synthetic.make_batch("C3", 300, 150)
+    a = host_arrays(b)
+    a["stubs"] = stubs_from_counts(a, 9)
+    ref = run_oracle(a, F, abi.STUBS_EXACT, rates=False)["out"]
+    d = b.to("cuda")
+    sp, sb, st = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in a["stubs"])
+    eng = GsmEngine()
+    eng.set_mode(abi.STUBS_EXACT, F)
+    eng.bind_batch(d)
+    eng.bind_stubs(sp, sb, st)
+    out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device="cuda")
+    eng.eval_device(out)
+    eng.sync()
+    assert_close(out.cpu().numpy(), ref, what="exact mode, device-bound")
+    eng.close()
+
+
+def test_two_handles_on_two_threads_give_identical_rows():
+    """one handle per chain, handles usable from any thread, no process-global state.  Two handles with trees of
+    different sizes (different launch configurations and shared-memory sizes) evaluate concurrently, many times."""
+    import threading
+    ba, bb = synthetic.make_batch("C4", 600, 700, seed=5), synthetic.make_batch("C3", 900, 90, seed=6)
+    aa, ab = host_arrays(ba), host_arrays(bb)
+    ref_a, ref_b = run_capi(aa, ba.flags, ba.stub_mode), run_capi(ab, bb.flags, bb.stub_mode)
+    errors = []
+
+    def work(a, b, ref, reps):
+        try:
+            eng = GsmEngine(max_trees=b.n_trees, max_nodes=b.n_nodes)
+            for _ in range(reps):
+                got = run_capi(a, b.flags, b.stub_mode, engine=eng)
+                for k in ("out", "rates", "wspikes"):
+                    if not np.array_equal(got[k], ref[k], equal_nan=True):
+                        errors.append(k)
+            eng.close()
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(aa, ba, ref_a, 12)), threading.Thread(target=work, args=(ab, bb, ref_b, 12)),
+          threading.Thread(target=work, args=(aa, ba, ref_a, 12))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
+def test_new_batch_needs_its_own_parameters():
+    """gsm_upload_trees starts a new batch: per-tree parameters of the previous one are not silently reused."""
+    b = synthetic.make_batch("C2", 8, 20)
+    a = host_arrays(b)
+    eng = GsmEngine(max_trees=16, max_nodes=b.n_nodes)
+    run_capi(a, b.flags, b.stub_mode, engine=eng)
+    eng.upload_trees(np.concatenate([a["height"], a["height"]]), np.concatenate([a["parent"], a["parent"]]))
+    eng.upload_branch_params(np.concatenate([a["rate"]] * 2), np.concatenate([a["spike"]] * 2), np.concatenate([a["nstubs"]] * 2))
+    with pytest.raises(GsmError) as ei:
+        eng.eval()
+    assert ei.value.code == abi.E_STATE
+    eng.close()
+
+
+def test_nonpositive_node_counts_in_a_ragged_batch():
+    """node_count <= 0 gives a NaN row and does not disturb the trees evaluated after it (redo list of the lean path)."""
+    b = synthetic.make_batch("C3", 64, 30)
+    a = host_arrays(b)
+    nc = np.full(64, b.n_nodes, np.int32)
+    nc[::5] = 0
+    nc[3] = -2
+    a["spike"][1::5, 2] = -1.0                       # invalid states next to them: handed to the generic path as well
+    ref = run_oracle(a, b.flags, b.stub_mode, node_count=nc)
+    got = run_capi(a, b.flags, b.stub_mode, node_count=nc)
+    assert np.all(np.isnan(got["out"][nc <= 0]))
+    ok = nc > 0
+    assert_close(got["out"][ok], ref["out"][ok], what="rows next to empty trees")

@@ -30,15 +30,15 @@ def test_proposals_match_oracle_and_full_reevaluation(kind, T, n, P, hyper):
     assert np.array_equal(got, full, equal_nan=True)
 
 
-def test_proposals_chunked_and_resident_batch_untouched(monkeypatch):
+def test_proposals_chunked_and_resident_batch_untouched():
     b = synthetic.make_batch("C3", 16, 100)
     a = host_arrays(b)
     pr = synthetic.make_proposals(a, 500)
     eng = _engine_with(a, b)
     before = eng.eval()["out"]
     one = eng.eval_dirty(**pr)
-    monkeypatch.setenv("GSM_HOST_CHUNK_MB", "1")        # ~160 proposals per chunk
     eng2 = _engine_with(a, b)
+    eng2.set_option("host_chunk_mb", 1)                  # ~160 proposals per chunk
     many = eng2.eval_dirty(**pr)
     assert np.array_equal(one, many, equal_nan=True)
     assert np.array_equal(eng.eval()["out"], before, equal_nan=True)      # proposals do not modify the resident batch

@@ -18,7 +18,7 @@ out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 ref = None
 for blk, minb in cfgs:
-    os.environ["GSM_BLOCK"], os.environ["GSM_MINB"] = str(blk), str(minb)
+    eng.set_option("block", blk); eng.set_option("minb", minb)
     for _ in range(3): eng.eval_device(out, None, None, st.cuda_stream)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
