@@ -106,6 +106,32 @@ class ClockSampler(threading.Thread):
                 "samples": len(vals)}
 
 
+def csrc_sha():
+    """hash of the kernel sources (the counters file under profiles/ is stamped with the hash it was captured from)"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "gammaspikemodel_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".inc")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def kernel_counters(workload):
+    """ncu counters of the dominant kernel captured on this workload (profiles/kernel_counters.json, written by
+    tools/ncu_counters.py); `stale` says whether the kernel sources have changed since the capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+            kc = json.load(f)
+    except Exception:
+        return None
+    if kc.get("workload") != workload:
+        return None
+    kc["stale"] = kc.get("csrc_sha") != csrc_sha()
+    return kc
+
+
 def host_threads():
     """host cores this process may use (the CPU arm runs OpenMP over trees on all of them)"""
     try:
@@ -182,6 +208,62 @@ def run_reference(args, rank):
     emit(line)
 
 
+def run_extras(dev, device_index, peak_gbs):
+    """The other BASELINE configs on this GPU, each timed with CUDA events on its launch stream after 3 warm-up launches
+    (inputs resident in HBM), every one guarded so that a failure here cannot take the headline line down."""
+    import torch
+    from gammaspikemodel_b200 import GsmEngine, abi, synthetic
+    res = []
+
+    def resident(name, kind, trees, taxa, mode=None, flags=None, steps=10, note=""):
+        try:
+            b = synthetic.make_batch_chunked(kind, trees, taxa, seed=synthetic.SEEDS[kind], device=dev, chunk=31250)
+            e = GsmEngine(device=device_index)
+            e.set_mode(b.stub_mode if mode is None else mode, b.flags if flags is None else flags)
+            e.bind_batch(b)
+            out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    e.eval_device(out, None, None, st.cuda_stream)
+                st.synchronize()
+                l0 = e.launch_count
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(steps):
+                    e.eval_device(out, None, None, st.cuda_stream)
+                e1.record(st)
+                st.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            br = b.n_trees * b.n_nodes
+            nbytes = br * BYTES_PER_BRANCH + b.n_trees * BYTES_PER_TREE
+            res.append({"workload": name, "trees": b.n_trees, "taxa": taxa, "nodes_per_tree": b.n_nodes, "ms_per_step": ms,
+                        "value": br / ms * 1e3, "unit": UNIT, "hbm_gbs": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / peak_gbs,
+                        "launches_per_step": (e.launch_count - l0) // steps, "finite_frac": float(torch.isfinite(out[:, 0]).double().mean()),
+                        "l2": "inputs (%.2f GB) %s L2" % (nbytes / 1e9, "larger than" if nbytes > 256e6 else "fit"), "note": note})
+            e.close()
+            del b, out
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            res.append({"workload": name, "error": repr(ex)})
+
+    resident("BASELINE config 3: 100k trees x 1,000 taxa, FBDWS, sampled ancestors, rho<1, indicator per state", "C3", 100_000, 1000)
+    resident("BASELINE config 2: 10k trees x 200 taxa, BDWS, spikes on", "C2", 10_000, 200, steps=20)
+    resident("mixture-mode spike prior (Stubs nostub mode, BSP:102-172; the wiring of both BEAUti templates): 20k trees x 1,000 taxa",
+             "C3", 20_000, 1000, mode=abi.STUBS_NOSTUB, steps=5, note="fp64-bound: Poisson x Gamma mixture over the stub count of every branch")
+    try:
+        import tools.bench_proposals as bp
+        r = bp.run(64, 4096, 500, reps=5, device=device_index)
+        r["unit"] = "proposals/s"
+        r["value"] = r["proposals_per_s"]
+        r["note"] = ("BASELINE config 5 through gsm_eval_dirty: host CSR arrays (pinned) in, result rows out, wall clock of the "
+                     "whole call incl. H2D / D2H; incremental O(dirty) path + full path for scalers / hyper-parameter moves")
+        res.append(r)
+    except Exception as ex:
+        res.append({"workload": "C5", "error": repr(ex)})
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +274,7 @@ def main():
     ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (C2, C3, mixture mode, C5) timed after the headline region")
     ap.add_argument("--want-rates", action="store_true", help="also write per-branch effective rates (44 B/branch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
@@ -276,6 +359,8 @@ def main():
                 free_ev[i].record(cstream)
         return out_b[i]
 
+    gather_note = ("nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the next steps' "
+                   "kernels (three result buffers); the timed region ends after the last gather")
     chunks = 1
     for _ in range(args.warmup):
         step()
@@ -385,18 +470,40 @@ def main():
                          "(%.1f s) on 1 thread; C restatement of the Java reference (no JVM in this image)"
                          % (t_all, N, reps_all, dt_all, threads, t_one, reps_one, dt_one)}
 
+    # ---- fp64 pipe: measured DFMA peak of this GPU (micro-benchmark, outside the timed region) ----
+    fp64 = None
+    if rank == 0:
+        try:
+            fma_per_s = eng.measure_fp64_peak()
+            kc = kernel_counters(args.workload)
+            fp64 = {"peak": 2 * fma_per_s / 1e12, "unit": "TFLOP/s",
+                    "peak_source": "gsm_measure_fp64_peak: DFMA micro-benchmark on this GPU in this run (8 independent chains per thread, "
+                                   "2,048 threads per SM, best of 5); every fp64-pipe instruction counted as one FMA slot = 2 flop"}
+            if kc:
+                ipb = kc["fp64_thread_instr_per_branch"]
+                ach = 2 * ipb * branches / (kern_ms_max * 1e-3) / 1e12
+                fp64.update({"achieved": ach, "frac": ach / fp64["peak"], "fp64_instr_per_branch": ipb,
+                             "instr_per_branch": kc.get("thread_instr_per_branch"),
+                             "counters_source": kc.get("source"), "counters_csrc_sha": kc.get("csrc_sha"), "counters_stale": kc["stale"]})
+        except Exception as ex:   # the headline line must survive a failing side measurement
+            fp64 = {"error": repr(ex)}
+
+    # ---- extra workloads (rank 0, N=1): the other BASELINE configs, timed after and outside the headline region ----
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del out_b, out_rates
+        eng.close()
+        eng._keep = None
+        engs.clear()
+        del batch
+        torch.cuda.empty_cache()
+        extras = run_extras(dev, local_rank, measured_peak()[0])
+
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_bytes = branches * (BYTES_PER_BRANCH + (8 if args.want_rates else 0)) + T * BYTES_PER_TREE
         achieved = per_launch_bytes / (kern_ms_max * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)
-                if tj.get("workload") == args.workload:
-                    traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        kc = kernel_counters(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -405,18 +512,19 @@ def main():
                        "branches_per_step": world * branches, "outputs": "logP+rates" if args.want_rates else "logP",
                        "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
                        if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
-                       "gather": ("nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the "
-                                  "next steps' kernels (three result buffers); the timed region ends after the last gather")
-                       if distributed else "none (1 GPU)",
+                       "gather": gather_note if distributed else "none (1 GPU)",
                        "launches_per_step": launches // max(1, args.steps),
                        "generate_s": round(t_gen, 1), "parity_sample": parity},
             "clocks": sampler.summary(),
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "gsm_lean_kernel", "kernel_ms": kern_ms_max,
-                         "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src},
+                         "traffic": kc["dram_bytes_per_launch"] if kc else None,
+                         "traffic_source": ("%s (csrc %s%s)" % (kc.get("source"), kc.get("csrc_sha"), ", STALE: kernel sources changed since" if kc["stale"] else ", current")) if kc else None,
+                         "kernel": "gsm_lean_kernel (kernel_ms also contains gsm_post_kernel, < 2 % of the step)", "kernel_ms": kern_ms_max,
+                         "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src, "fp64": fp64},
             "cpu_baseline": cpu,
+            "extra_workloads": extras,
         }
         emit(line)
     for e in engs:

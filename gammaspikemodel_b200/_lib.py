@@ -29,7 +29,8 @@ SIGNATURES = {
     "gsm_bind_device_stubs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_eval": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsm_eval_host": (C.c_int, [_vp, _i64, _i32] + [_vp] * 11),
-    "gsm_eval_dirty": (C.c_int, [_vp, _i64] + [_vp] * 10),
+    "gsm_eval_dirty": (C.c_int, [_vp, _i64] + [_vp] * 11),
+    "gsm_last_dirty_full_count": (_i64, [_vp]),
     "gsm_stub_cdf": (C.c_int, [_vp, _i64, _i32, _vp, _i32, C.POINTER(_i32)]),
     "gsm_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gsm_host_free": (C.c_int, [_vp]),
@@ -37,6 +38,7 @@ SIGNATURES = {
     "gsm_bind_device": (C.c_int, [_vp, _i64, _i32, _i64] + [_vp] * 8),
     "gsm_eval_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "gsm_sync": (C.c_int, [_vp]),
+    "gsm_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "gsm_launch_count": (_i64, [_vp]),
 }
 

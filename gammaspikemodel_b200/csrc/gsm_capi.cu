@@ -71,6 +71,13 @@ struct gsm_handle {
     int64_t prop_cap = 0;
     GsmScratch scratch;          // lean-path scratch of the handle's own stream
     int64_t scratch_trees = 0;
+    // gsm_eval_dirty: base of the resident batch + per-call lists
+    GsmDirtyWork dirty;
+    unsigned char *dw_children = nullptr, *dw_base_rows = nullptr, *dw_base_K = nullptr;
+    int64_t dirty_trees = 0, dirty_cells = 0, dirty_props = 0, last_dirty_full = 0;
+    bool base_valid = false;
+    uint32_t base_flags = 0;
+    int32_t base_mode = 0;
     GsmLaunchCtx ctx;            // device facts, probe results, gsm_set_option overrides (nothing process-global)
     int64_t host_chunk_mb = 256; // streaming chunk of gsm_eval_host / gsm_eval_dirty (gsm_set_option "host_chunk_mb")
     std::string err;
@@ -250,6 +257,8 @@ int gsm_destroy(gsm_handle* h) {
     dfree(h->d_node_count); dfree(h->d_params); dfree(h->d_use); dfree(h->d_out); dfree(h->d_out_rates);
     dfree(h->d_out_wsp); dfree(h->d_cdf); dfree(h->d_prop);
     dfree(h->d_stub_ptr); dfree(h->d_stub_branch); dfree(h->d_stub_time); dfree(h->d_stub_counts);
+    dfree(h->dw_children); dfree(h->dw_base_rows); dfree(h->dw_base_K); dfree(h->dirty.tree_flag); dfree(h->dirty.out_base);
+    dfree(h->dirty.full_list); dfree(h->dirty.counters); dfree(h->dirty.out_all);
     free_scratch(h->scratch, h->scratch_trees);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -308,6 +317,7 @@ int gsm_upload_trees(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const doub
     // branch arrays and per-tree scalars belong to a tree upload: a new batch must bring its own
     h->have_rate = h->have_spike = h->have_nstubs = h->have_params = h->have_use = false;
     h->have_stubs = h->stub_counts_valid = false;
+    h->base_valid = false;
     h->cur = GsmBatch{};
     h->cur.n_trees = n_trees;
     h->cur.n_nodes = n_nodes;
@@ -328,6 +338,7 @@ int gsm_upload_branch_params(gsm_handle* h, const double* rate, const double* sp
     h->have_spike |= spike != nullptr;
     h->have_nstubs |= nstubs != nullptr;
     if (nstubs) h->stub_counts_valid = false;   // EXACT mode: the derived counts live in the same rows
+    h->base_valid = false;
     return GSM_OK;
 }
 
@@ -344,6 +355,7 @@ int gsm_upload_tree_params(gsm_handle* h, const double* params, const uint8_t* u
     GSM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_params = true;
     h->have_use = use_spike != nullptr;
+    h->base_valid = false;
     return GSM_OK;
 }
 
@@ -379,6 +391,7 @@ int gsm_upload_stubs(gsm_handle* h, const int64_t* stub_ptr, const int32_t* stub
     GSM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_stubs = true;
     h->stub_counts_valid = false;
+    h->base_valid = false;
     h->have_nstubs = true;   // the counts are derived from the list (resident_batch)
     return GSM_OK;
 }
@@ -563,9 +576,37 @@ int gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes, const double*
     return GSM_OK;
 }
 
+// scratch of gsm_eval_dirty: base of the resident batch (valid until the batch changes) + per-call lists
+static int ensure_dirty_work(gsm_handle* h, const GsmBatch& src, int64_t n_props) {
+    const int64_t T = src.n_trees, cells = T * src.stride;
+    if (h->dirty_trees < T || h->dirty_cells < cells) {
+        dfree(h->dw_children); dfree(h->dw_base_rows); dfree(h->dw_base_K); dfree(h->dirty.tree_flag); dfree(h->dirty.out_base);
+        h->dirty_trees = h->dirty_cells = 0;
+        h->base_valid = false;
+        GSM_CUDA(h, dalloc(&h->dw_children, cells * 8));
+        GSM_CUDA(h, dalloc(&h->dw_base_rows, T * static_cast<int64_t>(gsm_base_row_bytes())));
+        GSM_CUDA(h, dalloc(&h->dw_base_K, T * static_cast<int64_t>(gsm_base_k_bytes())));
+        GSM_CUDA(h, dalloc(&h->dirty.tree_flag, T));
+        GSM_CUDA(h, dalloc(&h->dirty.out_base, T * GSM_NOUT));
+        h->dirty.children = h->dw_children; h->dirty.base_rows = h->dw_base_rows; h->dirty.base_K = h->dw_base_K;
+        h->dirty_trees = T;
+        h->dirty_cells = cells;
+    }
+    if (h->dirty_props < n_props) {
+        dfree(h->dirty.full_list); dfree(h->dirty.out_all);
+        h->dirty_props = 0;
+        GSM_CUDA(h, dalloc(&h->dirty.full_list, n_props));
+        GSM_CUDA(h, dalloc(&h->dirty.out_all, n_props * GSM_NOUT));
+        h->dirty_props = n_props;
+    }
+    if (!h->dirty.counters) GSM_CUDA(h, dalloc(&h->dirty.counters, 2));
+    return GSM_OK;
+}
+
 int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, const int64_t* dirty_ptr,
                    const int32_t* dirty_nodes, const double* new_height, const double* new_rate, const double* new_spike,
-                   const int32_t* new_nstubs, const double* new_params, const uint8_t* new_use_spike, double* out_tree) {
+                   const int32_t* new_nstubs, const double* height_scale, const double* new_params, const uint8_t* new_use_spike,
+                   double* out_tree) {
     if (!h) return GSM_E_ARG;
     if (n_props < 0) return fail(h, GSM_E_ARG, "gsm_eval_dirty: negative n_props");
     if (n_props == 0) return GSM_OK;
@@ -579,20 +620,13 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
     const int64_t D = dirty_ptr[n_props];
     if (dirty_ptr[0] != 0 || D < 0) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_ptr must start at 0 and be non-decreasing");
     if (D > 0 && !dirty_nodes) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_nodes is NULL");
-    for (int64_t p = 0; p < n_props; p++) {
-        if (tree_of_prop[p] < 0 || tree_of_prop[p] >= src.n_trees)
-            return fail(h, GSM_E_ARG, "gsm_eval_dirty: proposal %lld refers to tree %d of %lld", (long long)p, tree_of_prop[p], (long long)src.n_trees);
-        if (dirty_ptr[p + 1] < dirty_ptr[p]) return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty_ptr decreases at proposal %lld", (long long)p);
-    }
-    for (int64_t d = 0; d < D; d++)
-        if (dirty_nodes[d] < 0 || dirty_nodes[d] >= src.n_nodes)
-            return fail(h, GSM_E_ARG, "gsm_eval_dirty: dirty node %d outside [0, %d)", dirty_nodes[d], src.n_nodes);
     GSM_CUDA(h, cudaSetDevice(h->device));
     // ---- proposal arrays -> one device buffer (16-byte aligned sections) ----
     auto al = [](int64_t v) { return (v + 15) & ~static_cast<int64_t>(15); };
     const int64_t o_tree = 0, o_ptr = al(o_tree + n_props * 4), o_nodes = al(o_ptr + (n_props + 1) * 8), o_h = al(o_nodes + D * 4),
                   o_r = al(o_h + (new_height ? D * 8 : 0)), o_s = al(o_r + (new_rate ? D * 8 : 0)), o_k = al(o_s + (new_spike ? D * 8 : 0)),
-                  o_par = al(o_k + (new_nstubs ? D * 4 : 0)), o_use = al(o_par + (new_params ? n_props * GSM_NPARAM * 8 : 0)),
+                  o_sc = al(o_k + (new_nstubs ? D * 4 : 0)), o_par = al(o_sc + (height_scale ? n_props * 8 : 0)),
+                  o_use = al(o_par + (new_params ? n_props * GSM_NPARAM * 8 : 0)),
                   total = al(o_use + (new_use_spike ? n_props : 0)) + 16;
     if (h->prop_cap < total) {
         dfree(h->d_prop);
@@ -612,9 +646,9 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
     GSM_CUDA(h, up(o_r, new_rate, D * 8));
     GSM_CUDA(h, up(o_s, new_spike, D * 8));
     GSM_CUDA(h, up(o_k, new_nstubs, D * 4));
+    GSM_CUDA(h, up(o_sc, height_scale, n_props * 8));
     GSM_CUDA(h, up(o_par, new_params, n_props * GSM_NPARAM * 8));
     GSM_CUDA(h, up(o_use, new_use_spike, n_props));
-    GSM_CUDA(h, cudaStreamSynchronize(h->stream));   // the slots' streams read this buffer
     GsmProposals pr{};
     pr.tree_of_prop = reinterpret_cast<const int32_t*>(base + o_tree);
     pr.dirty_ptr = reinterpret_cast<const int64_t*>(base + o_ptr);
@@ -623,42 +657,76 @@ int gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, 
     pr.new_rate = new_rate ? reinterpret_cast<const double*>(base + o_r) : nullptr;
     pr.new_spike = new_spike ? reinterpret_cast<const double*>(base + o_s) : nullptr;
     pr.new_nstubs = new_nstubs ? reinterpret_cast<const int32_t*>(base + o_k) : nullptr;
+    pr.height_scale = height_scale ? reinterpret_cast<const double*>(base + o_sc) : nullptr;
     pr.new_params = new_params ? reinterpret_cast<const double*>(base + o_par) : nullptr;
     pr.new_use_spike = new_use_spike ? reinterpret_cast<const uint8_t*>(base + o_use) : nullptr;
-    // ---- proposed states, chunk by chunk, through the two staging slots ----
-    const int64_t chunk_mb = h->host_chunk_mb;
-    int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (src.stride * 32));
-    chunk = std::min(chunk, n_props);
-    rc = ensure_slots(h, chunk, src.stride, false, false);
+    // ---- base of the resident batch (children table, accumulators): once per resident batch and wiring ----
+    rc = ensure_dirty_work(h, src, n_props);
     if (rc != GSM_OK) return rc;
-    chunk = std::min(h->slot_trees, n_props);
-    int64_t k = 0;
-    for (int64_t p0 = 0; p0 < n_props; p0 += chunk, ++k) {
-        const int64_t P = std::min(chunk, n_props - p0);
-        Slot& s = h->slots[k & 1];
-        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
-        GsmBatchMut dst{s.height, s.parent, s.node_count, s.rate, s.spike, s.nstubs, s.params, s.use_spike};
-        int nl = gsm_launch_patch(src, pr, p0, P, dst, s.stream);
-        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty patch launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    const bool same_batch = h->base_valid && h->base_flags == h->flags && h->base_mode == h->stub_mode && !h->external;
+    if (!same_batch) {
+        int nl = gsm_launch_dirty_base(h->ctx, src, h->dirty, h->stream);
+        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty base launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
         h->launches += nl;
-        GsmBatch b = src;
-        b.n_trees = P;
-        b.height = s.height; b.parent = s.parent; b.node_count = s.node_count;
-        b.rate = src.rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = src.nstubs ? s.nstubs : nullptr;
-        b.params = s.params; b.use_spike = s.use_spike;
-        nl = gsm_launch_eval(h->ctx, b, s.scratch, s.out, nullptr, nullptr, s.stream);
-        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
-        h->launches += nl;
-        GSM_CUDA(h, cudaMemcpyAsync(out_tree + p0 * GSM_NOUT, s.out, P * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        GSM_CUDA(h, cudaEventRecord(s.done, s.stream));
-        s.busy = true;
+        h->base_valid = true;   // device-bound batches: the caller may rewrite the arrays between calls, so never reused
+        h->base_flags = h->flags;
+        h->base_mode = h->stub_mode;
     }
-    for (Slot& s : h->slots) {
-        if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
-        s.busy = false;
+    // ---- validation, classification and the incremental evaluations: one launch ----
+    int nl = gsm_launch_dirty_delta(src, pr, n_props, h->dirty, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty delta launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    int32_t counters[2] = {0, 0};
+    GSM_CUDA(h, cudaMemcpyAsync(counters, h->dirty.counters, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));   // also: the slots' streams read the proposal buffer
+    if (counters[1])
+        return fail(h, GSM_E_ARG, "gsm_eval_dirty: a proposal refers to a tree outside the batch, a node outside [0, %d) or "
+                                  "a decreasing dirty_ptr", src.n_nodes);
+    const int64_t n_full = counters[0];
+    h->last_dirty_full = n_full;
+    // ---- the other proposals: proposed states materialised chunk by chunk through the two staging slots ----
+    if (n_full > 0) {
+        const int64_t chunk_mb = h->host_chunk_mb;
+        int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / (src.stride * 32));
+        chunk = std::min(chunk, n_full);
+        rc = ensure_slots(h, chunk, src.stride, false, false);
+        if (rc != GSM_OK) return rc;
+        chunk = std::min(h->slot_trees, n_full);
+        int64_t k = 0;
+        for (int64_t q0 = 0; q0 < n_full; q0 += chunk, ++k) {
+            const int64_t P = std::min(chunk, n_full - q0);
+            Slot& s = h->slots[k & 1];
+            if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+            GsmBatchMut dst{s.height, s.parent, s.node_count, s.rate, s.spike, s.nstubs, s.params, s.use_spike};
+            nl = gsm_launch_patch(src, pr, h->dirty, q0, P, dst, s.stream);
+            if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty patch launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+            h->launches += nl;
+            GsmBatch b = src;
+            b.n_trees = P;
+            b.height = s.height; b.parent = s.parent; b.node_count = s.node_count;
+            b.rate = src.rate ? s.rate : nullptr; b.spike = s.spike; b.nstubs = src.nstubs ? s.nstubs : nullptr;
+            b.params = s.params; b.use_spike = s.use_spike;
+            b.stub_ptr = nullptr; b.stub_branch = nullptr; b.stub_time = nullptr;
+            nl = gsm_launch_eval(h->ctx, b, s.scratch, s.out, nullptr, nullptr, s.stream);
+            if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+            h->launches += nl;
+            nl = gsm_launch_scatter_rows(s.out, h->dirty.full_list, q0, P, h->dirty.out_all, s.stream);
+            if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_eval_dirty scatter launch: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+            h->launches += nl;
+            GSM_CUDA(h, cudaEventRecord(s.done, s.stream));
+            s.busy = true;
+        }
+        for (Slot& s : h->slots) {
+            if (s.busy) GSM_CUDA(h, cudaEventSynchronize(s.done));
+            s.busy = false;
+        }
     }
+    GSM_CUDA(h, cudaMemcpyAsync(out_tree, h->dirty.out_all, n_props * GSM_NOUT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
     return GSM_OK;
 }
+
+int64_t gsm_last_dirty_full_count(const gsm_handle* h) { return h ? h->last_dirty_full : 0; }
 
 int gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t cap, int32_t* len) {
     if (!h) return GSM_E_ARG;
@@ -745,6 +813,20 @@ int gsm_sync(gsm_handle* h) {
     if (!h) return GSM_E_ARG;
     GSM_CUDA(h, cudaSetDevice(h->device));
     GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GSM_OK;
+}
+
+int gsm_measure_fp64_peak(gsm_handle* h, double* fma_per_sec) {
+    if (!h || !fma_per_sec) return GSM_E_ARG;
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    if (h->cdf_cap < 2) {
+        dfree(h->d_cdf);
+        GSM_CUDA(h, dalloc(&h->d_cdf, (int64_t)4097));
+        h->cdf_cap = 4097;
+    }
+    int nl = gsm_launch_dfma_peak(h->ctx, h->d_cdf, 5, fma_per_sec, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_measure_fp64_peak: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
     return GSM_OK;
 }
 

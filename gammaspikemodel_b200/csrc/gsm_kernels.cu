@@ -186,10 +186,21 @@ static_assert(sizeof(GsmLeanRow) == 128, "GsmLeanRow must be 128 bytes");
 // generic evaluation of one tree by one CTA (every wiring, every special value): the statement-by-statement
 // path.  Used directly for wirings outside the lean family and for the trees the lean kernel hands back.
 // ---------------------------------------------------------------------------------------------------------
+// Per-tree state kept for incremental proposal evaluation (gsm_eval_dirty): the reduced accumulators of the generic path
+// before the epilogue, the root, and whether the tree qualifies (one root, every parent in range, no invalid-state flag).
+struct __align__(16) GsmBaseRow {
+    double acc[6];                                   // GsmAcc: tree, stub, spike, rate, burst, dist
+    int32_t n_extant, n_leaf, n_da, n_extinct, bad;
+    int32_t root, n, ok;
+    int32_t pad[8];
+};
+static_assert(sizeof(GsmBaseRow) == 112, "GsmBaseRow layout");
+
 struct GsmGenericShared {
     GsmTreeConsts K;
     uint64_t mbar;
     int32_t root;
+    int32_t nroot, nbadpar;
     double red[6][16];
     int32_t redi[5][16];
 };
@@ -198,7 +209,8 @@ struct GsmGenericShared {
 template <int BLOCK, bool WANT_RATES>
 static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t parity, unsigned char* smem_raw,
                                         GsmGenericShared& sh, double* __restrict__ out_tree, double* __restrict__ out_rates,
-                                        double* __restrict__ out_wspikes) {
+                                        double* __restrict__ out_wspikes, GsmBaseRow* __restrict__ base_rows = nullptr,
+                                        GsmTreeConsts* __restrict__ base_K = nullptr) {
     constexpr int NWARP = BLOCK / 32;
     const int64_t S = b.stride;
     double* sh_h = reinterpret_cast<double*>(smem_raw);
@@ -216,6 +228,7 @@ static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
     double* orow = out_tree + t * GSM_NOUT;
     if (n <= 0) {
         if (tid < GSM_NOUT) orow[tid] = NAN;
+        if (base_rows && tid == 0) base_rows[t].ok = 0;
         return false;
     }
     const int64_t row = t * S;
@@ -223,6 +236,8 @@ static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
     // ---- phase 0 ----
     if (tid == 0) {
         sh.root = -1;
+        sh.nroot = 0;
+        sh.nbadpar = 0;
         const uint32_t bytes_h = (static_cast<uint32_t>(n) * 8u + 15u) & ~15u;
         const uint32_t bytes_p = (static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
         mbar_arrive_expect_tx(&sh.mbar, bytes_h + bytes_p);
@@ -251,8 +266,13 @@ static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
         const int32_t p = sh_par[i];
         if (static_cast<uint32_t>(p) < static_cast<uint32_t>(n)) sh_nonleaf[p] = 1;
         else {
-            if (p < 0) sh.root = i;
-            else sh_par[i] = -1;  // out-of-range parent: treated as detached (never dereferenced)
+            if (p < 0) {
+                sh.root = i;
+                if (base_rows) atomicAdd(&sh.nroot, 1);
+            } else {
+                sh_par[i] = -1;  // out-of-range parent: treated as detached (never dereferenced)
+                if (base_rows) atomicAdd(&sh.nbadpar, 1);
+            }
         }
     }
     __syncthreads();
@@ -365,6 +385,20 @@ static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
             R.n_extinct += sh.redi[3][w]; R.bad |= sh.redi[4][w];
         }
         const int32_t root = sh.root;
+        if (base_rows) {
+            GsmBaseRow br;
+            br.acc[0] = R.tree; br.acc[1] = R.stub; br.acc[2] = R.spike; br.acc[3] = R.rate; br.acc[4] = R.burst; br.acc[5] = R.dist;
+            br.n_extant = R.n_extant; br.n_leaf = R.n_leaf; br.n_da = R.n_da; br.n_extinct = R.n_extinct; br.bad = R.bad;
+            br.root = root; br.n = n;
+            bool fin = true;
+#pragma unroll
+            for (int k = 0; k < 6; k++) fin = fin && (fabs(br.acc[k]) < INFINITY);
+            br.ok = (fin && R.bad == 0 && sh.nroot == 1 && sh.nbadpar == 0 && root >= 0) ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) br.pad[k] = 0;
+            base_rows[t] = br;
+            base_K[t] = K;
+        }
         double res[GSM_NOUT];
         if (root < 0) {
 #pragma unroll
@@ -384,7 +418,9 @@ static __device__ bool gsm_generic_tree(const GsmBatch& b, int64_t t, uint32_t p
 template <int BLOCK, int MINB, bool WANT_RATES>
 __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b, double* __restrict__ out_tree,
                                                                double* __restrict__ out_rates,
-                                                               double* __restrict__ out_wspikes) {
+                                                               double* __restrict__ out_wspikes,
+                                                               GsmBaseRow* __restrict__ base_rows,
+                                                               GsmTreeConsts* __restrict__ base_K) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ GsmGenericShared sh;
     if (threadIdx.x == 0) {
@@ -392,7 +428,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_eval_kernel(const GsmBatch b,
         fence_mbar_init();
     }
     __syncthreads();
-    gsm_generic_tree<BLOCK, WANT_RATES>(b, blockIdx.x, 0u, smem_raw, sh, out_tree, out_rates, out_wspikes);
+    gsm_generic_tree<BLOCK, WANT_RATES>(b, blockIdx.x, 0u, smem_raw, sh, out_tree, out_rates, out_wspikes, base_rows, base_K);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1351,18 +1387,19 @@ cudaError_t gsm_launch_ctx_init(GsmLaunchCtx& ctx, int device) {
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_generic(GsmLaunchCtx& ctx, const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st) {
+static cudaError_t launch_generic(GsmLaunchCtx& ctx, const GsmBatch& b, double* o, double* r, double* w, cudaStream_t st,
+                                  GsmBaseRow* base_rows = nullptr, GsmTreeConsts* base_K = nullptr) {
     const size_t smem = generic_smem_bytes(b.stride);
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     cudaError_t e;
     if (r || w) {
         auto kern = gsm_eval_kernel<BLOCK, MINB, true>;
         if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w, base_rows, base_K);
     } else {
         auto kern = gsm_eval_kernel<BLOCK, MINB, false>;
         if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w);
+        kern<<<grid, BLOCK, smem, st>>>(b, o, r, w, base_rows, base_K);
     }
     return cudaGetLastError();
 }
@@ -1520,12 +1557,228 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// proposal batch (gsm_eval_dirty): one CTA per proposal copies the rows of its tree (16-byte accesses) and then
-// applies the proposal's edits
+// proposal batches (gsm_eval_dirty, BASELINE config 5)
+//
+// The reference re-evaluates every branch after every proposal (BSP:294-295, STP:836-842).  Here a proposal that edits a
+// few nodes and leaves the per-tree scalars alone is evaluated INCREMENTALLY, O(dirty): with the reduced accumulators of
+// the resident state ("base", captured once per resident batch by the generic kernel),
+//     acc(proposed) = acc(base) - sum_{j in closure} term_j(resident) + sum_{j in closure} term_j(proposed),
+// where the closure of an edited node d is d itself and, when its height changes, its two children, its parent and its
+// sibling (branch lengths, expected stub counts, sampled-ancestor / fake status: Node.isDirectAncestor / isFake look one
+// level up and down).  Both term sets are evaluated by the statement-by-statement node functions the base was built with
+// (gsm_node_pass_a / gsm_node_pass_b), so the resident terms cancel to rounding; the epilogue (gsm_finalize) then runs on
+// the updated accumulators with the proposed root height.  One warp per proposal, one lane per closure node, fixed order.
+// Everything else -- hyper-parameter / indicator moves, proposals with more than GSM_DELTA_MAX_DIRTY edited nodes (tree
+// scalers), trees whose base is not finite or not a proper tree -- is materialised and evaluated in full (gsm_patch_kernel +
+// the kernels above), so the reference's -inf / NaN behaviour is inherited there.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gsm_patch_kernel(const GsmBatch src, const GsmProposals pr, int64_t p0, const GsmBatchMut dst) {
+#define GSM_DELTA_MAX_DIRTY 6    // 5 closure candidates per edited node <= 30 lanes
+
+// children of every internal node (BEAST trees are binary; a third child marks the tree as not eligible)
+__global__ void __launch_bounds__(256) gsm_children_kernel(const GsmBatch b, int2* __restrict__ children, int32_t* __restrict__ tree_flag) {
+    const int64_t t = blockIdx.x;
+    int2* row = children + t * b.stride;
+    for (int64_t i = threadIdx.x; i < b.stride; i += blockDim.x) row[i] = make_int2(-1, -1);
+    if (threadIdx.x == 0) tree_flag[t] = 0;
+    __syncthreads();
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    const int32_t* par = b.parent + t * b.stride;
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int32_t p = par[i];
+        if (static_cast<uint32_t>(p) >= static_cast<uint32_t>(n)) continue;
+        int* slot = reinterpret_cast<int*>(row + p);
+        if (atomicCAS(slot, -1, i) != -1 && atomicCAS(slot + 1, -1, i) != -1) tree_flag[t] = 1;
+    }
+}
+
+struct GsmDirtyDev {   // device view of GsmDirtyWork
+    const int2* children;
+    const GsmBaseRow* base_rows;
+    const GsmTreeConsts* base_K;
+    const int32_t* tree_flag;
+    int32_t* full_list;
+    int32_t* counters;     // [0] proposals for the full path, [1] argument error
+    double* out_all;
+};
+
+// the two children of j in a fixed order (smaller node number first); -1 = none
+static __device__ __forceinline__ int2 delta_children(const int2* __restrict__ ch, int32_t j) {
+    int2 c = ch[j];
+    if (c.y >= 0 && c.y < c.x) { const int32_t x = c.x; c.x = c.y; c.y = x; }
+    return c;
+}
+
+// one warp per proposal
+__global__ void __launch_bounds__(128) gsm_delta_kernel(const GsmBatch b, const GsmProposals pr, int64_t n_props, const GsmDirtyDev w) {
+    __shared__ GsmTreeConsts sK[4];
+    __shared__ int32_t s_node[4][GSM_DELTA_MAX_DIRTY];
+    __shared__ double s_h[4][GSM_DELTA_MAX_DIRTY], s_r[4][GSM_DELTA_MAX_DIRTY], s_s[4][GSM_DELTA_MAX_DIRTY];
+    __shared__ int32_t s_k[4][GSM_DELTA_MAX_DIRTY];
+    __shared__ int32_t s_cand[4][32];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * 4 + wp;
+    if (p >= n_props) return;
+    const int64_t t64 = pr.tree_of_prop[p];
+    const int64_t d0 = pr.dirty_ptr[p], d1 = pr.dirty_ptr[p + 1];
+    // ---- validation (was a host loop over every CSR entry) and classification ----
+    bool arg_bad = t64 < 0 || t64 >= b.n_trees || d1 < d0;
+    const int64_t t = arg_bad ? 0 : t64;
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    if (!arg_bad) {
+        bool bad = false;
+        for (int64_t d = d0 + lane; d < d1; d += 32) {
+            const int32_t node = pr.dirty_nodes[d];
+            bad = bad || node < 0 || node >= b.n_nodes;
+        }
+        arg_bad = __any_sync(0xffffffffu, bad);
+    }
+    if (arg_bad) {
+        if (lane == 0) w.counters[1] = 1;
+        return;
+    }
+    const int64_t nd = d1 - d0;
+    const GsmBaseRow base = w.base_rows[t];
+    bool full = nd > GSM_DELTA_MAX_DIRTY || base.ok == 0 || w.tree_flag[t] != 0 || (pr.height_scale && !(pr.height_scale[p] == 1.0));
+    if (!full && pr.new_params) {   // per-tree scalars replaced: every branch term changes
+        bool diff = false;
+        if (lane < GSM_NPARAM) {
+            const double a = pr.new_params[p * GSM_NPARAM + lane], c = b.params[t * GSM_NPARAM + lane];
+            diff = !(a == c);
+        }
+        full = __any_sync(0xffffffffu, diff);
+    }
+    if (!full && pr.new_use_spike) {
+        const uint8_t cur = b.use_spike ? b.use_spike[t] : static_cast<uint8_t>(1);
+        full = (pr.new_use_spike[p] != 0) != (cur != 0);
+    }
+    const int64_t row = t * b.stride;
+    if (!full) {   // an edited node beyond the tree's own node count cannot be expressed as a delta
+        bool out = false;
+        if (lane < nd) out = pr.dirty_nodes[d0 + lane] >= n;
+        full = __any_sync(0xffffffffu, out);
+    }
+    if (full) {
+        if (lane == 0) w.full_list[atomicAdd(w.counters, 1)] = static_cast<int32_t>(p);
+        return;
+    }
+    // ---- the edits of this proposal -> shared memory ----
+    if (lane < nd) {
+        const int64_t d = d0 + lane;
+        const int32_t node = pr.dirty_nodes[d];
+        s_node[wp][lane] = node;
+        s_h[wp][lane] = pr.new_height ? pr.new_height[d] : b.height[row + node];
+        s_r[wp][lane] = (pr.new_rate && b.rate) ? pr.new_rate[d] : (b.rate ? b.rate[row + node] : 1.0);
+        s_s[wp][lane] = pr.new_spike ? pr.new_spike[d] : b.spike[row + node];
+        s_k[wp][lane] = (pr.new_nstubs && b.nstubs) ? pr.new_nstubs[d] : (b.nstubs ? b.nstubs[row + node] : 0);
+    }
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.base_K + t);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sK[wp]);
+        for (int k = lane; k < static_cast<int>(sizeof(GsmTreeConsts) / 4); k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    const GsmTreeConsts& K = sK[wp];
+    const int2* ch = w.children + row;
+    const int32_t* par = b.parent + row;
+    const int ndi = static_cast<int>(nd);
+    // patched reads of the proposed state (NEW) or plain reads of the resident state
+    auto find = [&](int32_t j) { int f = -1; for (int k = 0; k < ndi; k++) if (s_node[wp][k] == j) f = k; return f; };
+    auto H = [&](int32_t j, bool nw) { const int f = nw ? find(j) : -1; return f >= 0 ? s_h[wp][f] : b.height[row + j]; };
+    // ---- closure candidates: lane c -> edited node c / 5, role c % 5 (self, children, parent, sibling) ----
+    int32_t cand = -1;
+    if (lane < 5 * ndi) {
+        const int k = lane / 5, role = lane % 5;
+        const int32_t d = s_node[wp][k];
+        const bool moved = !(__double_as_longlong(s_h[wp][k]) == __double_as_longlong(b.height[row + d]));
+        if (role == 0) cand = d;
+        else if (moved) {
+            const int32_t pd = par[d];
+            if (role == 1) cand = delta_children(ch, d).x;
+            else if (role == 2) cand = delta_children(ch, d).y;
+            else if (role == 3) cand = pd >= 0 ? pd : -1;
+            else if (pd >= 0) {
+                const int2 c = delta_children(ch, pd);
+                cand = c.x == d ? c.y : c.x;
+            }
+        }
+    }
+    s_cand[wp][lane] = cand;
+    __syncwarp();
+    for (int k = 0; k < lane; k++)
+        if (s_cand[wp][k] == cand) cand = -1;   // each node once
+    // ---- terms of this lane's node in the resident and in the proposed state ----
+    GsmAcc A[2];
+    gsm_acc_zero(A[0]);
+    gsm_acc_zero(A[1]);
+    if (cand >= 0) {
+        const int32_t j = cand;
+        const int32_t pj = par[j];
+        const bool root = pj < 0;
+        const int2 cj = delta_children(ch, j);
+        const bool nonleaf = cj.x >= 0;
+        int2 cp = make_int2(-1, -1);
+        if (!root) cp = delta_children(ch, pj);
+#pragma unroll 1
+        for (int v = 0; v < 2; v++) {
+            const bool nw = v == 1;
+            const double h = H(j, nw);
+            const double hp = root ? h : H(pj, nw);
+            uint32_t nf = 0;
+            if (nonleaf) nf |= GSM_NF_NONLEAF;
+            if (root) nf |= GSM_NF_ROOT;
+            if (!nonleaf && !root && hp == h) nf |= GSM_NF_DA;
+            // Node.isFake: a non-leaf with a direct-ancestor child (a leaf child at the same height)
+            auto leaf_at = [&](int32_t c, double hh) { return c >= 0 && ch[c].x < 0 && H(c, nw) == hh; };
+            if (nonleaf && (leaf_at(cj.x, h) || leaf_at(cj.y, h))) nf |= GSM_NF_FAKE;
+            if (!root && (leaf_at(cp.x, hp) || leaf_at(cp.y, hp))) nf |= GSM_NF_PARENT_FAKE;
+            const double aux = gsm_node_pass_a(K, A[v], nf, h, hp);
+            double auxp = aux;
+            if (!root) auxp = K.need_aux ? gsm_log(fma(K.omc2, gsm_exp(-K.c1 * hp), K.opc2)) : 0.0;   // == gsm_node_pass_a of the parent
+            const int f = nw ? find(j) : -1;
+            const double rate = f >= 0 ? s_r[wp][f] : (b.rate ? b.rate[row + j] : 1.0);
+            const double spike = f >= 0 ? s_s[wp][f] : b.spike[row + j];
+            const int32_t nst = f >= 0 ? s_k[wp][f] : (b.nstubs ? b.nstubs[row + j] : 0);
+            gsm_node_pass_b<false>(K, g_logfact, A[v], j, n, nf, h, hp, aux, auxp, rate, spike, nst, nullptr, nullptr);
+        }
+    }
+    // ---- fixed-order reduction of (proposed - resident), update of the base accumulators, epilogue ----
+    double dv[6] = {A[1].tree - A[0].tree, A[1].stub - A[0].stub, A[1].spike - A[0].spike,
+                    A[1].rate - A[0].rate, A[1].burst - A[0].burst, A[1].dist - A[0].dist};
+    // a term that is -inf / NaN in the proposed state must survive the subtraction of a finite resident term
+#pragma unroll
+    for (int k = 0; k < 6; k++) dv[k] = warp_sum(dv[k]);
+    const int32_t c_ext = __reduce_add_sync(0xffffffffu, A[1].n_extant - A[0].n_extant),
+                  c_da = __reduce_add_sync(0xffffffffu, A[1].n_da - A[0].n_da),
+                  c_exc = __reduce_add_sync(0xffffffffu, A[1].n_extinct - A[0].n_extinct),
+                  c_bad = static_cast<int32_t>(__reduce_or_sync(0xffffffffu, static_cast<uint32_t>(A[1].bad)));
+    if (lane == 0) {
+        GsmAcc R;
+        R.tree = base.acc[0] + dv[0]; R.stub = base.acc[1] + dv[1]; R.spike = base.acc[2] + dv[2];
+        R.rate = base.acc[3] + dv[3]; R.burst = base.acc[4] + dv[4]; R.dist = base.acc[5] + dv[5];
+        R.n_extant = base.n_extant + c_ext; R.n_leaf = base.n_leaf; R.n_da = base.n_da + c_da;
+        R.n_extinct = base.n_extinct + c_exc; R.bad = c_bad;
+        const int32_t root = base.root;
+        const double T = H(root, true);
+        const int2 cr = delta_children(ch, root);
+        auto leaf_at_new = [&](int32_t c) { return c >= 0 && ch[c].x < 0 && H(c, true) == T; };
+        const bool root_fake = leaf_at_new(cr.x) || leaf_at_new(cr.y);
+        GsmTreeConsts K2 = K;
+        gsm_finish_consts(K2, T);
+        double res[GSM_NOUT];
+        gsm_finalize(K2, R, n, root_fake, res);
+        double* orow = w.out_all + p * GSM_NOUT;
+#pragma unroll
+        for (int k = 0; k < GSM_NOUT; k++) orow[k] = res[k];
+    }
+}
+
+// one CTA per proposal of the full path copies the rows of its tree (16-byte accesses) and then applies the proposal's edits
+__global__ void __launch_bounds__(256) gsm_patch_kernel(const GsmBatch src, const GsmProposals pr, const int32_t* __restrict__ list,
+                                                        const int2* __restrict__ children, int64_t q0, const GsmBatchMut dst) {
     const int64_t q = blockIdx.x;            // row of the destination batch
-    const int64_t p = p0 + q;                // proposal
+    const int64_t p = list[q0 + q];          // proposal
     const int64_t t = pr.tree_of_prop[p];
     const int64_t S = src.stride;
     const int64_t so = t * S, doff = q * S;
@@ -1557,11 +1810,26 @@ __global__ void __launch_bounds__(256) gsm_patch_kernel(const GsmBatch src, cons
     if (tid < GSM_NPARAM) dst.params[q * GSM_NPARAM + tid] = pr.new_params ? pr.new_params[p * GSM_NPARAM + tid] : src.params[t * GSM_NPARAM + tid];
     if (tid == 32) dst.use_spike[q] = pr.new_use_spike ? pr.new_use_spike[p] : (src.use_spike ? src.use_spike[t] : static_cast<uint8_t>(1));
     if (tid == 33) dst.node_count[q] = src.node_count ? src.node_count[t] : src.n_nodes;
+    const double scale = pr.height_scale ? pr.height_scale[p] : 1.0;
+    if (!(scale == 1.0)) {
+        __syncthreads();   // (uniform branch) the scaled heights overwrite row entries other threads have just copied
+        // Tree.scale(s) -> Node.scale: every internal node that is not fake (no leaf child at its own height)
+        int32_t n = src.node_count ? src.node_count[t] : src.n_nodes;
+        if (n > src.n_nodes) n = src.n_nodes;
+        const int2* ch = children + so;
+        for (int32_t i = tid; i < n; i += blockDim.x) {
+            const int2 c = ch[i];
+            if (c.x < 0) continue;
+            const double h = src.height[so + i];
+            const bool fake = (ch[c.x].x < 0 && src.height[so + c.x] == h) || (c.y >= 0 && ch[c.y].x < 0 && src.height[so + c.y] == h);
+            if (!fake) dst.height[doff + i] = h * scale;
+        }
+    }
     __syncthreads();   // the edits overwrite what this CTA has just copied
     const int64_t d0 = pr.dirty_ptr[p], d1 = pr.dirty_ptr[p + 1];
     for (int64_t d = d0 + tid; d < d1; d += blockDim.x) {
         const int32_t node = pr.dirty_nodes[d];
-        if (node < 0 || node >= src.n_nodes) continue;   // validated on the host as well
+        if (node < 0 || node >= src.n_nodes) continue;   // flagged by gsm_delta_kernel as an argument error
         if (pr.new_height) dst.height[doff + node] = pr.new_height[d];
         if (pr.new_rate && src.rate) dst.rate[doff + node] = pr.new_rate[d];
         if (pr.new_spike) dst.spike[doff + node] = pr.new_spike[d];
@@ -1569,10 +1837,69 @@ __global__ void __launch_bounds__(256) gsm_patch_kernel(const GsmBatch src, cons
     }
 }
 
-int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, int64_t count, const GsmBatchMut& dst,
+// result rows of a chunk of the full path -> their proposals' rows
+__global__ void gsm_scatter_rows_kernel(const double* __restrict__ rows, const int32_t* __restrict__ list, int64_t q0, int64_t count,
+                                        double* __restrict__ out_all) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count * GSM_NOUT) return;
+    const int64_t q = i / GSM_NOUT, k = i % GSM_NOUT;
+    out_all[static_cast<int64_t>(list[q0 + q]) * GSM_NOUT + k] = rows[i];
+}
+
+size_t gsm_base_row_bytes() { return sizeof(GsmBaseRow); }
+size_t gsm_base_k_bytes() { return sizeof(GsmTreeConsts); }
+
+static GsmDirtyDev dirty_dev(const GsmDirtyWork& w) {
+    GsmDirtyDev d;
+    d.children = reinterpret_cast<const int2*>(w.children);
+    d.base_rows = reinterpret_cast<const GsmBaseRow*>(w.base_rows);
+    d.base_K = reinterpret_cast<const GsmTreeConsts*>(w.base_K);
+    d.tree_flag = w.tree_flag;
+    d.full_list = w.full_list;
+    d.counters = w.counters;
+    d.out_all = w.out_all;
+    return d;
+}
+
+// base of the resident batch: children table + accumulators of every tree (generic kernel, result rows to w.out_base)
+int gsm_launch_dirty_base(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmDirtyWork& w, cudaStream_t stream) {
+    if (b.n_trees <= 0) return 0;
+    gsm_children_kernel<<<static_cast<unsigned>(b.n_trees), 256, 0, stream>>>(b, reinterpret_cast<int2*>(w.children), w.tree_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    GsmBaseRow* rows = reinterpret_cast<GsmBaseRow*>(w.base_rows);
+    GsmTreeConsts* Ks = reinterpret_cast<GsmTreeConsts*>(w.base_K);
+    if (b.n_nodes <= 512) e = launch_generic<128, 6>(ctx, b, w.out_base, nullptr, nullptr, stream, rows, Ks);
+    else if (b.n_nodes <= 2048) e = launch_generic<256, 3>(ctx, b, w.out_base, nullptr, nullptr, stream, rows, Ks);
+    else e = launch_generic<384, 2>(ctx, b, w.out_base, nullptr, nullptr, stream, rows, Ks);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 2;
+}
+
+// validation + classification + the incremental evaluation of every eligible proposal
+int gsm_launch_dirty_delta(const GsmBatch& b, const GsmProposals& pr, int64_t n_props, const GsmDirtyWork& w, cudaStream_t stream) {
+    if (n_props <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(w.counters, 0, 2 * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    gsm_delta_kernel<<<static_cast<unsigned>((n_props + 3) / 4), 128, 0, stream>>>(b, pr, n_props, dirty_dev(w));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}
+
+int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, const GsmDirtyWork& w, int64_t q0, int64_t count, const GsmBatchMut& dst,
                      cudaStream_t stream) {
     if (count <= 0) return 0;
-    gsm_patch_kernel<<<static_cast<unsigned>(count), 256, 0, stream>>>(src, pr, p0, dst);
+    gsm_patch_kernel<<<static_cast<unsigned>(count), 256, 0, stream>>>(src, pr, w.full_list, reinterpret_cast<const int2*>(w.children), q0, dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    return 1;
+}
+
+int gsm_launch_scatter_rows(const double* d_rows, const int32_t* d_list, int64_t q0, int64_t count, double* d_out_all, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    const int64_t n = count * GSM_NOUT;
+    gsm_scatter_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(d_rows, d_list, q0, count, d_out_all);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     return 1;
@@ -1599,6 +1926,50 @@ int gsm_launch_stub_counts(const GsmBatch& b, int32_t* d_counts, cudaStream_t st
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp64 pipe micro-benchmark (bench.py: the denominator of roofline.fp64): eight independent DFMA chains per thread,
+// 2,048 resident threads per SM.  Returns thread-level fused multiply-adds per second (best of `reps` launches).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 8) gsm_dfma_peak_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123456.789) out[0] = s;   // keeps the chains alive; practically never true
+}
+
+int gsm_launch_dfma_peak(const GsmLaunchCtx& ctx, double* d_scratch, int reps, double* fma_per_sec, cudaStream_t stream) {
+    const int iters = 2000;
+    const dim3 grid(static_cast<unsigned>(ctx.sm_count * 8));
+    cudaEvent_t e0, e1;
+    cudaError_t e;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return -static_cast<int>(e);
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return -static_cast<int>(e); }
+    double best_ms = 1e30;
+    int launches = 0;
+    for (int r = 0; r < reps + 1; r++) {   // first launch = warm-up
+        cudaEventRecord(e0, stream);
+        gsm_dfma_peak_kernel<<<grid, 256, 0, stream>>>(d_scratch, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, stream);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        launches++;
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    *fma_per_sec = static_cast<double>(grid.x) * 256.0 * iters * 128.0 / (best_ms * 1e-3);
+    return launches;
 }
 
 int gsm_launch_stub_cdf(const GsmBatch& b, int64_t tree, int32_t node, double* d_cdf, int32_t cap, int32_t* d_len,

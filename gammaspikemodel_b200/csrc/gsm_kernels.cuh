@@ -72,6 +72,7 @@ struct GsmProposals {
     const double* new_rate;
     const double* new_spike;
     const int32_t* new_nstubs;
+    const double* height_scale;    // [P] or nullptr: Tree.scale factor of the internal non-fake nodes
     const double* new_params;      // [P][GSM_NPARAM] or nullptr
     const uint8_t* new_use_spike;  // [P] or nullptr
 };
@@ -79,12 +80,34 @@ struct GsmBatchMut {   // writable twin of GsmBatch's arrays
     double* height; int32_t* parent; int32_t* node_count; double* rate; double* spike; int32_t* nstubs; double* params;
     uint8_t* use_spike;
 };
-int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, int64_t p0, int64_t count, const GsmBatchMut& dst,
+// Device scratch of gsm_eval_dirty (all device pointers; owned by the handle):
+struct GsmDirtyWork {
+    void* children = nullptr;      // [T][stride] int2: the two children of every node (-1 = none)
+    void* base_rows = nullptr;     // [T] accumulators of the resident trees (gsm_base_row_bytes() each)
+    void* base_K = nullptr;        // [T] per-tree constants (gsm_base_k_bytes() each)
+    int32_t* tree_flag = nullptr;  // [T] 1: the tree is not binary
+    double* out_base = nullptr;    // [T][GSM_NOUT] result rows of the resident trees
+    int32_t* full_list = nullptr;  // [P] proposals that take the full path
+    int32_t* counters = nullptr;   // [2] number of entries of full_list, argument-error flag
+    double* out_all = nullptr;     // [P][GSM_NOUT] result rows of every proposal
+};
+size_t gsm_base_row_bytes();
+size_t gsm_base_k_bytes();
+// children table + accumulators of the resident batch (once per resident batch)
+int gsm_launch_dirty_base(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmDirtyWork& w, cudaStream_t stream);
+// validates every proposal (counters[1]), evaluates the eligible ones incrementally into out_all and lists the others
+int gsm_launch_dirty_delta(const GsmBatch& b, const GsmProposals& pr, int64_t n_props, const GsmDirtyWork& w, cudaStream_t stream);
+// full path: dst rows [q] = src rows [tree_of_prop[list[q0 + q]]] with that proposal's edits applied
+int gsm_launch_patch(const GsmBatch& src, const GsmProposals& pr, const GsmDirtyWork& w, int64_t q0, int64_t count, const GsmBatchMut& dst,
                      cudaStream_t stream);
+int gsm_launch_scatter_rows(const double* d_rows, const int32_t* d_list, int64_t q0, int64_t count, double* d_out_all, cudaStream_t stream);
 
 // EXACT mode: counts[t][i] = number of listed stubs of tree t on branch i (Stubs.getNStubsOnBranch, Stubs:357-364);
 // rows of `stride` int32, every entry of a row is written.
 int gsm_launch_stub_counts(const GsmBatch& b, int32_t* d_counts, cudaStream_t stream);
+
+// fp64 pipe micro-benchmark: thread-level DFMA per second of the current device (best of `reps` launches).
+int gsm_launch_dfma_peak(const GsmLaunchCtx& ctx, double* d_scratch, int reps, double* fma_per_sec, cudaStream_t stream);
 
 // Fills the device-side sum_{i=2..n} log(i) table of the current device (idempotent).
 cudaError_t gsm_init_tables();

@@ -134,7 +134,7 @@ class GsmEngine:
                                          vp(out_wspikes)))
 
     def eval_dirty(self, tree_of_prop, dirty_ptr, dirty_nodes, new_height=None, new_rate=None, new_spike=None,
-                   new_nstubs=None, new_params=None, new_use_spike=None):
+                   new_nstubs=None, height_scale=None, new_params=None, new_use_spike=None, out=None):
         """Proposal batch on the resident batch (gsm_eval_dirty): returns out [n_props][NOUT]."""
         tree_of_prop = _np(tree_of_prop, np.int32)
         P = tree_of_prop.shape[0]
@@ -145,13 +145,19 @@ class GsmEngine:
         new_rate = _np(new_rate, np.float64, (D,))
         new_spike = _np(new_spike, np.float64, (D,))
         new_nstubs = _np(new_nstubs, np.int32, (D,))
+        height_scale = _np(height_scale, np.float64, (P,))
         new_params = _np(new_params, np.float64, (P, abi.NPARAM))
         new_use_spike = _np(new_use_spike, np.uint8, (P,))
-        out = np.empty((P, abi.NOUT), np.float64)
+        if out is None:
+            out = np.empty((P, abi.NOUT), np.float64)
         self._ck(self._lib.gsm_eval_dirty(self._h, P, _p(tree_of_prop), _p(dirty_ptr), _p(dirty_nodes), _p(new_height),
-                                          _p(new_rate), _p(new_spike), _p(new_nstubs), _p(new_params), _p(new_use_spike),
-                                          _p(out)))
+                                          _p(new_rate), _p(new_spike), _p(new_nstubs), _p(height_scale), _p(new_params),
+                                          _p(new_use_spike), _p(out)))
         return out
+
+    @property
+    def last_dirty_full_count(self):
+        return int(self._lib.gsm_last_dirty_full_count(self._h))
 
     def stub_cdf(self, tree, node, cap=4096):
         buf = np.empty(cap, np.float64)
@@ -172,6 +178,12 @@ class GsmEngine:
         """Asynchronous launch on `stream` (an int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
         self._ck(self._lib.gsm_eval_device(self._h, _dp(out_tree), _dp(out_rates), _dp(out_wspikes),
                                            C.c_void_p(stream) if stream else None))
+
+    def measure_fp64_peak(self):
+        """thread-level DFMA per second of this device (micro-benchmark; the denominator of bench.py's roofline.fp64)"""
+        v = C.c_double(0.0)
+        self._ck(self._lib.gsm_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
 
     def sync(self):
         self._ck(self._lib.gsm_sync(self._h))

@@ -102,7 +102,7 @@ def _expected_stubs(h1, h0, lam, mu, psi, rho):
     return torch.nan_to_num(e, nan=0.0, posinf=0.0, neginf=0.0).clamp_(min=0.0, max=50.0)
 
 
-def make_batch(kind, n_trees, n_taxa, seed=None, device="cpu", tree_offset=0):
+def make_batch(kind, n_trees, n_taxa, seed=None, device="cpu", tree_offset=0, shared_tree=False):
     """kind: 'C2' (BDWS: psi=0, rho=1, ultrametric, spikes on), 'C3' (FBDWS: psi>0, rho<1, dated tips,
     5% sampled ancestors, indicator Bernoulli(0.5) per state), 'C4' (ultrametric; rho=1 for even trees,
     U(0.1,1) for odd trees)."""
@@ -179,6 +179,13 @@ def make_batch(kind, n_trees, n_taxa, seed=None, device="cpu", tree_offset=0):
         height[:, :n] = lh
         is_sa[:, :n] = sa
 
+    if shared_tree:   # config 5: one tree (and its tree-prior parameters) for every chain state
+        parent = parent[:1].expand(T, N).contiguous()
+        height = height[:1].expand(T, N).contiguous()
+        is_sa = is_sa[:1].expand(T, N).contiguous()
+        root_h = root_h[:1].expand(T).contiguous()
+        lam, mu, psi, rho = (x[:1].expand(T).contiguous() for x in (lam, mu, psi, rho))
+
     # ---- derived predicates (as Node.isDirectAncestor / isFake define them) ----
     par_c = parent.clamp(min=0)
     hp = height[ar, par_c]
@@ -232,6 +239,15 @@ def make_batch_chunked(kind, n_trees, n_taxa, seed=None, device="cpu", chunk=163
                  spike=cat("spike"), nstubs=cat("nstubs"), params=cat("params"), use_spike=cat("use_spike"), kind=b0.kind)
 
 
+def make_chain_states(n_chains, n_taxa, seed=None, device="cpu", kind="C2"):
+    """BASELINE config 5: ONE tree (topology, heights, tree-prior parameters) replicated to `n_chains` chain states; every
+    chain has its own branch rates, spikes, stub counts (drawn for that tree) and clock / spike hyper-parameters
+    ("one 500-taxon tree replicated to 64 chain states")."""
+    b = make_batch(kind, n_chains, n_taxa, seed=SEEDS["C5"] if seed is None else seed, device=device, shared_tree=True)
+    b.kind = "C5"
+    return b
+
+
 def make_proposals(a, n_props, seed=None, hyper=True):
     """BASELINE config 5: a batch of MCMC proposals on the host arrays `a` (dense [T][N] numpy arrays as the C ABI takes
     them), drawn from the operator mix of the reference's template (GammaSpikeClockModel.xml:80-112):
@@ -241,7 +257,8 @@ def make_proposals(a, n_props, seed=None, hyper=True):
         15 %  SpikeFlipOperator (SpikeFlipOperator.java:30-67): one spike redrawn
         20 %  StumpedTreeConstantDistanceOperator (:61-183): one internal height + the three adjacent rates
         10 %  stub count +-1 on one branch
-        10 %  StumpedTreeScaler (:63-161): every height scaled
+        10 %  StumpedTreeScaler (:63-161): Tree.scale(s) (every internal node that is not fake) through height_scale,
+              with lambda scaled down as the template's down-parameter
         10 %  hyper-parameter / indicator move (scale operators on GSMspikeShape, GSMclockSD, lambda; BitFlip on
               GSMuseSpikeModel): per-tree scalars replaced (only when hyper=True)
 
@@ -257,6 +274,7 @@ def make_proposals(a, n_props, seed=None, hyper=True):
     nodes, nh, nr, ns, nk = [], [], [], [], []
     new_params = a["params"][tree_of_prop].copy()
     new_use = a["use_spike"][tree_of_prop].copy()
+    scale = np.ones(n_props, np.float64)
     for p in range(n_props):
         t = int(tree_of_prop[p])
         h, par, rate, spike, nst = height[t], parent[t], a["rate"][t], a["spike"][t], a["nstubs"][t]
@@ -287,9 +305,9 @@ def make_proposals(a, n_props, seed=None, hyper=True):
             i = int(rng.integers(0, N - 1))
             put(i, kk=max(0, int(nst[i]) + (1 if rng.random() < 0.5 else -1)))
         elif k == 4:
-            s = float(rng.uniform(0.9, 1.1))
-            for i in range(N):
-                put(i, hh=h[i] * s)
+            scale[p] = float(rng.uniform(0.9, 1.1))
+            if hyper:
+                new_params[p, abi.P_LAMBDA] /= scale[p]
         else:
             which = int(rng.integers(0, 4))
             if which == 0:
@@ -303,7 +321,7 @@ def make_proposals(a, n_props, seed=None, hyper=True):
         ptr[p + 1] = len(nodes)
     out = dict(tree_of_prop=tree_of_prop, dirty_ptr=ptr, dirty_nodes=np.asarray(nodes, np.int32),
                new_height=np.asarray(nh, np.float64), new_rate=np.asarray(nr, np.float64),
-               new_spike=np.asarray(ns, np.float64), new_nstubs=np.asarray(nk, np.int32))
+               new_spike=np.asarray(ns, np.float64), new_nstubs=np.asarray(nk, np.int32), height_scale=scale)
     if hyper:
         out["new_params"] = new_params
         out["new_use_spike"] = new_use.astype(np.uint8)

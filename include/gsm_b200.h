@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 1
+#define GSM_ABI_VERSION 2
 
 /* ---- status codes ---- */
 #define GSM_OK             0
@@ -162,20 +162,32 @@ int  gsm_eval_host(gsm_handle* h, int64_t n_trees, int32_t n_nodes,
                    double* out_tree, double* out_rates, double* out_wspikes);
 
 /* MCMC proposal batch on the resident batch (BASELINE config 5: chains x proposals on one tree each).  The
- * reference re-evaluates all N branches after every proposal (BSP:294-295, STP:842; the proposals are the operators
+ * reference re-evaluates all N branches after every proposal (BSP:294-295, STP:836-842; the proposals are the operators
  * SpikeUpRateDown.java:23-47, SpikeFlipOperator.java:30-67, StumpedTreeConstantDistanceOperator.java:61-183,
  * StumpedTreeScaler.java:63-161, ... and BEAST's scale / bit-flip operators on the hyper-parameters).  Here proposal p
  * is "tree tree_of_prop[p] of the resident batch with the nodes dirty_nodes[dirty_ptr[p] .. dirty_ptr[p+1]) replaced"
  * (CSR; the nodes of one proposal must be distinct): new_height / new_rate / new_spike / new_nstubs hold one value per
- * CSR entry, and a NULL array leaves that quantity as it is.  new_params [n_props][GSM_NPARAM] / new_use_spike
+ * CSR entry, and a NULL array leaves that quantity as it is.  height_scale [n_props] (may be NULL) is BEAST's
+ * Tree.scale(s) as the tree scalers use it (StumpedTreeScaler.java:115; Node.scale): the height of every internal node
+ * that is not fake is multiplied by height_scale[p] before the CSR edits are applied (1.0 = no scaling), so a scale move
+ * costs 8 bytes instead of N CSR entries.  new_params [n_props][GSM_NPARAM] / new_use_spike
  * [n_props] (either may be NULL) replace the per-tree scalars: hyper-parameter and indicator moves, which dirty every
- * branch.  out_tree [n_props][GSM_NOUT] receives the result row of each proposed state, bit-identical to gsm_eval on
- * that state.  The resident batch itself is not modified (an accepted proposal is uploaded by the caller).  The
- * proposed states are materialised on the device, chunk by chunk, and run through the same kernels as gsm_eval. */
+ * branch.  out_tree [n_props][GSM_NOUT] receives the result row of each proposed state.  The resident batch itself is
+ * not modified (an accepted proposal is uploaded by the caller).
+ *   Cost is O(dirty): a proposal that edits at most 6 nodes and leaves the per-tree scalars alone is evaluated from the
+ * cached accumulators of its resident tree -- only the edited nodes, their children, parents and siblings are
+ * re-evaluated (old and new state) and the per-tree epilogue re-run; the cache is built on the first call after the
+ * resident batch changed.  All other proposals (height_scale != 1, hyper-parameter / indicator moves, trees whose resident
+ * state is invalid) are materialised on the device and evaluated in full by the kernels of gsm_eval.  Results equal
+ * gsm_eval on the proposed state to the 1e-10 tolerance of the path (the incremental sums are regrouped, so not bit for
+ * bit); tree / node indices are validated on the device (GSM_E_ARG). */
 int  gsm_eval_dirty(gsm_handle* h, int64_t n_props, const int32_t* tree_of_prop, const int64_t* dirty_ptr,
                     const int32_t* dirty_nodes, const double* new_height, const double* new_rate,
-                    const double* new_spike, const int32_t* new_nstubs, const double* new_params,
-                    const uint8_t* new_use_spike, double* out_tree);
+                    const double* new_spike, const int32_t* new_nstubs, const double* height_scale,
+                    const double* new_params, const uint8_t* new_use_spike, double* out_tree);
+
+/* Number of proposals of the last gsm_eval_dirty call that took the full (materialise + re-evaluate) path. */
+int64_t gsm_last_dirty_full_count(const gsm_handle* h);
 
 /* BranchSpikePrior.getCumulativeProbs(mu, nodeNr) (BSP:315-389) for one branch of one resident tree, with
  * mu = StumpedTreePrior.getMeanStubNumber(h_node, h_parent) (STP:876-892) as Stubs.sampleNStubsOnBranch
@@ -203,6 +215,10 @@ int  gsm_bind_device_stubs(gsm_handle* h, const int64_t* d_stub_ptr, const int32
 int  gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, double* d_out_wspikes,
                      void* cuda_stream);
 int  gsm_sync(gsm_handle* h);
+
+/* Measurement helper (bench.py, roofline.fp64): throughput of the device's fp64 pipe in thread-level fused multiply-adds
+ * per second, from a DFMA micro-benchmark (eight independent chains per thread, full occupancy, best of five launches). */
+int  gsm_measure_fp64_peak(gsm_handle* h, double* fma_per_sec);
 
 /* Number of kernels this handle has launched since creation (bench "gpu_launches"). */
 int64_t gsm_launch_count(const gsm_handle* h);

@@ -173,6 +173,17 @@ def apply_proposals(a, pr):
     b = {k: a[k][t].copy() for k in ("height", "parent", "rate", "spike", "nstubs")}
     b["params"] = pr["new_params"].copy() if pr.get("new_params") is not None else a["params"][t].copy()
     b["use_spike"] = pr["new_use_spike"].copy() if pr.get("new_use_spike") is not None else a["use_spike"][t].copy()
+    if pr.get("height_scale") is not None:                # BEAST Tree.scale: internal nodes that are not fake
+        N = b["height"].shape[1]
+        for q in np.nonzero(pr["height_scale"] != 1.0)[0]:
+            h, p = b["height"][q], b["parent"][q]
+            internal = np.zeros(N, bool)
+            internal[p[p >= 0]] = True
+            leaf_da = ~internal & (p >= 0) & (h == h[np.maximum(p, 0)])
+            fake = np.zeros(N, bool)
+            fake[p[leaf_da]] = True
+            sel = internal & ~fake
+            b["height"][q, sel] = h[sel] * pr["height_scale"][q]
     ptr = pr["dirty_ptr"]
     rows = np.repeat(np.arange(len(t)), np.diff(ptr))
     cols = pr["dirty_nodes"]
@@ -180,3 +191,21 @@ def apply_proposals(a, pr):
         if pr.get(name) is not None:
             b[key][rows, cols] = pr[name]
     return b
+
+
+def stub_term_noise(a):
+    """Rounding noise of the REFERENCE's own stub density per tree (psi == 0, rho == 1 states): the Java evaluates
+    E = I(h1) - I(h0) with I(h) = 2 (log(l e^{(l-m)h} - m) + l (T - h)) (STP:758-769), a difference of O(l T) numbers, so a
+    branch with a tiny expected stub count E and n > 0 stubs contributes a few n * ulp(I) / E of noise to n log E.  Used where
+    randomly proposed states hit such branches: the oracle (same operation order as the Java) is then itself only accurate
+    to this bound, and 50-digit arithmetic sides with the device value (tests/test_conditioning.py)."""
+    h, par, ns, prm = a["height"], a["parent"], a["nstubs"], a["params"]
+    lam, mu = prm[:, abi.P_LAMBDA:abi.P_LAMBDA + 1], prm[:, abi.P_MU:abi.P_MU + 1]
+    T = h.max(axis=1, keepdims=True)
+    hp = np.take_along_axis(h, np.maximum(par, 0), axis=1)
+    with np.errstate(all="ignore"):
+        I = lambda x: 2 * (np.log(lam * np.exp((lam - mu) * x) - mu) + lam * (T - x))
+        E = I(h) - I(hp)
+        mag = np.maximum(np.abs(I(h)), np.abs(I(hp)))
+        noise = np.where((par >= 0) & (ns > 0) & (hp > h), ns * 32 * np.spacing(mag) / np.maximum(E, 1e-300), 0.0)
+    return noise.sum(axis=1)
