@@ -543,7 +543,7 @@ __host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si,
     end += static_cast<uint32_t>(si) * 16u;
     l.ring = end;
     end += ring_bytes;
-    const uint32_t sz[3] = {(GSM_LEAN_MTAB_N + 1) * 16u, (GSM_LEAN_MAX_NST + 1) * 16u, (static_cast<uint32_t>(si) + 15u) & ~15u};
+    const uint32_t sz[3] = {(GSM_LEAN_MTAB_N + 1) * 16u, (GSM_LEAN_MAX_NST + 1) * 32u, (static_cast<uint32_t>(si) + 15u) & ~15u};
     uint32_t off[3];
     for (int k = 0; k < 3; k++) {
         if (free1 - free0 >= sz[k]) {
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double* sh_as = sh_hs + SI;
     unsigned char* sh_ring = smem_raw + lay.ring;   // 16-byte aligned
     GsmLogEntry* sh_mtab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.mtab);
-    GsmLogEntry* sh_ntab = reinterpret_cast<GsmLogEntry*>(smem_raw + lay.ntab);
+    GsmLeanN* sh_ntab = reinterpret_cast<GsmLeanN*>(smem_raw + lay.ntab);
     uint8_t* sh_fk = smem_raw + lay.fk;
     GsmTreeConsts& K = sh.K;
 
@@ -998,12 +998,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         // (BSP:97-99 with the Lanczos logGamma of commons-math; STP:567)
         const int m = tid + 1;
         const double shape = K.shape;
-        GsmLogEntry e, f;
+        GsmLogEntry e;
+        GsmLeanN f;
         e.invc = shape * m - 1;
         e.logc = gsm_log6_hi(c.t6, shape) - lean_log_gamma(c.t6, shape * m);
         sh_mtab[m] = e;
-        f.invc = e.logc;
-        f.logc = -g_logfact[m - 1];
+        f.gcon = e.logc;
+        f.nlf = -g_logfact[m - 1];
+        f.w = e.invc;
+        f.nd = static_cast<double>(m - 1);
         sh_ntab[m - 1] = f;
         if (tid == 0) {
             e.invc = -1.0;

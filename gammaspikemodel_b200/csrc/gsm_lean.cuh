@@ -211,7 +211,9 @@ GSM_HD uint32_t gsm_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 // ---- per-tree constants held in registers -----------------------------------------------------------------------
 // per-tree tables in shared memory (built by the setup warp):
 //   mtab[m]  = {shape m - 1, log(shape) - logGamma(shape m)}, m = 0..64; mtab[0] = {-1, 0}            (BSP:97-99)
-//   ntab[n]  = {log(shape) - logGamma(shape (n + 1)), -sum_{i=2..n} log i}, n = 0..63                 (BSP:97-99, STP:567)
+//   ntab[n]  = {log(shape) - logGamma(shape (n + 1)), -sum_{i=2..n} log i, shape (n + 1) - 1, (double)n}, n = 0..63
+//              (BSP:97-99, STP:567): everything a branch with n stubs needs from its count, two 16-byte loads
+struct __attribute__((aligned(16))) GsmLeanN { double gcon, nlf, w, nd; };
 struct GsmLeanC {
     // pass A
     double neg_c1, omc2, opc2, kS, c1, rho;
@@ -220,7 +222,7 @@ struct GsmLeanC {
     double shape, base, eff_mean;
     GsmT6 t6;
     const GsmLogEntry* mtab;
-    const GsmLogEntry* ntab;
+    const GsmLeanN* ntab;
     int32_t L;                 // leaves are nodes 0..L-1
     int32_t leaf_term;         // 0: none, 1: psi > 0 (STP:337-343), 2: origin / root conditioned (STP:467-474)
     bool use_counts;           // stub counts exist (COUNTS / EXACT); else getNStubsOnBranch == -1 (Stubs:348-350)
@@ -350,7 +352,7 @@ struct GsmLeanAccB {
     double lenr;       // sum len * r                                                             (SPL:44-49 / PRCM:233)
     double auxint, hint;     // sums over internal nodes of aux, h
     double auxfake, hfake;   // GENERAL: the same over fake internal nodes
-    int32_t k_mk, k_k; // sum m_i K_i, sum K_i of x_i shape: ln2/64 (shape k_mk - k_k) belongs to gam
+    int32_t k_mk, k_k; // sum (m_i - 1) K_i, sum K_i of x_i shape: ln2/64 (shape (k_mk + k_k) - k_k) belongs to gam
     int32_t k_nk;      // sum n_i (K_i + 64) of E_i / 2: ln2/64 k_nk belongs to stub
     int32_t n_extant, n_extinct, n_da, n_fake;
     uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
@@ -415,33 +417,32 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
     S.k_k += ks;
     S.spk += spike;
     if (!GENERAL && STDW) {
-        // m = n + 1: one 16-byte entry carries the Gamma constant of the spike prior and -log(n!) of the stub prior
-        const GsmLogEntry ne = c.ntab[ni];
-        const double nd = gsm_u2d((int32_t)ni);
-        const double md = nd + 1.0;
-        S.gam = fma(ys, fma(c.shape, md, -1.0), S.gam);
-        S.gamc += ne.invc;
-        S.k_mk += ((int32_t)ni + 1) * ks;
+        // m = n + 1: one 32-byte entry carries the Gamma constant and weight of the spike prior, -log(n!) of the stub prior and
+        // n as a double (no integer -> double conversions, no shape m - 1 arithmetic in the loop)
+        const GsmLeanN ne = c.ntab[ni];
+        S.gam = fma(ys, ne.w, S.gam);
+        S.gamc += ne.gcon;
+        S.k_mk += (int32_t)ni * ks;                     // sum (m - 1) K: the K themselves are in k_k
         // ---- stub density, count mode: STP:555-571 / 621-637 ----
         S.chk = gsm_umax(S.chk, gsm_chk_pos(E2));
         int32_t ke;
         const double yE = gsm_log6_y3(gsm_log6_r(c.t6, E2, ke));
-        S.stub = fma(nd, yE, S.stub);
-        S.nlf += ne.logc;
+        S.stub = fma(ne.nd, yE, S.stub);
+        S.nlf += ne.nlf;
         S.k_nk += (int32_t)ni * (ke + 64);
     } else {
         const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
         const GsmLogEntry me = c.mtab[mi];              // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
         S.gam = fma(ys, me.invc, S.gam);
         S.gamc += me.logc;
-        S.k_mk += (int32_t)mi * ks;
+        S.k_mk += ((int32_t)mi - 1) * ks;
         if (stub_term) {
             const uint32_t chkE = gsm_chk_pos(E2);
             S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
             int32_t ke;
             const double yE = gsm_log6_y3(gsm_log6_r(c.t6, E2, ke));   // finite garbage when E2 == 0 (len == 0): times n = 0
             S.stub = fma(gsm_u2d((int32_t)ni), yE, S.stub);
-            S.nlf += c.ntab[ni].logc;
+            S.nlf += c.ntab[ni].nlf;
             S.k_nk += (int32_t)ni * (ke + 64);
         }
     }
@@ -517,7 +518,7 @@ GSM_HD void gsm_lean_combine(const GsmTreeConsts& K, const GsmLeanC& c, const Gs
     o.tree = tree;
     const double l64 = GSM_LN2_64;
     o.stub = fma(l64, (double)S.k_nk, S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);         // sum n log E - log n! - E
-    o.spike = fma(l64, fma(c.shape, (double)S.k_mk, -(double)S.k_k), S.gam + S.gamc) - c.shape * S.spk;
+    o.spike = fma(l64, fma(c.shape, (double)(S.k_mk + S.k_k), -(double)S.k_k), S.gam + S.gamc) - c.shape * S.spk;
     o.rate = -K.inv_2s2 * (S.lr2 - 2 * K.m_ln * S.lr) - S.lr;                                // sum -(lr - m)^2/(2 s^2) - lr, without n m^2
     o.burst = c.eff_mean * (GENERAL ? S.spk_el : S.spk);
     o.dist = c.base * S.lenr;

@@ -224,14 +224,17 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmTreeConsts K;
     memset(&K, 0, sizeof K);
     gsm_setup_scalars(K, params, use_spike, flags, stub_mode);
-    GsmLogEntry mtab[GSM_LEAN_MTAB_N], ntab[GSM_LEAN_MAX_NST + 1];
+    GsmLogEntry mtab[GSM_LEAN_MTAB_N];
+    GsmLeanN ntab[GSM_LEAN_MAX_NST + 1];
     mtab[0].invc = -1.0;
     mtab[0].logc = 0.0;
     for (int m = 1; m < GSM_LEAN_MTAB_N; m++) {
         mtab[m].invc = K.shape * m - 1;
         mtab[m].logc = gsm_log(K.shape) - gsm_log_gamma(K.shape * m);
-        ntab[m - 1].invc = mtab[m].logc;
-        ntab[m - 1].logc = -g_logfact_host[m - 1];
+        ntab[m - 1].gcon = mtab[m].logc;
+        ntab[m - 1].nlf = -g_logfact_host[m - 1];
+        ntab[m - 1].w = mtab[m].invc;
+        ntab[m - 1].nd = (double)(m - 1);
     }
     if (!gsm_lean_consts_ok(K)) return false;
     GsmLeanC c;
