@@ -687,7 +687,7 @@ struct LeanBCtx {
 };
 
 // one node pair (i0, i0 + 1), both leaves (LEAF = 1) or both internal (LEAF = 0)
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT>
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, bool MIX>
 static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, int i0, bool on,
                                                    const double2 rr, const double2 ss, double2 h2, const int2 kk, int2 pp,
                                                    int32_t* sh_root_nroot, double2* __restrict__ orate2, double2* __restrict__ owsp2) {
@@ -743,9 +743,9 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
         gsm_lean_leaf_term<LT>(c, SA, !da1, h2.y, a2.y, e1, G1);
     }
     double er[2], ew[2];
-    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, i0, root0, pf0, fs0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
-    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW>(c, SB, i0 + 1, root1, pf1, fs1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1],
-                                                     &ew[1]);
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW, MIX>(c, SB, i0, root0, pf0, fs0, h2.x, hp0, a2.x, ap0, rr.x, ss.x, kk.x, &er[0], &ew[0]);
+    gsm_lean_b_node<GENERAL, WANT_RATES, LEAF, STDW, MIX>(c, SB, i0 + 1, root1, pf1, fs1, h2.y, hp1, a2.y, ap1, rr.y, ss.y, kk.y, &er[1],
+                                                          &ew[1]);
     if (WANT_RATES) {
         if (orate2) orate2[i0 >> 1] = make_double2(er[0], er[1]);
         if (owsp2) owsp2[i0 >> 1] = make_double2(ew[0], ew[1]);
@@ -754,7 +754,7 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
 
 // virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
 // (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi.  PAIRS node pairs per thread and chunk (pair tid + p BLOCK).
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST>
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX>
 static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
                                                      const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
                                                      int32_t* sh_root_nroot, double2* __restrict__ orate2,
@@ -803,8 +803,8 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
         for (int p = 0; p < PAIRS; p++) {
             const int ip = i0 + 2 * p * BLOCK;
             const bool on = ip >= lo && ip + 1 < hi;
-            lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT>(c, SA, SB, x, ip, on, rr[p], ss[p], h2[p], kk[p], pp[p], sh_root_nroot,
-                                                             orate2, owsp2);
+            lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT, MIX>(c, SA, SB, x, ip, on, rr[p], ss[p], h2[p], kk[p], pp[p], sh_root_nroot,
+                                                                  orate2, owsp2);
         }
         i0 += 2 * HB;
         if (++s == NST) {
@@ -816,16 +816,18 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
 
 // main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
 // chunks were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
                                                    int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
                                                    double2* __restrict__ owsp2) {
-    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
-    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
-                                                           orate2, owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
+                                                                orate2, owsp2);
 }
 
-template <int BLOCK, int MINB, bool WANT_RATES>
+// MIXK: the mixture-mode spike prior (BSP:102-172) is a kernel of its own, so that its body does not weigh on the register
+// allocation of the known-n kernel.
+template <int BLOCK, int MINB, bool WANT_RATES, bool MIXK>
 __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b, GsmLeanRow* __restrict__ rows,
                                                                int32_t* __restrict__ redo_count,
                                                                int32_t* __restrict__ redo_count_next,
@@ -972,10 +974,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     }
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
+    if (c.mix != MIXK) {   // cannot happen with launch_lean: the kernel flavour follows the wiring
+        drain();
+        if (tid == 0) lean_redo(redo_count, redo_list, rows, t);
+        return;
+    }
     c.t6.log_ar = smem_u32(sh_logtab) | (static_cast<uint32_t>(lane & 15) * 8u);
     c.t6.exp_ar = smem_u32(sh_exptab) | (static_cast<uint32_t>(lane & 7) * 8u);
     c.mtab = sh_mtab;
     c.ntab = sh_ntab;
+    c.mixtab = reinterpret_cast<const GsmLogEntry*>(sh_ntab);   // mixture mode has no stub counts: the two tables share the space
     // shared-window addresses of the internal arrays, biased so that node i is at + i * 8
     LeanBCtx x;
     x.a_hs = smem_u32(sh_hs) - static_cast<uint32_t>(L4) * 8u;
@@ -1003,11 +1011,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         e.invc = shape * m - 1;
         e.logc = gsm_log6_hi(c.t6, shape) - lean_log_gamma(c.t6, shape * m);
         sh_mtab[m] = e;
-        f.gcon = e.logc;
-        f.nlf = -g_logfact[m - 1];
-        f.w = e.invc;
-        f.nd = static_cast<double>(m - 1);
-        sh_ntab[m - 1] = f;
+        if (!MIXK) {
+            f.gcon = e.logc;
+            f.nlf = -g_logfact[m - 1];
+            f.w = e.invc;
+            f.nd = static_cast<double>(m - 1);
+            sh_ntab[m - 1] = f;
+        } else {
+            // g[m] = Gamma(shape m) / Gamma(shape (m + 1)); [m - 1] = {g[m] / m, 1 / m}, [64 + m] = {g[m] / (m + 1), 1 / (m + 1)}
+            const double lg_m = gsm_log6_hi(c.t6, shape) - e.logc;   // logGamma(shape m)
+            const double g = gsm_exp6(c.t6, lg_m - lean_log_gamma(c.t6, shape * (m + 1)));
+            GsmLogEntry* mt = reinterpret_cast<GsmLogEntry*>(sh_ntab);
+            GsmLogEntry r;
+            r.logc = lean_rcp(static_cast<double>(m));
+            r.invc = g * r.logc;
+            mt[m - 1] = r;
+            if (m < GSM_LEAN_MAX_NST) {
+                r.logc = lean_rcp(static_cast<double>(m + 1));
+                r.invc = g * r.logc;
+                mt[GSM_LEAN_MAX_NST + 1 + m] = r;
+            }
+            if (tid == 0) {   // [64 + 0]: only its 1 / (k + 1) is used (the k = 0 term of a fake node's child is zero)
+                r.logc = 1.0;
+                r.invc = 0.0;
+                mt[GSM_LEAN_MAX_NST + 1] = r;
+            }
+        }
         if (tid == 0) {
             e.invc = -1.0;
             e.logc = 0.0;
@@ -1082,8 +1111,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         int32_t nst = -1;
         if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? sh.tail_i[k][1] : 0;
         double er, ew;
-        gsm_lean_b_node<true, WANT_RATES, 2, false>(c, ST, i, root, pf, fs, h, hp, aux, auxp, sh.tail_d[k][1], sh.tail_d[k][2], nst, &er,
-                                                    &ew);
+        gsm_lean_b_node<true, WANT_RATES, 2, false, MIXK>(c, ST, i, root, pf, fs, h, hp, aux, auxp, sh.tail_d[k][1], sh.tail_d[k][2], nst, &er,
+                                                          &ew);
         if (WANT_RATES) {
             if (out_rates) out_rates[row + i] = er;
             if (out_wspikes) out_wspikes[row + i] = ew;
@@ -1173,18 +1202,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
     int32_t* rn = &sh.root;   // {root, nroot}
-#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
+#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
+#define GSM_PASS_B3(G, LT) { if constexpr (MIXK) GSM_PASS_B(G, false, LT, true); else { if (stdw) GSM_PASS_B(G, true, LT, false); else GSM_PASS_B(G, false, LT, false); } }
     if (general) {
         if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
         if (!detect) __syncthreads();
-        if (c.leaf_term == 0) { if (stdw) GSM_PASS_B(true, true, 0); else GSM_PASS_B(true, false, 0); }
-        else if (c.leaf_term == 1) { if (stdw) GSM_PASS_B(true, true, 1); else GSM_PASS_B(true, false, 1); }
-        else { if (stdw) GSM_PASS_B(true, true, 2); else GSM_PASS_B(true, false, 2); }
+        if (c.leaf_term == 0) GSM_PASS_B3(true, 0)
+        else if (c.leaf_term == 1) GSM_PASS_B3(true, 1)
+        else GSM_PASS_B3(true, 2)
     } else {
-        if (c.leaf_term == 0) { if (stdw) GSM_PASS_B(false, true, 0); else GSM_PASS_B(false, false, 0); }
-        else if (c.leaf_term == 1) { if (stdw) GSM_PASS_B(false, true, 1); else GSM_PASS_B(false, false, 1); }
-        else { if (stdw) GSM_PASS_B(false, true, 2); else GSM_PASS_B(false, false, 2); }
+        if (c.leaf_term == 0) GSM_PASS_B3(false, 0)
+        else if (c.leaf_term == 1) GSM_PASS_B3(false, 1)
+        else GSM_PASS_B3(false, 2)
     }
+#undef GSM_PASS_B3
 #undef GSM_PASS_B
     GSM_WARP_T1(0);
     // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree) and, when L is odd, the
@@ -1431,8 +1462,9 @@ static cudaError_t lean_cta_bytes(GsmLaunchCtx& ctx, const GsmBatch& b, const Gs
     const int k = rates ? 1 : 0;
     if (a_dyn[k] < 0) {
         cudaError_t e;
-        if (rates) e = lean_probe(gsm_lean_kernel<BLOCK, MINB, true>, BLOCK, b, sc, st, &a_dyn[k]);
-        else e = lean_probe(gsm_lean_kernel<BLOCK, MINB, false>, BLOCK, b, sc, st, &a_dyn[k]);
+        // (the mixture kernels have the same static shared memory: one probe serves both flavours)
+        if (rates) e = lean_probe(gsm_lean_kernel<BLOCK, MINB, true, false>, BLOCK, b, sc, st, &a_dyn[k]);
+        else e = lean_probe(gsm_lean_kernel<BLOCK, MINB, false, false>, BLOCK, b, sc, st, &a_dyn[k]);
         if (e != cudaSuccess) return e;
     }
     *dyn = lean_smem_bytes(b.n_nodes, a_dyn[k], HB, NST);
@@ -1451,15 +1483,19 @@ static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmSc
     cudaError_t e;
     size_t smem = 0, all = 0;
     if ((e = lean_cta_bytes<BLOCK, MINB>(ctx, b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
-    if (r || w) {
-        auto kern = gsm_lean_kernel<BLOCK, MINB, true>;
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
-    } else {
-        auto kern = gsm_lean_kernel<BLOCK, MINB, false>;
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    const bool mixk = gsm_lean_mixture(b.flags, b.stub_mode);
+#define GSM_LAUNCH_LEAN(R, M)                                                     \
+    {                                                                             \
+        auto kern = gsm_lean_kernel<BLOCK, MINB, R, M>;                           \
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;                 \
+        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);      \
     }
+    if (r || w) {
+        if (mixk) GSM_LAUNCH_LEAN(true, true) else GSM_LAUNCH_LEAN(true, false)
+    } else {
+        if (mixk) GSM_LAUNCH_LEAN(false, true) else GSM_LAUNCH_LEAN(false, false)
+    }
+#undef GSM_LAUNCH_LEAN
     return cudaGetLastError();
 }
 

@@ -63,11 +63,14 @@ inline void gsm_lean_blob_fill(GsmLeanBlob& b) {
 }
 
 GSM_HD bool gsm_lean_wiring_ok(uint32_t flags, int32_t stub_mode) {
-    const bool stubs_spike = (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0;
-    const bool known_n = !stubs_spike || stub_mode != GSM_STUBS_NOSTUB;          // BSP:77
+    // known-n spike prior (BSP:77-100) and the Poisson mixture over the stub count (BSP:102-172, Stubs nostub mode: the
+    // wiring of both BEAUti templates) are both covered; the mixture is a flavour of the pass B body (MIX)
     // reversible-jump placement terms (STP:573-600, 639-663) are evaluated by the generic path only
     const bool rj_terms = stub_mode == GSM_STUBS_EXACT && (flags & GSM_F_STUBS_TO_TREE_PRIOR) && !(flags & GSM_F_IGNORE_STUB_PRIOR);
-    return known_n && !rj_terms && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
+    return !rj_terms && (flags & GSM_F_HAS_RATES) && !(flags & GSM_F_NO_SPIKE_DATED_TIPS);
+}
+GSM_HD bool gsm_lean_mixture(uint32_t flags, int32_t stub_mode) {   // BSP:77 false
+    return (flags & GSM_F_STUBS_TO_SPIKE_PRIOR) != 0 && stub_mode == GSM_STUBS_NOSTUB;
 }
 
 // fp64 constants that do not fit an instruction immediate live in constant memory on the device, so that the hot
@@ -223,12 +226,15 @@ struct GsmLeanC {
     GsmT6 t6;
     const GsmLogEntry* mtab;
     const GsmLeanN* ntab;
+    const GsmLogEntry* mixtab; // mixture mode (overlays ntab): [k] = {g[k+1] / (k+1), 1 / (k+1)}, [64 + k] = {g[k] / (k+1), 1 / (k+1)},
+                               // g[j] = Gamma(shape j) / Gamma(shape (j+1)), k = 0..62
     int32_t L;                 // leaves are nodes 0..L-1
     int32_t leaf_term;         // 0: none, 1: psi > 0 (STP:337-343), 2: origin / root conditioned (STP:467-474)
     bool use_counts;           // stub counts exist (COUNTS / EXACT); else getNStubsOnBranch == -1 (Stubs:348-350)
     bool s2p, s2c;             // stubs wired to the spike prior (BSP:81) / the clock model (PRCM:192-195)
     bool stub_term;            // STP:219 && count mode
     bool use_rate;             // relaxed clock (PRCM:216)
+    bool mix;                  // mixture-mode spike prior (BSP:102-172)
     bool sa_unscanned;         // the tree was not scanned for sampled ancestors (no fake flags): a direct-ancestor leaf met by
                                // a GENERAL body sends the tree to the generic path
 };
@@ -241,7 +247,9 @@ GSM_HD bool gsm_lean_consts_ok(const GsmTreeConsts& K) {
     const bool par = (K.shape > 1e-300) && (K.shape < 1e300) && (K.sigma < 1e150) && (K.base == K.base) &&
                      (K.spike_mean == K.spike_mean) && (fabs(K.kE) < INFINITY) && (fabs(K.kS) < INFINITY) &&
                      (K.psi < 700.0);   // exp(psi) overflow makes STP -inf (STP:176-178): generic path
-    return fin && par;
+    // mixture mode: g[m] = Gamma(shape m) / Gamma(shape (m + 1)) must stay inside the range of the table-driven exp
+    const bool mixok = K.spike_known_n || (K.shape <= 80.0);
+    return fin && par && mixok;
 }
 
 GSM_HD void gsm_lean_consts(const GsmTreeConsts& K, GsmLeanC& c, int32_t n) {
@@ -255,6 +263,7 @@ GSM_HD void gsm_lean_consts(const GsmTreeConsts& K, GsmLeanC& c, int32_t n) {
     c.s2c = (K.flags & GSM_F_STUBS_TO_CLOCK) != 0;
     c.stub_term = K.stub_term && K.stub_counts;
     c.use_rate = !(K.flags & GSM_F_RELAXED_FALSE);
+    c.mix = !K.spike_known_n;
     c.sa_unscanned = false;
 }
 
@@ -354,6 +363,8 @@ struct GsmLeanAccB {
     double auxfake, hfake;   // GENERAL: the same over fake internal nodes
     int32_t k_mk, k_k; // sum (m_i - 1) K_i, sum K_i of x_i shape: ln2/64 (shape (k_mk + k_k) - k_k) belongs to gam
     int32_t k_nk;      // sum n_i (K_i + 64) of E_i / 2: ln2/64 k_nk belongs to stub
+    double mix;        // MIX: sum y(S_i), S_i = the mixture sum of a branch relative to its first term   (BSP:112-151)
+    int32_t k_mix;     // ... and the K parts
     int32_t n_extant, n_extinct, n_da, n_fake;
     uint32_t chk;      // specialness of rate, spike*shape, E/2 (and, GENERAL, of impossible combinations)
     uint32_t chk_n;    // max stub count as unsigned (negative counts become huge)
@@ -362,6 +373,8 @@ struct GsmLeanAccB {
 GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
     S.gam = S.gamc = S.spk = S.spk_el = S.lr = S.lr2 = S.stub = S.nlf = S.len = S.dA = S.lenr = 0.0;
     S.auxint = S.hint = S.auxfake = S.hfake = 0.0;
+    S.mix = 0.0;
+    S.k_mix = 0;
     S.k_mk = S.k_k = S.k_nk = S.n_extant = S.n_extinct = S.n_da = S.n_fake = 0;
     S.chk = S.chk_n = S.chk_len = 0u;
 }
@@ -372,7 +385,17 @@ GSM_HD void gsm_lean_acc_b_zero(GsmLeanAccB& S) {
 //   LEAF     1: i < L, 0: i >= L (compile-time for chunks on one side of L), 2: decided here
 //   STDW     the default wiring (stub counts wired to clock model, spike prior and tree prior; relaxed clock) is
 //            compiled in; false: the wiring is read from c
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW>
+// MIX (only with STDW == false): the spike prior is the Poisson mixture over the unknown stub count (BSP:102-172).  With
+//   mu = E (expected stubs on the branch), x = spike, xs = x shape, lgc[m] = log shape - logGamma(shape m):
+//   branchP = sum_{k < K} Pois(k; mu) Gamma(x; shape m(k), 1/shape),  K = first k with sum_{j<k} Pois(j; mu) >= 0.999,
+//   term_k = exp(-mu - xs + (shape m - 1) log xs + lgc[m] + k log mu - log k!).  For m(k) = k + 1 (BSP:197-213)
+//   log branchP = [-mu - xs + (shape - 1) log xs + lgc[1]] + log S,  S = sum_k w_k,  w_0 = 1,
+//   w_{k+1} = w_k (mu xs^shape) g[k+1] / (k+1): one exp for xs^shape, one for Pois(0) = e^-mu, one log for S, and a
+//   multiply-add per term -- instead of two exp and a table walk per term.  Children of a fake node have m(k) = k:
+//   term_0 counts only for x == 0 (then log branchP = -mu), else log branchP = [...] + log(mu S'), S' = sum_{1<=k<K} w'_k,
+//   w'_1 = 1, w'_{k+1} = w'_k (mu xs^shape) g[k] / (k+1).  The bracket is the known-n term with m = 1 and goes through the
+//   same accumulators; -mu is recovered from the length / aux sums.
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, bool MIX = false>
 GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool root, bool parent_fake, bool fake_self, double h,
                             double hp, double aux, double auxp, double rate, double spike, int32_t nst_raw, double* out_rate,
                             double* out_wspike) {
@@ -394,7 +417,7 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
         m = root ? ns + 1 : (da ? 0 : (pf ? ns : ns + 1));
         if (!(have_len || zero)) S.chk = 0xffffffffu;                                   // negative / NaN length
         if (da && c.sa_unscanned) S.chk = 0xffffffffu;                                  // its sibling's parent_fake is unknown here
-        if (m == 0 && spike != 0.0) S.chk = 0xffffffffu;                                // BSP:86-95 -> -inf
+        if (!MIX && m == 0 && spike != 0.0) S.chk = 0xffffffffu;                        // BSP:86-95 -> -inf
         if (stub_term && !have_len && nst != 0) S.chk = 0xffffffffu;                    // STP:232-240, 558-561
     } else {
         S.chk_len = gsm_umax(S.chk_len, gsm_chk_pos(len));
@@ -408,8 +431,20 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
     S.lr += lr;
     S.lr2 = fma(lr, lr, S.lr2);
 
-    // ---- BranchSpikePrior, known stub count: BSP:69-100 ----
+    // ---- BranchSpikePrior: BSP:69-100 (known stub count) / BSP:102-172 (MIX) ----
     const double xs = spike * c.shape;
+    bool mix_sum = false, mix_pf = false;
+    if (MIX) {
+        // which spike count the terms of this branch start from: m(0) = 1, or 0 for a sampled ancestor / a child of a fake
+        // node whose only admissible spike is zero (BSP:128-135, 158-164)
+        const bool zero_m = GENERAL && (da || (pf && (!have_len || spike == 0.0)));
+        m = zero_m ? 0 : 1;
+        if (zero_m && spike != 0.0) S.chk = 0xffffffffu;     // -inf (BSP:128-135, 158-164): generic path
+        mix_sum = GENERAL ? (have_len && !zero_m) : true;   // mu > 0 and a Gamma term exists
+        mix_pf = GENERAL && pf;
+        const uint32_t chk_mu = gsm_chk_pos(E2);             // mu = 2 E2 must be a positive normal number where it is used
+        S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chk_mu);
+    }
     const double arg_s = (GENERAL && m == 0) ? 1.0 : xs;
     S.chk = gsm_umax(S.chk, gsm_chk_pos(arg_s));
     int32_t ks;
@@ -435,7 +470,7 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
         const GsmLogEntry me = c.mtab[mi];              // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
         S.gam = fma(ys, me.invc, S.gam);
         S.gamc += me.logc;
-        S.k_mk += ((int32_t)mi - 1) * ks;
+        S.k_mk += ((int32_t)mi - 1) * ks;               // (MIX: m is 0 or 1; log 1 is K = 1, y = -ln2/64 in this table)
         if (stub_term) {
             const uint32_t chkE = gsm_chk_pos(E2);
             S.chk = gsm_umax(S.chk, (GENERAL && !have_len) ? 0u : chkE);
@@ -445,6 +480,49 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
             S.nlf += c.ntab[ni].nlf;
             S.k_nk += (int32_t)ni * (ke + 64);
         }
+    }
+    if (MIX) {
+        const double mu = 2.0 * E2;
+        const double lxs = fma(gsm_k2d(ks), GSM_LK(GSM_LK_LN2_64), ys);
+        double tpow = c.shape * lxs;                       // log xs^shape
+        if (!(fabs(tpow) < 690.0) || !(mu < 690.0)) {     // outside the range of the table-driven exp: generic path
+            if (mix_sum) S.chk = 0xffffffffu;
+            tpow = 0.0;
+        }
+        const double step = mu * gsm_exp6(c.t6, tpow);     // mu xs^shape
+        double pk = gsm_exp6(c.t6, mix_sum ? -mu : 0.0);   // Pois(0; mu)
+        double cum = 0.0, w = 1.0, Ssum = 0.0;
+        int32_t k = 0;
+        if (mix_sum) {
+            if (!mix_pf) {
+                do {                                       // BSP:117-149 with m = k + 1
+                    cum += pk;
+                    Ssum += w;
+                    const GsmLogEntry r = c.mixtab[k];
+                    pk *= mu * r.logc;                     // r.logc = 1 / (k + 1)
+                    w *= step * r.invc;                    // r.invc = g[k+1] / (k + 1)
+                    k++;
+                } while (cum < GSM_MAX_CUM_SUM && k < GSM_LEAN_MAX_NST);
+            } else {
+                do {                                       // m = k: the k = 0 term is zero (x != 0)
+                    cum += pk;
+                    Ssum += (k >= 1) ? w : 0.0;
+                    const GsmLogEntry r = c.mixtab[k + GSM_LEAN_MAX_NST + 1];   // {g[k] / (k + 1), 1 / (k + 1)}
+                    pk *= mu * r.logc;
+                    w = (k >= 1) ? w * step * r.invc : 1.0;
+                    k++;
+                } while (cum < GSM_MAX_CUM_SUM && k < GSM_LEAN_MAX_NST);
+                Ssum *= mu;
+            }
+            if (!(cum >= GSM_MAX_CUM_SUM)) S.chk = 0xffffffffu;   // more than 63 terms: generic path
+        } else {
+            Ssum = 1.0;
+        }
+        S.chk = gsm_umax(S.chk, gsm_chk_pos(Ssum));        // 0 (-> log 0 = -inf, BSP:151), inf, NaN: generic path
+        int32_t kq;
+        const double yq = gsm_log6_y3(gsm_log6_r(c.t6, Ssum, kq));
+        S.mix += yq;
+        S.k_mix += kq;
     }
     S.len += len;
     S.dA += dA;
@@ -519,6 +597,7 @@ GSM_HD void gsm_lean_combine(const GsmTreeConsts& K, const GsmLeanC& c, const Gs
     const double l64 = GSM_LN2_64;
     o.stub = fma(l64, (double)S.k_nk, S.stub + S.nlf) - 2 * fma(c.kEh, S.len, S.dA);         // sum n log E - log n! - E
     o.spike = fma(l64, fma(c.shape, (double)(S.k_mk + S.k_k), -(double)S.k_k), S.gam + S.gamc) - c.shape * S.spk;
+    if (c.mix) o.spike += fma(l64, (double)S.k_mix, S.mix) - 2 * fma(c.kEh, S.len, S.dA);   // sum log S_i - sum mu_i
     o.rate = -K.inv_2s2 * (S.lr2 - 2 * K.m_ln * S.lr) - S.lr;                                // sum -(lr - m)^2/(2 s^2) - lr, without n m^2
     o.burst = c.eff_mean * (GENERAL ? S.spk_el : S.spk);
     o.dist = c.base * S.lenr;

@@ -162,7 +162,7 @@ static void init_blob() {
 
 // pass B as the kernel splits it: leaf pairs (aux of a leaf computed on the spot), internal pairs from L4 = L & ~3 on, the
 // tail (node n-1 and, when L is odd, the pair that straddles L)
-template <bool GENERAL, bool WANT, bool STDW>
+template <bool GENERAL, bool WANT, bool STDW, bool MIX>
 static void lean_b_all(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, GsmLeanAccA& STA, GsmLeanAccB& ST, int n, int32_t stub_mode,
                        const double* h, const double* aux_int /* [i - L4] */, const int32_t* par, const uint8_t* fk /* [i - L4] */,
                        const double* rate, const double* spike, const int32_t* nstubs, int* root_out, int* nroot, bool* bad,
@@ -200,9 +200,9 @@ static void lean_b_all(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, GsmL
         double* o_r = out_rates ? out_rates + i : &dr;
         double* o_w = out_wsp ? out_wsp + i : &dw;
         const bool rt = root && gen;
-        if (tail) gsm_lean_b_node<true, WANT, 2, false>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
-        else if (leafclass == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
-        else gsm_lean_b_node<GENERAL, WANT, 0, STDW>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
+        if (tail) gsm_lean_b_node<true, WANT, 2, false, MIX>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
+        else if (leafclass == 1) gsm_lean_b_node<GENERAL, WANT, 1, STDW, MIX>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
+        else gsm_lean_b_node<GENERAL, WANT, 0, STDW, MIX>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
     };
     for (int i0 = 0; i0 + 1 < L; i0 += 2) { node(i0, 1, SA, SB, false); node(i0 + 1, 1, SA, SB, false); }
     for (int i0 = L4; i0 + 1 < n - 1; i0 += 2) {
@@ -228,18 +228,34 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     GsmLeanN ntab[GSM_LEAN_MAX_NST + 1];
     mtab[0].invc = -1.0;
     mtab[0].logc = 0.0;
+    GsmLogEntry* mixtab = reinterpret_cast<GsmLogEntry*>(ntab);   // mixture mode: overlays ntab, as in the kernel
+    memset(ntab, 0, sizeof ntab);
     for (int m = 1; m < GSM_LEAN_MTAB_N; m++) {
         mtab[m].invc = K.shape * m - 1;
         mtab[m].logc = gsm_log(K.shape) - gsm_log_gamma(K.shape * m);
-        ntab[m - 1].gcon = mtab[m].logc;
-        ntab[m - 1].nlf = -g_logfact_host[m - 1];
-        ntab[m - 1].w = mtab[m].invc;
-        ntab[m - 1].nd = (double)(m - 1);
+        if (K.spike_known_n) {
+            ntab[m - 1].gcon = mtab[m].logc;
+            ntab[m - 1].nlf = -g_logfact_host[m - 1];
+            ntab[m - 1].w = mtab[m].invc;
+            ntab[m - 1].nd = (double)(m - 1);
+        } else {
+            const double g = gsm_exp(gsm_log_gamma(K.shape * m) - gsm_log_gamma(K.shape * (m + 1)));
+            mixtab[m - 1].logc = 1.0 / m;
+            mixtab[m - 1].invc = g / m;
+            if (m < GSM_LEAN_MAX_NST) {
+                mixtab[GSM_LEAN_MAX_NST + 1 + m].logc = 1.0 / (m + 1);
+                mixtab[GSM_LEAN_MAX_NST + 1 + m].invc = g / (m + 1);
+            }
+        }
+    }
+    if (!K.spike_known_n) {
+        mixtab[GSM_LEAN_MAX_NST + 1].logc = 1.0;
+        mixtab[GSM_LEAN_MAX_NST + 1].invc = 0.0;
     }
     if (!gsm_lean_consts_ok(K)) return false;
     GsmLeanC c;
     gsm_lean_consts(K, c, n);
-    c.t6.log_t = g_blob.logtab; c.t6.exp_t = g_blob.exptab; c.mtab = mtab; c.ntab = ntab;
+    c.t6.log_t = g_blob.logtab; c.t6.exp_t = g_blob.exptab; c.mtab = mtab; c.ntab = ntab; c.mixtab = mixtab;
     const uint32_t nL = (uint32_t)(n - L);
     // phase 1: sampled-ancestor scan (only where they can occur)
     const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);
@@ -268,9 +284,9 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
     const bool stdw = gsm_lean_std_wiring(c);
     int root = -1, nroot = 0;
     bool bad = false;
-#define EMU_B(G, W) lean_b_all<G, WANT, W>(c, SA, SB, STA, ST, n, stub_mode, h, aux_int.data(), par_in, fk.data(), rate, spike, ns, &root, &nroot, &bad, out_rates, out_wsp)
-    if (general) { if (stdw) EMU_B(true, true); else EMU_B(true, false); }
-    else { if (stdw) EMU_B(false, true); else EMU_B(false, false); }
+#define EMU_B(G, W, M) lean_b_all<G, WANT, W, M>(c, SA, SB, STA, ST, n, stub_mode, h, aux_int.data(), par_in, fk.data(), rate, spike, ns, &root, &nroot, &bad, out_rates, out_wsp)
+    if (general) { if (stdw) EMU_B(true, true, false); else if (c.mix) EMU_B(true, false, true); else EMU_B(true, false, false); }
+    else { if (stdw) EMU_B(false, true, false); else if (c.mix) EMU_B(false, false, true); else EMU_B(false, false, false); }
 #undef EMU_B
     GsmLean6 s6, t6;
     if (general) gsm_lean_combine<true>(K, c, SA, SB, s6);

@@ -44,7 +44,7 @@ def test_emulated_lean_path_matches_oracle(case):
 # (Sampled ancestors under psi == 0 -- "c3-psi0-*-dated" -- are not in the list: the lean kernel only scans for sampled
 # ancestors where the tree prior can generate them, psi > 0 or origin / root conditioning; elsewhere a zero-length branch
 # is caught by its length check and the tree is handed to the generic path.)
-LEAN_FULL = {"c2-default", "c3-default", "c4-default", "c3-exact-counts", "c3-strict-clock", "c3-no-indicator", "c3-ignore-tree-prior", "c3-ignore-stub-prior",
+LEAN_FULL = {"c2-default", "c3-default", "c4-default", "c2-nostub-mixture", "c3-nostub-mixture", "c4-nostub-mixture", "c3-strict-clock", "c3-no-indicator", "c3-ignore-tree-prior", "c3-ignore-stub-prior",
              "c3-origin", "c3-origin-cond-sampling", "c3-origin-cond-rho", "c3-root-cond-sampling", "c3-root-cond-rho",
              "c2-psi0-rho-lt1", "c2-psi-on-ultrametric", "ragged-node-counts"}
 
