@@ -32,6 +32,8 @@ SIGNATURES = {
     "gsm_eval_dirty": (C.c_int, [_vp, _i64] + [_vp] * 11),
     "gsm_last_dirty_full_count": (_i64, [_vp]),
     "gsm_stub_cdf": (C.c_int, [_vp, _i64, _i32, _vp, _i32, C.POINTER(_i32)]),
+    "gsm_stub_cdf_trees": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "gsm_stub_choose": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "gsm_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gsm_host_free": (C.c_int, [_vp]),
     "gsm_device_stride": (_i64, [_i32]),

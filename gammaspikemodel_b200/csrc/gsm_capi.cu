@@ -754,6 +754,96 @@ int gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t
     return GSM_OK;
 }
 
+// scratch of the log-time whole-tree calls: allocated per call (these run once per logged state, not per MCMC step)
+namespace {
+struct LogScratch {
+    int64_t *trees = nullptr, *lens = nullptr, *ptr = nullptr;
+    double *sums = nullptr, *cdf = nullptr, *u = nullptr;
+    int32_t* out = nullptr;
+    ~LogScratch() {
+        cudaFree(trees); cudaFree(lens); cudaFree(ptr); cudaFree(sums); cudaFree(cdf); cudaFree(u); cudaFree(out);
+    }
+};
+int check_sel(gsm_handle* h, const GsmBatch& b, int64_t n_sel, const int64_t* trees, const char* who) {
+    if (n_sel < 0) return fail(h, GSM_E_ARG, "%s: negative n_sel", who);
+    if (!trees && n_sel > b.n_trees) return fail(h, GSM_E_ARG, "%s: n_sel %lld exceeds the batch (%lld trees)", who, (long long)n_sel, (long long)b.n_trees);
+    if (trees)
+        for (int64_t k = 0; k < n_sel; k++)
+            if (trees[k] < 0 || trees[k] >= b.n_trees) return fail(h, GSM_E_ARG, "%s: tree %lld outside the batch", who, (long long)trees[k]);
+    return GSM_OK;
+}
+}  // namespace
+
+int gsm_stub_cdf_trees(gsm_handle* h, int64_t n_sel, const int64_t* trees, int64_t* cdf_ptr, double* cdf, int64_t cap, int64_t* needed) {
+    if (!h) return GSM_E_ARG;
+    if (!cdf_ptr || !needed || cap < 0 || (cap > 0 && !cdf)) return fail(h, GSM_E_ARG, "gsm_stub_cdf_trees: bad output arguments");
+    GsmBatch b;
+    int rc = resident_batch(h, &b);
+    if (rc != GSM_OK) return rc;
+    if ((rc = check_sel(h, b, n_sel, trees, "gsm_stub_cdf_trees")) != GSM_OK) return rc;
+    *needed = 0;
+    cdf_ptr[0] = 0;
+    if (n_sel == 0 || b.n_nodes == 0) return GSM_OK;
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t items = n_sel * b.n_nodes;
+    LogScratch sc;
+    if (trees) {
+        GSM_CUDA(h, dalloc(&sc.trees, n_sel));
+        GSM_CUDA(h, cudaMemcpyAsync(sc.trees, trees, n_sel * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    GSM_CUDA(h, dalloc(&sc.lens, items));
+    GSM_CUDA(h, dalloc(&sc.sums, items));
+    GSM_CUDA(h, dalloc(&sc.ptr, items + 1));
+    int nl = gsm_launch_stub_len(b, n_sel, sc.trees, sc.lens, sc.sums, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_stub_cdf_trees: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    nl = gsm_launch_scan(sc.lens, sc.ptr, items, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_stub_cdf_trees: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    GSM_CUDA(h, cudaMemcpyAsync(cdf_ptr, sc.ptr, (items + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    *needed = cdf_ptr[items];
+    const int64_t w = std::min(*needed, cap);
+    if (w > 0) {
+        GSM_CUDA(h, dalloc(&sc.cdf, w));
+        nl = gsm_launch_stub_fill(b, n_sel, sc.trees, sc.ptr, sc.sums, sc.cdf, w, h->stream);
+        if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_stub_cdf_trees: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+        h->launches += nl;
+        GSM_CUDA(h, cudaMemcpyAsync(cdf, sc.cdf, w * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return GSM_OK;
+}
+
+int gsm_stub_choose(gsm_handle* h, int64_t n_sel, const int64_t* trees, const double* u, int32_t* nstubs_out) {
+    if (!h) return GSM_E_ARG;
+    if (!u || !nstubs_out) return fail(h, GSM_E_ARG, "gsm_stub_choose: NULL array");
+    if (!(h->flags & GSM_F_STUBS_TO_SPIKE_PRIOR))   // Stubs.spikePrior == null: Randomizer.nextPoisson, BEAST's own algorithm (Stubs:436-441)
+        return fail(h, GSM_E_UNSUPPORTED, "gsm_stub_choose: without a BranchSpikePrior wired to the stubs the reference draws with "
+                                          "Randomizer.nextPoisson (BEAST core RNG); only the randomChoice branch is provided");
+    GsmBatch b;
+    int rc = resident_batch(h, &b);
+    if (rc != GSM_OK) return rc;
+    if ((rc = check_sel(h, b, n_sel, trees, "gsm_stub_choose")) != GSM_OK) return rc;
+    if (n_sel == 0 || b.n_nodes == 0) return GSM_OK;
+    GSM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t items = n_sel * b.n_nodes;
+    LogScratch sc;
+    if (trees) {
+        GSM_CUDA(h, dalloc(&sc.trees, n_sel));
+        GSM_CUDA(h, cudaMemcpyAsync(sc.trees, trees, n_sel * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    GSM_CUDA(h, dalloc(&sc.u, items));
+    GSM_CUDA(h, dalloc(&sc.out, items));
+    GSM_CUDA(h, cudaMemcpyAsync(sc.u, u, items * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int nl = gsm_launch_stub_choose(b, n_sel, sc.trees, sc.u, sc.out, h->stream);
+    if (nl < 0) return fail(h, GSM_E_CUDA, "gsm_stub_choose: %s", cudaGetErrorString(static_cast<cudaError_t>(-nl)));
+    h->launches += nl;
+    GSM_CUDA(h, cudaMemcpyAsync(nstubs_out, sc.out, items * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GSM_OK;
+}
+
 int gsm_host_alloc(void** out, int64_t bytes) {
     if (!out || bytes < 0) return GSM_E_ARG;
     cudaError_t e = cudaHostAlloc(out, static_cast<size_t>(bytes > 0 ? bytes : 1), cudaHostAllocDefault);

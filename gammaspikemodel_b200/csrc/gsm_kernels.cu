@@ -1361,6 +1361,194 @@ __global__ void gsm_stub_cdf_kernel(const GsmBatch b, int64_t t, int32_t node, d
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Log-time stub sampling for whole trees (Stubs.sampleNStubs / sampleNStubsOnBranch, Stubs:389-458; the tree loggers call
+// Stubs.getArrayValue for every node, Stubs:666-674): one CTA per selected tree, one thread per branch at a time.
+//   gsm_stub_walk      the loop of BranchSpikePrior.getCumulativeProbs (BSP:334-370) for one branch
+//   gsm_stub_len       pass 1: array length and normalising sum of every branch
+//   gsm_stub_fill      pass 2: the normalised cumulative arrays (BSP:374-387), CSR
+//   gsm_stub_choose    Randomizer.randomChoice(cf) for a caller-supplied uniform per branch (the RNG itself is BEAST core)
+// ---------------------------------------------------------------------------------------------------------
+struct GsmStubBranch {
+    double mu, x;
+    bool draws;   // false: root or Poisson mean 0 -> 0 stubs without a draw (Stubs:416-434)
+};
+static __device__ __forceinline__ GsmStubBranch gsm_stub_branch(const GsmBatch& b, const GsmTreeConsts& K, int64_t t, int32_t node) {
+    GsmStubBranch r;
+    const int64_t row = t * b.stride;
+    const double h = b.height[row + node];
+    const int32_t p = b.parent[row + node];
+    const double hp = p < 0 ? h : b.height[row + p];
+    r.mu = 0.0;                                                              // STP:876-878
+    if (p >= 0 && hp > h) {                                                  // STP:749-769 through aux = log G
+        const double a1 = gsm_log(fma(K.omc2, gsm_exp(-K.c1 * h), K.opc2));
+        const double a0 = gsm_log(fma(K.omc2, gsm_exp(-K.c1 * hp), K.opc2));
+        r.mu = fma(hp - h, K.kE, 2 * (a1 - a0));
+    }
+    r.x = b.spike[row + node];                                               // BSP:328
+    r.draws = p >= 0 && r.mu != 0.0;
+    return r;
+}
+// calls emit(k, branchP) for every entry of the Java list `probs`; returns its length, *psum = branchPSum
+template <typename F>
+static __device__ __forceinline__ int32_t gsm_stub_walk(const GsmTreeConsts& K, bool use_gamma, double mu, double x, double* psum, F&& emit) {
+    const double log_mu = log(mu);
+    const double xs = x * K.shape, lxs = log(xs);
+    int32_t k = 0;
+    double pcs = 0.0, sum = 0.0;
+    while (pcs < GSM_MAX_CUM_SUM && k < GSM_K_CAP) {                         // BSP:334
+        double branchP = 0.0;
+        double pl = -mu + k * log_mu;                                        // BSP:339
+        pl -= gsm_logfact(g_logfact, k);                                     // BSP:340
+        const double pReal = exp(pl);
+        if (use_gamma) {
+            const double g = gsm_gamma_logdens(K, k + 1, x, xs, lxs);        // BSP:344-350
+            if (g == -INFINITY || g != g) {
+                if (pcs > 0) break;                                          // BSP:352
+            } else {
+                branchP += exp(pl + g);                                      // BSP:355
+            }
+        } else {
+            branchP += pReal;                                                // BSP:361
+        }
+        pcs += pReal;
+        sum += branchP;
+        emit(k, branchP);
+        k++;
+    }
+    *psum = sum;
+    return k;
+}
+static __device__ __forceinline__ void gsm_stub_tree_consts(const GsmBatch& b, int64_t t, GsmTreeConsts& K) {
+    if (threadIdx.x == 0) {
+        gsm_setup_consts(K, b.params + t * GSM_NPARAM, b.use_spike ? static_cast<int32_t>(b.use_spike[t]) : 1, b.flags, b.stub_mode);
+        for (int m = 0; m <= GSM_LUT_M; m++) gsm_lut_entry(K, K.shape, m);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) gsm_stub_len_kernel(const GsmBatch b, const int64_t* __restrict__ trees, int64_t* __restrict__ lens,
+                                                           double* __restrict__ sums) {
+    __shared__ GsmTreeConsts K;
+    const int64_t t = trees ? trees[blockIdx.x] : blockIdx.x;
+    gsm_stub_tree_consts(b, t, K);
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    const bool use_gamma = (b.flags & GSM_F_BSP_HAS_INDICATOR) && K.use_spike;   // BSP:347
+    for (int32_t i = threadIdx.x; i < b.n_nodes; i += blockDim.x) {
+        int64_t len = 0;
+        double sum = 0.0;
+        if (i < n) {
+            const GsmStubBranch br = gsm_stub_branch(b, K, t, i);
+            if (br.draws) len = gsm_stub_walk(K, use_gamma, br.mu, br.x, &sum, [](int32_t, double) {});
+        }
+        lens[static_cast<int64_t>(blockIdx.x) * b.n_nodes + i] = len;
+        sums[static_cast<int64_t>(blockIdx.x) * b.n_nodes + i] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(128) gsm_stub_fill_kernel(const GsmBatch b, const int64_t* __restrict__ trees, const int64_t* __restrict__ ptr,
+                                                            const double* __restrict__ sums, double* __restrict__ cdf, int64_t cap) {
+    __shared__ GsmTreeConsts K;
+    const int64_t t = trees ? trees[blockIdx.x] : blockIdx.x;
+    gsm_stub_tree_consts(b, t, K);
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    const bool use_gamma = (b.flags & GSM_F_BSP_HAS_INDICATOR) && K.use_spike;
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t item = static_cast<int64_t>(blockIdx.x) * b.n_nodes + i;
+        const int64_t o = ptr[item];
+        if (ptr[item + 1] == o) continue;
+        const GsmStubBranch br = gsm_stub_branch(b, K, t, i);
+        const double total = sums[item];
+        double cum = 0.0, dummy;
+        gsm_stub_walk(K, use_gamma, br.mu, br.x, &dummy, [&](int32_t k, double branchP) {
+            const double pr = branchP / total;                               // BSP:374-377
+            if (o + k < cap) cdf[o + k] = pr + cum;                          // BSP:381-387
+            cum += pr;
+        });
+    }
+}
+
+// Randomizer.randomChoice(cf) (BEAST.base 2.7.7, recalled): s = 0 if U <= cf[0]; else the first s >= 1 with
+// cf[s-1] < U <= cf[s]; cf.length when no entry qualifies (e.g. a 0/0 array).
+__global__ void __launch_bounds__(128) gsm_stub_choose_kernel(const GsmBatch b, const int64_t* __restrict__ trees, const double* __restrict__ u,
+                                                              int32_t* __restrict__ out) {
+    __shared__ GsmTreeConsts K;
+    const int64_t t = trees ? trees[blockIdx.x] : blockIdx.x;
+    gsm_stub_tree_consts(b, t, K);
+    int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
+    if (n > b.n_nodes) n = b.n_nodes;
+    const bool use_gamma = (b.flags & GSM_F_BSP_HAS_INDICATOR) && K.use_spike;
+    for (int32_t i = threadIdx.x; i < b.n_nodes; i += blockDim.x) {
+        const int64_t item = static_cast<int64_t>(blockIdx.x) * b.n_nodes + i;
+        int32_t pick = 0;
+        if (b.stub_mode != GSM_STUBS_NOSTUB) pick = -1;                      // Stubs:412
+        else if (i < n) {
+            const GsmStubBranch br = gsm_stub_branch(b, K, t, i);
+            if (br.draws) {
+                double total = 0.0, dummy;
+                const int32_t len = gsm_stub_walk(K, use_gamma, br.mu, br.x, &total, [](int32_t, double) {});
+                const double U = u[item];
+                double cum = 0.0, prev = 0.0;
+                int32_t s = len;
+                gsm_stub_walk(K, use_gamma, br.mu, br.x, &dummy, [&](int32_t k, double branchP) {
+                    const double pr = branchP / total;
+                    const double cf = pr + cum;
+                    cum += pr;
+                    if (s == len && U <= cf && (k == 0 || U > prev)) s = k;
+                    prev = cf;
+                });
+                pick = s;
+            }
+        }
+        out[item] = pick;
+    }
+}
+
+int gsm_launch_stub_len(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, int64_t* d_lens, double* d_sums, cudaStream_t stream) {
+    if (n_sel <= 0) return 0;
+    gsm_stub_len_kernel<<<static_cast<unsigned>(n_sel), 128, 0, stream>>>(b, d_trees, d_lens, d_sums);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+int gsm_launch_stub_fill(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, const int64_t* d_ptr, const double* d_sums, double* d_cdf,
+                         int64_t cap, cudaStream_t stream) {
+    if (n_sel <= 0) return 0;
+    gsm_stub_fill_kernel<<<static_cast<unsigned>(n_sel), 128, 0, stream>>>(b, d_trees, d_ptr, d_sums, d_cdf, cap);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+int gsm_launch_stub_choose(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, const double* d_u, int32_t* d_out, cudaStream_t stream) {
+    if (n_sel <= 0) return 0;
+    gsm_stub_choose_kernel<<<static_cast<unsigned>(n_sel), 128, 0, stream>>>(b, d_trees, d_u, d_out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+// exclusive prefix sum of the array lengths -> CSR pointers (n + 1 entries); single CTA, log-time path
+__global__ void __launch_bounds__(1024) gsm_scan_kernel(const int64_t* __restrict__ lens, int64_t* __restrict__ ptr, int64_t n) {
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (n + 1023) / 1024, lo = tid * per, hi = lo + per < n ? lo + per : n;
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; i++) s += lens[i];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < 1024; k++) { const int64_t v = part[k]; part[k] = run; run += v; }
+        ptr[n] = run;
+    }
+    __syncthreads();
+    int64_t run = part[tid];
+    for (int64_t i = lo; i < hi; i++) { ptr[i] = run; run += lens[i]; }
+}
+int gsm_launch_scan(const int64_t* d_lens, int64_t* d_ptr, int64_t n, cudaStream_t stream) {
+    gsm_scan_kernel<<<1, 1024, 0, stream>>>(d_lens, d_ptr, n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------------------
 cudaError_t gsm_init_tables() {

@@ -106,6 +106,14 @@ int gsm_launch_scatter_rows(const double* d_rows, const int32_t* d_list, int64_t
 // rows of `stride` int32, every entry of a row is written.
 int gsm_launch_stub_counts(const GsmBatch& b, int32_t* d_counts, cudaStream_t stream);
 
+// Log-time stub sampling for whole trees (Stubs:389-458, BSP:315-389).  d_trees: the selected trees (nullptr = trees 0 .. n_sel-1);
+// items are (selected tree, node) in tree-major order, n_sel * n_nodes of them.
+int gsm_launch_stub_len(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, int64_t* d_lens, double* d_sums, cudaStream_t stream);
+int gsm_launch_scan(const int64_t* d_lens, int64_t* d_ptr, int64_t n, cudaStream_t stream);
+int gsm_launch_stub_fill(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, const int64_t* d_ptr, const double* d_sums, double* d_cdf,
+                         int64_t cap, cudaStream_t stream);
+int gsm_launch_stub_choose(const GsmBatch& b, int64_t n_sel, const int64_t* d_trees, const double* d_u, int32_t* d_out, cudaStream_t stream);
+
 // fp64 pipe micro-benchmark: thread-level DFMA per second of the current device (best of `reps` launches).
 int gsm_launch_dfma_peak(const GsmLaunchCtx& ctx, double* d_scratch, int reps, double* fma_per_sec, cudaStream_t stream);
 

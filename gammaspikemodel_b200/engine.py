@@ -165,6 +165,28 @@ class GsmEngine:
         self._ck(self._lib.gsm_stub_cdf(self._h, int(tree), int(node), _p(buf), cap, C.byref(n)))
         return buf[: min(n.value, cap)].copy(), n.value
 
+    def stub_cdf_trees(self, trees=None, n_sel=None):
+        """getCumulativeProbs of every branch of the selected trees: returns (cdf_ptr [n_sel * N + 1], cdf)"""
+        trees = _np(trees, np.int64)
+        n_sel = len(trees) if trees is not None else (self.n_trees if n_sel is None else int(n_sel))
+        ptr = np.zeros(n_sel * self.n_nodes + 1, np.int64)
+        need = C.c_int64(0)
+        cdf = np.empty(max(1, 16 * n_sel * self.n_nodes), np.float64)
+        self._ck(self._lib.gsm_stub_cdf_trees(self._h, n_sel, _p(trees), _p(ptr), _p(cdf), cdf.size, C.byref(need)))
+        if need.value > cdf.size:
+            cdf = np.empty(need.value, np.float64)
+            self._ck(self._lib.gsm_stub_cdf_trees(self._h, n_sel, _p(trees), _p(ptr), _p(cdf), cdf.size, C.byref(need)))
+        return ptr, cdf[: need.value].copy()
+
+    def stub_choose(self, u, trees=None):
+        """Stubs.sampleNStubsOnBranch for every branch of the selected trees given uniforms u [n_sel][N]"""
+        u = _np(u, np.float64)
+        n_sel = u.shape[0]
+        trees = _np(trees, np.int64, (n_sel,))
+        out = np.empty((n_sel, self.n_nodes), np.int32)
+        self._ck(self._lib.gsm_stub_choose(self._h, n_sel, _p(trees), _p(u), _p(out)))
+        return out
+
     # ---- device-resident path (torch tensors own the memory) ----
     def bind_batch(self, batch):
         """batch: synthetic.Batch (or anything with the same tensor attributes) already on this device."""

@@ -194,6 +194,23 @@ int64_t gsm_last_dirty_full_count(const gsm_handle* h);
  * computes it (Stubs:424-447).  Writes min(*len, cap) cumulative probabilities; *len = the Java array length. */
 int  gsm_stub_cdf(gsm_handle* h, int64_t tree, int32_t node, double* cdf, int32_t cap, int32_t* len);
 
+/* The same for whole trees in one call (a logged state asks for every branch: Stubs.sampleNStubs Stubs:389-401, the tree
+ * loggers' Stubs.getArrayValue(i) for every node Stubs:666-674).  trees [n_sel] selects resident trees (NULL = trees
+ * 0 .. n_sel-1); items are (selected tree, node) in tree-major order, n_sel * n_nodes of them.  CSR output: the array of
+ * item j is cdf[cdf_ptr[j] .. cdf_ptr[j+1]); the root and branches with Poisson mean 0 (no draw in the reference,
+ * Stubs:416-434) have empty arrays.  cdf_ptr must hold n_sel * n_nodes + 1 entries; *needed receives the total length; at
+ * most `cap` doubles are written (call again with a larger buffer when *needed > cap). */
+int  gsm_stub_cdf_trees(gsm_handle* h, int64_t n_sel, const int64_t* trees, int64_t* cdf_ptr, double* cdf, int64_t cap,
+                        int64_t* needed);
+/* Stubs.sampleNStubsOnBranch for every branch of the selected trees, given the uniforms (Stubs:410-458 with
+ * Randomizer.randomChoice(getCumulativeProbs(mean, nodeNr)), Stubs:446-448): nstubs_out[j] = 0 for the root and for mean 0,
+ * -1 for every branch when stubs are estimated (stub_mode != GSM_STUBS_NOSTUB, Stubs:412), else the index randomChoice
+ * returns for U = u[j] (0 if U <= cf[0]; the first s with cf[s-1] < U <= cf[s]; cf.length if none).  The random numbers
+ * stay with the host: BEAST draws one Randomizer.nextDouble() per branch that reaches randomChoice, in node order; u[j] of
+ * the other branches is ignored.  Needs GSM_F_STUBS_TO_SPIKE_PRIOR (without a spike prior the reference uses
+ * Randomizer.nextPoisson, BEAST's own algorithm: GSM_E_UNSUPPORTED). */
+int  gsm_stub_choose(gsm_handle* h, int64_t n_sel, const int64_t* trees, const double* u, int32_t* nstubs_out);
+
 /* Pinned host memory for the arrays above (optional; any host pointer is accepted). */
 int  gsm_host_alloc(void** out, int64_t bytes);
 int  gsm_host_free(void* p);

@@ -351,6 +351,20 @@ int32_t gsmo_cumulative_probs(double mu, double spike, double shape, int use_ind
     return len;
 }
 
+/* Randomizer.randomChoice(double[] cf) of BEAST.base 2.7.7 (not under /root/reference; restated from memory of the BEAST 2
+ * source): s = 0 if U <= cf[0]; else the first s >= 1 with cf[s-1] < U <= cf[s]; cf.length if none. */
+int32_t gsmo_random_choice(const double* cf, int32_t len, double U) {
+    int32_t s;
+    if (len <= 0) return 0;
+    if (U <= cf[0]) {
+        s = 0;
+    } else {
+        for (s = 1; s < len; s++)
+            if (U <= cf[s] && U > cf[s - 1]) break;
+    }
+    return s;
+}
+
 /* ------------------------------------------------------------------------------------------
  * BranchRatePrior (BRP:29-65) — also equals the template's core Prior + LogNormal(M=1,S=GSMclockSD,
  * meanInRealSpace) of fxtemplates/GammaSpikeClockModel.xml:60-62.

@@ -124,6 +124,9 @@ void gsmo_eval_tree(const gsmo_config* cfg, const gsmo_tree* t, double* out, dou
 int32_t gsmo_cumulative_probs(double mu, double spike, double shape, int use_indicator_branch,
                               double* out, int32_t cap);
 
+/* Randomizer.randomChoice(cf) for a given uniform U (Stubs.sampleNStubsOnBranch Stubs:446-448) */
+int32_t gsmo_random_choice(const double* cf, int32_t len, double U);
+
 /* ---- batch (tree-major rows with a common stride) ---- */
 int gsmo_eval_batch(const gsmo_config* cfg, int64_t n_trees, int32_t n_nodes, int64_t stride,
                     const double* height, const int32_t* parent, const double* rate, const double* spike,

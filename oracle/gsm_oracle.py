@@ -128,6 +128,14 @@ def cumulative_probs(mu, spike, shape, use_indicator_branch, cap=4096):
     return np.array(buf[: min(n, cap)], dtype=np.float64), n
 
 
+def random_choice(cf, u):
+    cf = np.ascontiguousarray(cf, np.float64)
+    L = lib()
+    L.gsmo_random_choice.restype = C.c_int32
+    L.gsmo_random_choice.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+    return int(L.gsmo_random_choice(_ptr(cf), len(cf), float(u)))
+
+
 def param_maps(lambda_=None, net_div=None, r0=None, turnover=None, psi=None, sampling_proportion=None, rho=None):
     nan = float("nan")
     v = [nan if x is None else float(x) for x in (lambda_, net_div, r0, turnover, psi, sampling_proportion, rho)]

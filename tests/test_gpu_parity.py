@@ -352,3 +352,54 @@ def test_nonpositive_node_counts_in_a_ragged_batch():
     assert np.all(np.isnan(got["out"][nc <= 0]))
     ok = nc > 0
     assert_close(got["out"][ok], ref["out"][ok], what="rows next to empty trees")
+
+
+def test_whole_tree_stub_cdf_and_choice_match_oracle():
+    """Log-time stub sampling for every branch of whole trees in two launches (gsm_stub_cdf_trees) and the draw itself for
+    caller-supplied uniforms (gsm_stub_choose) against BSP.getCumulativeProbs + Randomizer.randomChoice restated in the
+    oracle, and against the one-branch call."""
+    b = synthetic.make_batch("C3", 6, 60, seed=4)
+    a = host_arrays(b)
+    flags = b.flags | abi.F_BSP_HAS_INDICATOR
+    a["use_spike"][:] = [1, 0, 1, 1, 0, 1]
+    eng = GsmEngine(max_trees=6, max_nodes=b.n_nodes)
+    run_capi(a, flags, abi.STUBS_NOSTUB, engine=eng)
+    sel = np.array([4, 0, 5, 2], np.int64)
+    ptr, cdf = eng.stub_cdf_trees(sel)
+    N = b.n_nodes
+    assert ptr.shape == (len(sel) * N + 1,) and ptr[-1] == len(cdf)
+    rng = np.random.default_rng(8)
+    u = rng.random((len(sel), N))
+    u[0, :5] = [0.0, 1.0, 0.999999999, 1e-300, 0.5]
+    picks = eng.stub_choose(u, sel)
+    L = oracle.lib()
+    checked = drawn = 0
+    for s, t in enumerate(sel):
+        lam, mu_, psi, rho = a["params"][t, abi.P_LAMBDA:abi.P_RHO + 1]
+        T_root = a["height"][t].max()
+        for node in range(N):
+            j = s * N + node
+            got = cdf[ptr[j]:ptr[j + 1]]
+            p = a["parent"][t, node]
+            mean = 0.0 if p < 0 else L.gsmo_mean_stub_number(a["height"][t, node], a["height"][t, p], lam, mu_, psi, rho, T_root)
+            if p < 0 or mean == 0:
+                assert len(got) == 0 and picks[s, node] == 0     # no draw: root / zero-length branch (Stubs:416-434)
+                continue
+            ref, n_ref = oracle.cumulative_probs(mean, a["spike"][t, node], a["params"][t, abi.P_SPIKE_SHAPE], a["use_spike"][t])
+            assert len(got) == n_ref
+            if a["spike"][t, node] == 0 and a["use_spike"][t]:
+                continue                                          # 0/0 in the Java as well
+            assert_close(got, ref, rtol=1e-9, atol=1e-12, what="cdf t=%d node=%d" % (t, node))
+            want = oracle.random_choice(ref, u[s, node])
+            near = np.any(np.abs(ref - u[s, node]) < 1e-9)       # a uniform this close to a CDF step may fall either side
+            assert picks[s, node] == want or near, (t, node, picks[s, node], want)
+            checked += 1
+            drawn += picks[s, node] > 0
+            if node % 11 == 0:
+                one, n_one = eng.stub_cdf(int(t), node)
+                assert n_one == n_ref and np.array_equal(one, got)
+    assert checked > 150 and drawn > 20
+    # stubs estimated: the reference returns -1 for every branch (Stubs:412)
+    eng.set_mode(abi.STUBS_COUNTS, flags)
+    assert np.all(eng.stub_choose(u, sel) == -1)
+    eng.close()
