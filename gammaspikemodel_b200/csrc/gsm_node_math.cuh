@@ -324,6 +324,40 @@ GSM_HD double gsm_node_pass_a(const GsmTreeConsts& K, GsmAcc& A, uint32_t nf, do
     const double G = fma(K.omc2, e_neg, K.opc2);
     const double aux = gsm_log(G);
 
+    // Where the Java's own expressions leave the finite range the aux algebra does not follow them by itself (it has no
+    // exp(+c1 h) and no log(e^{(l-m)h} - 1)): those nodes are evaluated with the Java expressions, literally, so that the
+    // state gets the reference's -inf / NaN (reproduce, do not fix).  Both conditions are false for every
+    // state BEAST can reach (heights >= 0, c1 T far below 700); the lean kernel hands such trees to this path.
+    const bool java_overflow = K.c1 * h > 700.0;                             // exp(c1 h) (1 + c2)^2 overflows near c1 h = 709
+    if ((K.tree_variant == GSM_TV_PSI || K.tree_variant == GSM_TV_CONDITIONED) && java_overflow) {
+        const double ep = exp(K.c1 * h), en = exp(-K.c1 * h);
+        const double q = ep * K.opc2 * K.opc2 + en * K.omc2 * K.omc2 + 2 * (1 - K.c2 * K.c2);                 // STP:489-491
+        const double p0 = (K.kS - K.c1 * (K.opc2 - en * K.omc2) / (K.opc2 + en * K.omc2)) / (2 * K.lambda);   // STP:506-507
+        const double p1 = (4 * K.rho) / (2 * (1 - K.c2 * K.c2) + en * K.omc2 * K.omc2 + ep * K.opc2 * K.opc2);   // STP:523-524
+        if (K.tree_variant == GSM_TV_PSI) {
+            if (!leaf) {
+                if (!(nf & GSM_NF_FAKE)) A.tree += log(K.lambda) + log(p1);                                   // STP:333
+            } else if (!(h <= GSM_LEAF_EPS) && !da) {
+                A.tree += log(p0) - log(p1);                                                                  // STP:342
+            }
+        } else {
+            if (leaf) {
+                if (!da) A.tree += log(K.psi) + log(q) + log(p0);                                             // STP:471 (h > 5e-12 here)
+            } else if (nf & GSM_NF_FAKE) {
+                A.tree += log(K.psi);                                                                         // STP:478
+            } else {
+                A.tree += log(K.lambda) - log(q);                                                             // STP:480
+            }
+        }
+        return aux;
+    }
+    if (K.tree_variant == GSM_TV_COMPLETE_RHO && !leaf && h < 0.0) {         // STP:423-426, 826-831 with a negative height
+        const double e = exp(K.lmm * h);
+        const double log_qt = log(K.mu * (e - 1)) - log(K.lambda * e - K.mu);
+        A.tree += log(K.lambda) + log(1 - exp(log_qt));
+        return aux;
+    }
+
     switch (K.tree_variant) {
         case GSM_TV_COMPLETE_RHO:                                            // STP:387-393, 423-426
             if (!leaf) A.tree += K.t_internal - aux;

@@ -26,11 +26,21 @@ def swap_labels(a, t, i, j):
     a["parent"][t] = q
 
 
+def reference_tree_case():
+    """the reference's own 36-taxon FBD tree with sampled ancestors (examples/stubs/nrStubs.xml:34-40; tests/golden)"""
+    from test_reference_fixture import reference_tree
+    return reference_tree(5)
+
+
 def build_cases():
     """yields (name, arrays, flags, stub_mode, node_count)"""
     c2, c3, c4 = _base("C2", 24, 40), _base("C3", 24, 60), _base("C4", 24, 33)
     out = []
     add = lambda name, a, flags=F, mode=abi.STUBS_COUNTS, nc=None: out.append((name, a, flags, mode, nc))
+    ref = reference_tree_case()
+    add("reference-nrstubs-tree", ref)                                     # FBDWS, psi > 0, 10 sampled ancestors, 36 taxa
+    add("reference-nrstubs-tree-nostub", ref, F, abi.STUBS_NOSTUB)         # nrStubs.xml / stochasticStubs.xml wirings
+    add("reference-nrstubs-tree-cond-root", ref, F | abi.F_COND_ROOT | abi.F_COND_SAMPLING)
     # ---- wirings ----
     add("c2-default", c2)
     add("c3-default", c3)
@@ -170,6 +180,15 @@ def build_cases():
     for t in range(a["height"].shape[0]):
         swap_labels(a, t, n3 - 1, n3 - 2 - (t % 7))
     add("c3-root-not-last", a)                                             # GENERAL flavour with the scan
+    # the Java's own overflow / domain behaviour outside the states BEAST can reach (reproduced, not fixed)
+    a = {k: v.copy() for k, v in c3.items()}
+    a["height"] *= 400.0                                                   # exp(c1 T) overflows: -inf, or NaN where an
+    add("c3-exp-c1T-overflow", a)                                          # extinct leaf's own exp(c1 h) overflows too (STP:342)
+    add("c3-exp-c1T-overflow-origin", variant(a, F, origin=1e5), F | abi.F_ORIGIN)
+    for nm, src in (("c3", c3), ("c2", c2), ("c4", c4)):
+        a = {k: v.copy() for k, v in src.items()}
+        a["height"] -= 0.3                                                 # negative heights: log(mu (e^{(l-m)h} - 1)) is NaN (STP:826-831)
+        add(nm + "-negative-heights", a)
     # ---- shapes ----
     add("two-taxa", _base("C3", 40, 2))
     add("single-node-trees", _base("C2", 7, 1))
