@@ -274,6 +274,9 @@ def main():
     ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the per-tree result rows reach rank 0: copy engines into rank 0's memory over NVLink (CUDA IPC, "
+                         "no SM used) or an NCCL all-gather; p2p falls back to nccl when peer memory cannot be opened")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (C2, C3, mixture mode, C5) timed after the headline region")
     ap.add_argument("--want-rates", action="store_true", help="also write per-branch effective rates (44 B/branch)")
     args = ap.parse_args()
@@ -326,7 +329,21 @@ def main():
     nbuf = 3 if distributed else 1
     out_b = [torch.empty((T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)]
     out_rates = torch.empty((T, S), dtype=torch.float64, device=dev) if args.want_rates else None
-    gathered = [torch.empty((world * T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)] if distributed else None
+    peer = None
+    if distributed and args.gather == "p2p":
+        from gammaspikemodel_b200.sharding import PeerGather
+        ok = torch.ones(1, device=dev)
+        try:
+            peer = PeerGather(rank, world, local_rank, T, abi.NOUT * 8, nbuf)
+        except Exception as ex:   # peer memory not available in this environment: every rank falls back together
+            sys.stderr.write("bench.py: p2p gather unavailable on rank %d (%r); using nccl\n" % (rank, ex))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            if peer is not None:
+                peer.close()
+            peer = None
+    gathered = [torch.empty((world * T, abi.NOUT), dtype=torch.float64, device=dev) for _ in range(nbuf)] if (distributed and peer is None) else None
     eng = GsmEngine(device=local_rank)
     eng.set_mode(batch.stub_mode, batch.flags)
     eng.bind_batch(batch)
@@ -355,11 +372,17 @@ def main():
             done_ev[i].record(tstream)
             with torch.cuda.stream(cstream):
                 cstream.wait_event(done_ev[i])
-                dist.all_gather_into_tensor(gathered[i], out_b[i])
+                if peer is not None:
+                    peer.push(i, out_b[i].data_ptr(), cstream.cuda_stream)
+                else:
+                    dist.all_gather_into_tensor(gathered[i], out_b[i])
                 free_ev[i].record(cstream)
         return out_b[i]
 
-    gather_note = ("nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the next steps' "
+    gather_note = ("every step's [T,8] result rows are pushed into rank 0's memory by the copy engines over NVLink (CUDA IPC peer "
+                   "memory, cudaMemcpyAsync on a second stream: no SM is taken from the kernels; three result buffers); the timed "
+                   "region ends after the last push has landed" if peer is not None else
+                   "nccl all_gather of the [T,8] result rows of every step, on a second stream: it overlaps the next steps' "
                    "kernels (three result buffers); the timed region ends after the last gather")
     chunks = 1
     for _ in range(args.warmup):
@@ -396,6 +419,26 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms, kern_ms_max = float(tmax[0]), float(tmax[1])
     value = world * branches * args.steps / (total_ms * 1e-3)
+
+    # ---- the gathered rows of the last step on rank 0 are the rows every rank computed ----
+    gather_check = None
+    if distributed:
+        last = (step_no[0] - 1) % nbuf
+        mine = out_b[last].view(torch.int64).sum(dim=0)            # per-column checksum of the bit patterns (exact, order-free)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            if peer is not None:
+                g = torch.from_numpy(peer.read_root(last)).to(dev)
+            else:
+                g = gathered[last]
+            got = g.contiguous().view(torch.int64).view(world, T, abi.NOUT).sum(dim=1)
+            want = torch.stack(sums)
+            same = bool(torch.equal(got, want))
+            first_rows = bool(torch.equal(torch.nan_to_num(g[:T]), torch.nan_to_num(out_b[last])))
+            gather_check = {"column_checksums_match": same, "rank0_rows_identical": first_rows}
+            if not (same and first_rows):
+                raise SystemExit("bench.py: gathered result rows differ from the rows the ranks computed")
 
     # ---- parity spot check of the timed outputs against the oracle (rank 0, 48 trees) ----
     parity = None
@@ -451,7 +494,29 @@ def main():
                 bad = np.argwhere(~((a_ == b_) | (np.isnan(a_) & np.isnan(b_))))
                 raise SystemExit("bench.py: host-buffer path and device-resident path disagree at %d entries, first %s: %r vs %r"
                                  % (len(bad), bad[0], a_[tuple(bad[0])], b_[tuple(bad[0])]))
+        # host -> device ceiling of this box at this N: the same pinned arrays as dense 1-D copies, every rank at once
+        dtmp = {k: torch.empty_like(v, device=dev) for k, v in hb.items()}
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            for k, v in hb.items():
+                dtmp[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        dtc = time.perf_counter() - t0
+        tc = torch.tensor([dtc], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        h2d_bytes = sum(v.numel() * v.element_size() for v in hb.values())
+        ceiling = world * 3 * h2d_bytes / float(tc[0]) / 1e9
+        del dtmp
+        e2e_gbs = world * e2e_steps * (Te * N * BYTES_PER_BRANCH + Te * 73) / dt / 1e9
         e2e = {"value": world * Te * N * e2e_steps / dt, "unit": UNIT,
+               "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": ceiling, "frac_of_h2d_ceiling": e2e_gbs / ceiling,
+               "h2d_ceiling_source": "the same pinned host arrays copied as dense 1-D cudaMemcpyAsync by all %d rank(s) at once, "
+                                     "3 passes, wall clock, max over ranks (PCIe / host-memory roofline of this box)" % world,
+               "fraction_of_a_full_step": Te / T,
                "h2d_bytes_per_step": Te * N * BYTES_PER_BRANCH + Te * 73, "d2h_bytes_per_step": Te * 64,
                "trees_per_step": Te, "steps": e2e_steps, "launches": e2e_launches,
                "note": "gsm_eval_host on pinned host arrays, chunked + double-buffered; bounded batch of the same workload"}
@@ -512,7 +577,7 @@ def main():
                        "branches_per_step": world * branches, "outputs": "logP+rates" if args.want_rates else "logP",
                        "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
                        if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
-                       "gather": gather_note if distributed else "none (1 GPU)",
+                       "gather": gather_note if distributed else "none (1 GPU)", "gather_check": gather_check,
                        "launches_per_step": launches // max(1, args.steps),
                        "generate_s": round(t_gen, 1), "parity_sample": parity},
             "clocks": sampler.summary(),
@@ -529,6 +594,9 @@ def main():
         emit(line)
     for e in engs:
         e.close()
+    if peer is not None:
+        dist.barrier()
+        peer.close()
     if distributed:
         dist.destroy_process_group()
 

@@ -40,6 +40,12 @@ SIGNATURES = {
     "gsm_bind_device": (C.c_int, [_vp, _i64, _i32, _i64] + [_vp] * 8),
     "gsm_eval_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "gsm_sync": (C.c_int, [_vp]),
+    "gsm_device_alloc": (C.c_int, [C.POINTER(_vp), _i32, _i64]),
+    "gsm_device_free": (C.c_int, [_vp, _i32]),
+    "gsm_ipc_export": (C.c_int, [_vp, C.c_char_p]),
+    "gsm_ipc_open": (C.c_int, [_i32, C.c_char_p, C.POINTER(_vp)]),
+    "gsm_ipc_close": (C.c_int, [_vp]),
+    "gsm_copy_async": (C.c_int, [_vp, _vp, _i64, _vp]),
     "gsm_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "gsm_launch_count": (_i64, [_vp]),
 }

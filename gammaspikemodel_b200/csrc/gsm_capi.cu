@@ -906,6 +906,69 @@ int gsm_sync(gsm_handle* h) {
     return GSM_OK;
 }
 
+// ---- device memory shared between the per-GPU processes of one box (result rows gathered by the copy engines) ----
+int gsm_device_alloc(void** out, int32_t device, int64_t bytes) {
+    if (!out || bytes < 0) return GSM_E_ARG;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GSM_E_ARG; }
+    cudaError_t e = cudaMalloc(out, static_cast<size_t>(bytes > 0 ? bytes : 1));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gsm_device_alloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? GSM_E_NOMEM : GSM_E_CUDA;
+    }
+    e = cudaMemset(*out, 0, static_cast<size_t>(bytes > 0 ? bytes : 1));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? GSM_OK : GSM_E_CUDA;
+}
+int gsm_device_free(void* p, int32_t device) {
+    if (!p) return GSM_OK;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GSM_E_ARG; }
+    return cudaFree(p) == cudaSuccess ? GSM_OK : GSM_E_CUDA;
+}
+int gsm_ipc_export(const void* dptr, unsigned char* handle64) {
+    if (!dptr || !handle64) return GSM_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hnd;
+    cudaError_t e = cudaIpcGetMemHandle(&hnd, const_cast<void*>(dptr));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gsm_ipc_export: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return GSM_E_CUDA;
+    }
+    memcpy(handle64, &hnd, 64);
+    return GSM_OK;
+}
+int gsm_ipc_open(int32_t device, const unsigned char* handle64, void** out) {
+    if (!handle64 || !out) return GSM_E_ARG;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GSM_E_ARG; }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(out, hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gsm_ipc_open: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return GSM_E_CUDA;
+    }
+    return GSM_OK;
+}
+int gsm_ipc_close(void* p) {
+    if (!p) return GSM_OK;
+    return cudaIpcCloseMemHandle(p) == cudaSuccess ? GSM_OK : GSM_E_CUDA;
+}
+int gsm_copy_async(void* dst, const void* src, int64_t bytes, void* cuda_stream) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return GSM_E_ARG;
+    if (bytes == 0) return GSM_OK;
+    cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, static_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("gsm_copy_async: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return GSM_E_CUDA;
+    }
+    return GSM_OK;
+}
+
 int gsm_measure_fp64_peak(gsm_handle* h, double* fma_per_sec) {
     if (!h || !fma_per_sec) return GSM_E_ARG;
     GSM_CUDA(h, cudaSetDevice(h->device));

@@ -233,6 +233,21 @@ int  gsm_eval_device(gsm_handle* h, double* d_out_tree, double* d_out_rates, dou
                      void* cuda_stream);
 int  gsm_sync(gsm_handle* h);
 
+/* ---- multi-GPU hosts: one process per GPU, result rows gathered over NVLink by the copy engines -------------
+ * Trees are independent, so the only exchange of the path is the gather of the per-tree result rows (64 B per tree).
+ * A rank allocates its receive buffer with gsm_device_alloc, exports it (gsm_ipc_export: a 64-byte cudaIpcMemHandle_t
+ * that the host passes to its peers through any channel), and every peer opens it (gsm_ipc_open; peer access over
+ * NVLink / NVSwitch is enabled on first use) and pushes its rows with gsm_copy_async on a side stream: a plain
+ * device-to-device copy, executed by the DMA engines, so that no SM is taken from the kernels it overlaps with.
+ * gsm_copy_async also moves host <-> device (cudaMemcpyDefault).  Ordering is the caller's: CUDA events between the
+ * kernel stream and the side stream, and a process-level barrier before the receiver reads. */
+int  gsm_device_alloc(void** out, int32_t device, int64_t bytes);
+int  gsm_device_free(void* p, int32_t device);
+int  gsm_ipc_export(const void* dptr, unsigned char* handle64);
+int  gsm_ipc_open(int32_t device, const unsigned char* handle64, void** out);
+int  gsm_ipc_close(void* p);
+int  gsm_copy_async(void* dst, const void* src, int64_t bytes, void* cuda_stream);
+
 /* Measurement helper (bench.py, roofline.fp64): throughput of the device's fp64 pipe in thread-level fused multiply-adds
  * per second, from a DFMA micro-benchmark (eight independent chains per thread, full occupancy, best of five launches). */
 int  gsm_measure_fp64_peak(gsm_handle* h, double* fma_per_sec);
