@@ -211,6 +211,23 @@ int  gsm_stub_cdf_trees(gsm_handle* h, int64_t n_sel, const int64_t* trees, int6
  * Randomizer.nextPoisson, BEAST's own algorithm: GSM_E_UNSUPPORTED). */
 int  gsm_stub_choose(gsm_handle* h, int64_t n_sel, const int64_t* trees, const double* u, int32_t* nstubs_out);
 
+/* ---- the step after the path: the tree-log line of one state (host side, no device work) ----------------
+ * StumpedTreeLogger.toNewick (logger/StumpedTreeLogger.java:77-199; the same shape as BEAST's TreeWithMetaDataLogger): the
+ * Newick string of the tree with per-node metadata `[&nstubs=..,rate=..,<id>=..]` and branch lengths, every number printed
+ * as Java's Double.toString does (JDK 19+ rule: shortest decimal that rounds to the double; decimal notation for
+ * 1e-3 <= |d| < 1e7, else d.dddE[-]n; "NaN", "Infinity").  left / right: Node.getLeft / getRight numbers (-1 = none; they fix
+ * the print order), parent (-1 = root), height: as uploaded.  nstubs (NULL = no stubs wired; the root prints none,
+ * STL:92), rate (NULL = no clock model; values = out_rates of gsm_eval), n_meta metadata functions with ids separated by
+ * '\n', values [n_meta][n_nodes] (e.g. out_wspikes for GSMweightedSpikes, GSMbranchRates) and dimensions (a node number
+ * >= the dimension prints nothing, STL:159, 187).  Matrix-valued metadata and the reversible-jump stub-location entries
+ * (STL:103-123) are not produced.  Returns the length of the string (written if it fits cap - 1, NUL-terminated), -1 on
+ * bad arguments.  The caller adds "tree STATE_<n> = " and ";" (STL:59-67). */
+int64_t gsm_format_newick(int32_t n_nodes, const int32_t* left, const int32_t* right, const int32_t* parent,
+                          const double* height, const int32_t* nstubs, const double* rate, int32_t n_meta,
+                          const char* meta_ids, const double* meta_values, const int32_t* meta_dim, char* out, int64_t cap);
+/* Java's Double.toString(d) (as used by every Loggable of the package: SPL:60, SpikeSize:74-78, STL:201-203). */
+int64_t gsm_java_double_to_string(double d, char* out, int64_t cap);
+
 /* Pinned host memory for the arrays above (optional; any host pointer is accepted). */
 int  gsm_host_alloc(void** out, int64_t bytes);
 int  gsm_host_free(void* p);

@@ -60,6 +60,9 @@ public final class GsmB200 {
     public static final MethodHandle STUB_CDF = mh("gsm_stub_cdf", fi(ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
     public static final MethodHandle STUB_CDF_TREES = mh("gsm_stub_cdf_trees", fi(ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     public static final MethodHandle STUB_CHOOSE = mh("gsm_stub_choose", fi(ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+    public static final MethodHandle FORMAT_NEWICK = mh("gsm_format_newick", FunctionDescriptor.of(JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS,
+            ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
+    public static final MethodHandle JAVA_DOUBLE_TO_STRING = mh("gsm_java_double_to_string", FunctionDescriptor.of(JAVA_LONG, JAVA_DOUBLE, ADDRESS, JAVA_LONG));
     public static final MethodHandle HOST_ALLOC = mh("gsm_host_alloc", fi(ADDRESS, JAVA_LONG));
     public static final MethodHandle HOST_FREE = mh("gsm_host_free", fi(ADDRESS));
     public static final MethodHandle DEVICE_STRIDE = mh("gsm_device_stride", FunctionDescriptor.of(JAVA_LONG, JAVA_INT));
