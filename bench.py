@@ -1,16 +1,16 @@
 #!/usr/bin/env python
 """bench.py — branch logP evaluations / second of the B200 hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4shard|c2|c3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c4shard|c2|c3] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of the hot path (clock-rate map + spike / rate / stub prior logP + tree prior +
 ProportionOfSaltation sums) over one resident synthetic batch: gsm_lean_kernel + gsm_post_kernel per rank; at N>1
 the NCCL all-gather of a step's per-tree result rows (the only collective on the path) runs on a second stream and
 overlaps the next step's kernels.
-Default workload: the per-GPU shard of BASELINE config 4 (1M trees x 2,000 taxa over 8 GPUs =
-125,000 trees x 3,999 nodes per GPU, 16 GB of inputs, far larger than L2); scaling is weak, so N=8 is
-exactly the 1M-tree configuration.
+Default workload: BASELINE config 4 as written, ONE batch of 1M trees x 2,000 taxa sharded across the N GPUs of the run
+(strong scaling: 128 GB of inputs resident on the one GPU at N=1, 125,000 trees = 16 GB per GPU at N=8; far larger than
+L2 at every N).  `--workload c4shard` is the weak-scaling twin (125,000 trees per GPU at every N).
 
 Prints ONE JSON line (rank 0).  `--impl reference` instead times the CPU restatement of the reference
 (oracle/, all host threads) on a bounded sample of the same workload.
@@ -43,6 +43,11 @@ WORKLOADS = {
     "c3": ("C3", 100_000, 1000, "BASELINE config 3: 100k trees x 1,000 taxa, FBDWS, sampled ancestors, rho<1, indicator per state"),
     "c2": ("C2", 10_000, 200, "BASELINE config 2: 10k trees x 200 taxa, BDWS, spikes on"),
 }
+# BASELINE config 4 as written: ONE batch of 1,000,000 trees x 2,000 taxa sharded across the N GPUs of the run (strong scaling:
+# 128 GB of inputs resident on one GPU at N = 1, 16 GB per GPU at N = 8).  "c4shard" is its weak-scaling twin (125,000 per GPU).
+C4_TOTAL_TREES = 1_000_000
+WORKLOADS["c4"] = ("C4", C4_TOTAL_TREES, 2000, "BASELINE config 4: 1,000,000 trees x 2,000 taxa sharded across the GPUs of the run "
+                                               "(all of it resident on one GPU at N = 1), BDWS stub counts, rho=1 / rho<1 alternating, spikes on")
 
 
 def measured_peak():
@@ -183,6 +188,7 @@ def run_reference(args, rank):
     import oracle
     from gammaspikemodel_b200 import synthetic
     kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
+    strong = args.workload == "c4"
     threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     trees = min(trees_per_gpu, 8192)
     batch = synthetic.make_batch_chunked(kind, trees, taxa, seed=synthetic.SEEDS[kind], chunk=2048)
@@ -198,7 +204,7 @@ def run_reference(args, rank):
     value = total_br / total_dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(1, done), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "trees_in_sample": trees, "taxa": taxa, "nodes_per_tree": n_nodes},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d trees x %d nodes, passes repeated for ~2 s per step (bounded sample of the workload), "
@@ -269,7 +275,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c4shard", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -311,6 +317,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     kind, trees_per_gpu, taxa, desc = WORKLOADS[args.workload]
+    strong = args.workload == "c4"
+    if strong:
+        trees_per_gpu = C4_TOTAL_TREES // world     # contiguous shards of the one batch (sharding.shard_range)
     if args.trees:
         trees_per_gpu = args.trees
     seed = synthetic.SEEDS[kind] + rank
@@ -571,9 +580,9 @@ def main():
         kc = kernel_counters(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "trees_per_gpu": T, "taxa": taxa, "nodes_per_tree": N,
+            "config": {"workload": desc, "trees_per_gpu": T, "trees_total": world * T, "taxa": taxa, "nodes_per_tree": N,
                        "branches_per_step": world * branches, "outputs": "logP+rates" if args.want_rates else "logP",
                        "l2": "inputs per launch (%.1f GB) larger than L2, no flush" % (per_launch_bytes / 1e9)
                        if per_launch_bytes > 256e6 else "inputs fit L2; not flushed",
@@ -584,8 +593,10 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": kc["dram_bytes_per_launch"] if kc else None,
-                         "traffic_source": ("%s (csrc %s%s)" % (kc.get("source"), kc.get("csrc_sha"), ", STALE: kernel sources changed since" if kc["stale"] else ", current")) if kc else None,
+                         "traffic": (kc["dram_bytes_per_launch"] * branches / kc["branches_per_launch"]) if kc else None,
+                         "traffic_source": ("%s, %d branches per launch, scaled to this launch's branch count (csrc %s%s)"
+                                            % (kc.get("source"), kc.get("branches_per_launch"), kc.get("csrc_sha"),
+                                               ", STALE: kernel sources changed since" if kc["stale"] else ", current")) if kc else None,
                          "kernel": "gsm_lean_kernel (kernel_ms also contains gsm_post_kernel, < 2 % of the step)", "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src, "fp64": fp64},
             "cpu_baseline": cpu,

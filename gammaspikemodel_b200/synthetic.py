@@ -226,17 +226,25 @@ def make_batch(kind, n_trees, n_taxa, seed=None, device="cpu", tree_offset=0, sh
 
 
 def make_batch_chunked(kind, n_trees, n_taxa, seed=None, device="cpu", chunk=16384):
-    """Same distribution as make_batch, generated in chunks to bound temporary memory (full-size bench batches)."""
-    parts = []
+    """Same distribution as make_batch, generated in chunks to bound temporary memory (full-size bench batches): the arrays
+    of the whole batch are allocated once and filled chunk by chunk, so the peak is the batch plus one chunk (the 1M-tree
+    configuration is 128 GB of inputs on one 180 GB GPU)."""
+    if n_trees <= chunk:
+        return make_batch(kind, n_trees, n_taxa, seed=seed, device=device)
+    out = None
     for t0 in range(0, n_trees, chunk):
-        parts.append(make_batch(kind, min(chunk, n_trees - t0), n_taxa, seed=seed, device=device, tree_offset=t0))
-    if len(parts) == 1:
-        return parts[0]
-    b0 = parts[0]
-    cat = lambda name: torch.cat([getattr(p, name) for p in parts], dim=0)
-    return Batch(n_trees=n_trees, n_taxa=b0.n_taxa, n_nodes=b0.n_nodes, stride=b0.stride, flags=b0.flags,
-                 stub_mode=b0.stub_mode, height=cat("height"), parent=cat("parent"), rate=cat("rate"),
-                 spike=cat("spike"), nstubs=cat("nstubs"), params=cat("params"), use_spike=cat("use_spike"), kind=b0.kind)
+        part = make_batch(kind, min(chunk, n_trees - t0), n_taxa, seed=seed, device=device, tree_offset=t0)
+        if out is None:
+            alloc = lambda x: torch.empty((n_trees,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            out = Batch(n_trees=n_trees, n_taxa=part.n_taxa, n_nodes=part.n_nodes, stride=part.stride, flags=part.flags,
+                        stub_mode=part.stub_mode, height=alloc(part.height), parent=alloc(part.parent), rate=alloc(part.rate),
+                        spike=alloc(part.spike), nstubs=alloc(part.nstubs), params=alloc(part.params),
+                        use_spike=alloc(part.use_spike), kind=part.kind)
+        t1 = t0 + part.n_trees
+        for name in ("height", "parent", "rate", "spike", "nstubs", "params", "use_spike"):
+            getattr(out, name)[t0:t1] = getattr(part, name)
+        del part
+    return out
 
 
 def make_chain_states(n_chains, n_taxa, seed=None, device="cpu", kind="C2"):
