@@ -290,6 +290,8 @@ int gsm_set_option(gsm_handle* h, const char* name, int64_t value) {
         h->ctx.block = static_cast<int>(value);
     } else if (!strcmp(name, "minb")) {
         h->ctx.minb = static_cast<int>(value);
+    } else if (!strcmp(name, "producer")) {
+        h->ctx.producer = value != 0;
     } else {
         return fail(h, GSM_E_ARG, "gsm_set_option: unknown option '%s'", name);
     }

@@ -754,7 +754,7 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
 
 // virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
 // (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi.  PAIRS node pairs per thread and chunk (pair tid + p BLOCK).
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX>
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, bool PROD>
 static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
                                                      const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
                                                      int32_t* sh_root_nroot, double2* __restrict__ orate2,
@@ -792,8 +792,9 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
         if ((tid & 31) == 0) {
             mbar_arrive_a(a_empty + s * 8u);
             // Chunk v + STAGES - 1 goes into the stage chunk v - 1 came from, once every warp has taken its pairs of v - 1.
-            // The requesting duty rotates over the warps, so that no warp falls behind the others because of it.
-            if ((tid >> 5) == (v & (BLOCK / 32 - 1)) && v >= 1 && v + NST - 1 < rg.nvc) {
+            // PROD: the producer warp of the CTA does that (lean_producer).  Else the requesting duty rotates over the warps,
+            // so that no warp falls behind the others because of it.
+            if (!PROD && (tid >> 5) == (v & (BLOCK / 32 - 1)) && v >= 1 && v + NST - 1 < rg.nvc) {
                 const uint32_t sp = s == 0u ? NST - 1u : s - 1u;
                 mbar_wait_a(a_empty + sp * 8u, (s == 0u ? ph ^ 1u : ph));
                 ring_issue<2 * HB>(rg, v + NST - 1, sp);
@@ -816,19 +817,29 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
 
 // main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
 // chunks were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, bool PROD>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
                                                    int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
                                                    double2* __restrict__ owsp2) {
-    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2, owsp2);
-    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid, sh_root_nroot,
-                                                                orate2, owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2,
+                                                                                  owsp2);
+    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid,
+                                                                                  sh_root_nroot, orate2, owsp2);
 }
 
 // MIXK: the mixture-mode spike prior (BSP:102-172) is a kernel of its own, so that its body does not weigh on the register
 // allocation of the known-n kernel.
-template <int BLOCK, int MINB, bool WANT_RATES, bool MIXK>
-__global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b, GsmLeanRow* __restrict__ rows,
+// PROD: a second warpgroup of four warps holds the producer warp, which requests every chunk after the first NST ones, so
+// that the four consumer warps never run request code.  setmaxnreg works on whole warpgroups (measured: it never returns
+// for a warpgroup of one warp, and register allocation per warp has a granularity that makes 5 warps x 136 registers
+// take the room of 5 x 144): the kernel starts at 80 registers (3 CTAs x 256 threads), the producer warpgroup gives
+// 56 x 128 back and the consumer warpgroup takes them.
+#define GSM_PROD_CONSUMER_REGS 136
+#define GSM_PROD_PRODUCER_REGS 24
+#define GSM_PROD_THREADS 128
+#define GSM_LEAN_BOUNDS(B, M, P) __launch_bounds__((B) + ((P) ? GSM_PROD_THREADS : 0), M)
+template <int BLOCK, int MINB, bool WANT_RATES, bool MIXK, bool PROD = false>
+__global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatch b, GsmLeanRow* __restrict__ rows,
                                                                int32_t* __restrict__ redo_count,
                                                                int32_t* __restrict__ redo_count_next,
                                                                int32_t* __restrict__ redo_list, double* __restrict__ out_rates,
@@ -864,6 +875,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int64_t t = blockIdx.x;
+    // barriers of the consumer warps once the producer warp has gone its own way (named barrier 2)
+    auto csync = [&]() {
+        if (PROD) asm volatile("bar.sync 2, %0;" ::"n"(BLOCK) : "memory");
+        else __syncthreads();
+    };
+    auto csync_or = [&](bool pred) -> bool {
+        if (PROD) {
+            uint32_t r;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, 2, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(r)
+                         : "r"(pred ? 1u : 0u), "n"(BLOCK)
+                         : "memory");
+            return r != 0u;
+        }
+        return __syncthreads_or(pred ? 1 : 0) != 0;
+    };
     GSM_PHASE_START();
     if (t == 0 && tid == 0) *redo_count_next = 0;   // counter of the next evaluation on this handle (ping-pong)
     int32_t n = b.node_count ? b.node_count[t] : b.n_nodes;
@@ -896,6 +923,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     rg.end_int = (n - 1 + 3) & ~3;
     const int nvc = rg.nvc;
 
+    if (PROD) {
+        if (warp >= NWARP) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GSM_PROD_PRODUCER_REGS));
+            __syncthreads();   // barriers initialised
+            __syncthreads();   // per-tree scalars in shared memory, first NST chunks requested
+            // the producer: chunk v goes into stage v % NST once every consumer warp has taken its pairs of chunk v - NST
+            // (the consumers leave without a pass B when the per-tree constants send the tree to the generic path)
+            if (warp == NWARP && lane == 0 && gsm_lean_consts_ok(K) && ((K.spike_known_n == 0) == MIXK)) {
+                uint32_t s = 0u, ph = 0u;   // stage and parity of its previous use
+#pragma unroll 1
+                for (int v = NST; v < nvc; ++v) {
+                    mbar_wait_a(rg.a_empty + s * 8u, ph);
+                    ring_issue<2 * HB>(rg, v, s);
+                    if (++s == NST) {
+                        s = 0u;
+                        ph ^= 1u;
+                    }
+                }
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GSM_PROD_CONSUMER_REGS));
+    }
     // global loads whose latency would otherwise sit between the first two barriers: issued before anything else
     int32_t parent_last = 0;
     double prm_v[GSM_NPARAM];
@@ -1048,7 +1098,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         // Node.isDirectAncestor: a leaf at its parent's height -> the parent isFake.  Leaf heights and parents straight from
         // global memory (the ring will read them again from L2).
         for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
-        __syncthreads();
+        csync();
         const double* hrow = b.height + row;
         const int32_t* prow = b.parent + row;
         // GSM_SCAN_U leaves per thread and round: all their global loads are issued before the first one is used
@@ -1190,7 +1240,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         x.auxz = gsm_lean_aux(c, S0, 0.0, x.ez, x.Gz);
     }
     GSM_PHASE_MARK(3);   // pass A (thread 0's share)
-    const bool any = __syncthreads_or(anyda ? 1 : 0) != 0;
+    const bool any = csync_or(anyda);
     GSM_PHASE_MARK(4);   // waiting for the other warps
     const bool general = any || !sh.root_last;
 
@@ -1202,11 +1252,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
     int32_t* rn = &sh.root;   // {root, nroot}
-#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
+#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M, PROD>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
 #define GSM_PASS_B3(G, LT) { if constexpr (MIXK) GSM_PASS_B(G, false, LT, true); else { if (stdw) GSM_PASS_B(G, true, LT, false); else GSM_PASS_B(G, false, LT, false); } }
     if (general) {
         if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
-        if (!detect) __syncthreads();
+        if (!detect) csync();
         if (c.leaf_term == 0) GSM_PASS_B3(true, 0)
         else if (c.leaf_term == 1) GSM_PASS_B3(true, 1)
         else GSM_PASS_B3(true, 2)
@@ -1260,7 +1310,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gsm_lean_kernel(const GsmBatch b,
         sh.redi[4][warp] = c4; sh.redi[5][warp] = c5; sh.redi[6][warp] = c6;
         sh.redu[0][warp] = u0; sh.redu[1][warp] = u1; sh.redu[2][warp] = u2; sh.redu[3][warp] = u3; sh.redu[4][warp] = u4;
     }
-    __syncthreads();
+    csync();
     GSM_PHASE_MARK(6);   // waiting for the other warps (pass B)
     if (warp == 0) {
         // lanes 0..5 sum one double each over the warps (fixed order); lanes 8..14 the integers; lanes 16..20 the maxima
@@ -1641,18 +1691,18 @@ static cudaError_t lean_probe(KERN kern, int block, const GsmBatch& b, const Gsm
 
 // dynamic + static + driver-reserved shared memory one CTA of the lean kernel <BLOCK, MINB> takes for this batch
 // index of a compiled-in lean configuration in GsmLaunchCtx::a_dyn
-constexpr int gsm_lean_cfg_index(int block, int minb) { return block == 128 ? (minb == 4 ? 0 : (minb == 3 ? 1 : 3)) : 2; }
-template <int BLOCK, int MINB>
+constexpr int gsm_lean_cfg_index(int block, int minb, bool prod) { return prod ? 4 : (block == 128 ? (minb == 4 ? 0 : (minb == 3 ? 1 : 3)) : 2); }
+template <int BLOCK, int MINB, bool PROD>
 static cudaError_t lean_cta_bytes(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, bool rates, cudaStream_t st, size_t* dyn,
                                   size_t* all) {
-    int* a_dyn = ctx.a_dyn + 2 * gsm_lean_cfg_index(BLOCK, MINB);
+    int* a_dyn = ctx.a_dyn + 2 * gsm_lean_cfg_index(BLOCK, MINB, PROD);
     constexpr int HB = BLOCK * gsm_lean_pairs(BLOCK, MINB), NST = gsm_lean_stages(BLOCK, MINB);
     const int k = rates ? 1 : 0;
     if (a_dyn[k] < 0) {
         cudaError_t e;
         // (the mixture kernels have the same static shared memory: one probe serves both flavours)
-        if (rates) e = lean_probe(gsm_lean_kernel<BLOCK, MINB, true, false>, BLOCK, b, sc, st, &a_dyn[k]);
-        else e = lean_probe(gsm_lean_kernel<BLOCK, MINB, false, false>, BLOCK, b, sc, st, &a_dyn[k]);
+        if (rates) e = lean_probe(gsm_lean_kernel<BLOCK, MINB, true, false, PROD>, BLOCK + (PROD ? GSM_PROD_THREADS : 0), b, sc, st, &a_dyn[k]);
+        else e = lean_probe(gsm_lean_kernel<BLOCK, MINB, false, false, PROD>, BLOCK + (PROD ? GSM_PROD_THREADS : 0), b, sc, st, &a_dyn[k]);
         if (e != cudaSuccess) return e;
     }
     *dyn = lean_smem_bytes(b.n_nodes, a_dyn[k], HB, NST);
@@ -1661,7 +1711,7 @@ static cudaError_t lean_cta_bytes(GsmLaunchCtx& ctx, const GsmBatch& b, const Gs
     return cudaSuccess;
 }
 
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, bool PROD>
 static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
     const dim3 grid(static_cast<unsigned>(b.n_trees));
     GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
@@ -1670,13 +1720,13 @@ static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmSc
     int32_t* list = sc.redo + 4;
     cudaError_t e;
     size_t smem = 0, all = 0;
-    if ((e = lean_cta_bytes<BLOCK, MINB>(ctx, b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
+    if ((e = lean_cta_bytes<BLOCK, MINB, PROD>(ctx, b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
     const bool mixk = gsm_lean_mixture(b.flags, b.stub_mode);
-#define GSM_LAUNCH_LEAN(R, M)                                                     \
-    {                                                                             \
-        auto kern = gsm_lean_kernel<BLOCK, MINB, R, M>;                           \
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;                 \
-        kern<<<grid, BLOCK, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);      \
+#define GSM_LAUNCH_LEAN(R, M)                                                                        \
+    {                                                                                                \
+        auto kern = gsm_lean_kernel<BLOCK, MINB, R, M, PROD>;                                        \
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;                                    \
+        kern<<<grid, BLOCK + (PROD ? GSM_PROD_THREADS : 0), smem, st>>>(b, rows, cnt, cnt_next, list, r, w);       \
     }
     if (r || w) {
         if (mixk) GSM_LAUNCH_LEAN(true, true) else GSM_LAUNCH_LEAN(true, false)
@@ -1745,7 +1795,7 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
         int block = 128, minb = 4;
         if (b.n_nodes > 512) {
             size_t dyn = 0, all = 0;
-            cudaError_t pe = lean_cta_bytes<128, 3>(ctx, b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
+            cudaError_t pe = lean_cta_bytes<128, 3, false>(ctx, b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
             if (pe != cudaSuccess) return -static_cast<int>(pe);
             if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) <= ctx.smem_per_sm) {
                 minb = 3;
@@ -1756,10 +1806,15 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
         }
         if (ctx.block > 0) block = ctx.block;
         if (ctx.minb > 0) minb = ctx.minb;
+        // 128 x 3 runs with a producer warp (160 threads per CTA) unless gsm_set_option("producer", 0)
+        if (block == 128 && minb == 3 && ctx.producer != 0) {
+            e = launch_lean<128, 3, true>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
+        } else {
 #define GSM_CFG(B, M) \
-    if (block == B && minb == M) e = launch_lean<B, M>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
-        GSM_LEAN_CFGS
+    if (block == B && minb == M) e = launch_lean<B, M, false>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
+            GSM_LEAN_CFGS
 #undef GSM_CFG
+        }
         if (e != cudaSuccess) return -static_cast<int>(e);
         if (b.n_nodes <= 2048) e = launch_post<256, 3>(ctx, b, sc, d_out_tree, d_out_rates, d_out_wspikes, stream);
         else e = launch_post<384, 2>(ctx, b, sc, d_out_tree, d_out_rates, d_out_wspikes, stream);

@@ -1,3 +1,5 @@
-timeout 900 python bench.py --workload c4full --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-e2e > gpurun_out/r2f_c4full.json 2> gpurun_out/r2f_c4full.err
-tail -3 gpurun_out/r2f_c4full.err; cut -c1-900 gpurun_out/r2f_c4full.json
-nvidia-smi --query-gpu=memory.total,memory.used --format=csv
+mkdir -p gpurun_out
+timeout 90 python tools/tune.py C4 60000 2000 128x3n 128x3 128x3n 128x3 > gpurun_out/p1_tune_c4.log 2>&1 || { echo HANG_OR_FAIL; tail -3 gpurun_out/p1_tune_c4.log; exit 1; }
+timeout 90 python tools/tune.py C3 50000 1000 128x3n 128x3 > gpurun_out/p1_tune_c3.log 2>&1
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/p1_pytest.log
+cat gpurun_out/p1_tune_c4.log gpurun_out/p1_tune_c3.log gpurun_out/p1_pytest.log

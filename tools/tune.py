@@ -10,15 +10,16 @@ if os.environ.get("GSM_LIB_PATH"):   # debug build with phase counters (tools/bu
 from gammaspikemodel_b200 import GsmEngine, abi, synthetic
 
 kind, trees, taxa = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-cfgs = [tuple(map(int, c.split("x"))) for c in sys.argv[4:]]
+# a configuration is BLOCKxMINB, optionally followed by "n" = no producer warp (128x3n)
+cfgs = [tuple(map(int, c.rstrip("n").split("x"))) + (0 if c.endswith("n") else 1,) for c in sys.argv[4:]]
 dev = torch.device("cuda", 0)
 b = synthetic.make_batch_chunked(kind, trees, taxa, device=dev, chunk=31250)
 eng = GsmEngine(device=0); eng.set_mode(b.stub_mode, b.flags); eng.bind_batch(b)
 out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 ref = None
-for blk, minb in cfgs:
-    eng.set_option("block", blk); eng.set_option("minb", minb)
+for blk, minb, prod in cfgs:
+    eng.set_option("block", blk); eng.set_option("minb", minb); eng.set_option("producer", prod)
     for _ in range(3): eng.eval_device(out, None, None, st.cuda_stream)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,5 +47,5 @@ for blk, minb in cfgs:
     maxdiff = 0.0 if ref is None else float((torch.nan_to_num(cur) - torch.nan_to_num(ref)).abs().max())
     if ref is None: ref = cur
     br = b.n_trees * b.n_nodes
-    print(json.dumps({"kind": kind, "trees": trees, "taxa": taxa, "block": blk, "minb": minb, "ms": round(ms, 4),
+    print(json.dumps({"kind": kind, "trees": trees, "taxa": taxa, "block": blk, "minb": minb, "producer": prod, "ms": round(ms, 4),
                       "branch_evals_per_s": br / ms * 1e3, "GBps": br * 32 / ms / 1e6, "bitwise_same_as_first": same, "max_abs_diff_vs_first": maxdiff}), flush=True)
