@@ -292,6 +292,10 @@ int gsm_set_option(gsm_handle* h, const char* name, int64_t value) {
         h->ctx.minb = static_cast<int>(value);
     } else if (!strcmp(name, "producer")) {
         h->ctx.producer = value != 0;
+    } else if (!strcmp(name, "smem_pad")) {
+        h->ctx.smem_pad = static_cast<size_t>(value);
+    } else if (!strcmp(name, "persistent")) {
+        h->ctx.persistent = static_cast<int>(value);
     } else {
         return fail(h, GSM_E_ARG, "gsm_set_option: unknown option '%s'", name);
     }

@@ -526,7 +526,8 @@ struct GsmLeanLayout {
     uint32_t logtab, exptab, arrays, ring, mtab, ntab, fk, total;
 };
 __host__ __device__ inline int gsm_lean_si(int n_nodes) { return (((n_nodes + 1) >> 1) + 8 + 1) & ~1; }   // n - L4 + pad, even
-__host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si, uint32_t ring_bytes) {
+// pk (persistent kernel): no mtab
+__host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si, uint32_t ring_bytes, bool pk = false) {
     GsmLeanLayout l;
     const uint32_t gap = (8192u - (a_dyn & 8191u)) & 8191u;
     uint32_t free0 = 0u, free1 = gap;             // free part of the gap
@@ -543,7 +544,8 @@ __host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si,
     end += static_cast<uint32_t>(si) * 16u;
     l.ring = end;
     end += ring_bytes;
-    const uint32_t sz[3] = {(GSM_LEAN_MTAB_N + 1) * 16u, (GSM_LEAN_MAX_NST + 1) * 32u, (static_cast<uint32_t>(si) + 15u) & ~15u};
+    const uint32_t sz[3] = {pk ? 0u : (GSM_LEAN_MTAB_N + 1) * 16u, (GSM_LEAN_MAX_NST + 1) * 32u,
+                            (static_cast<uint32_t>(si) + 15u) & ~15u};
     uint32_t off[3];
     for (int k = 0; k < 3; k++) {
         if (free1 - free0 >= sz[k]) {
@@ -607,6 +609,14 @@ static __device__ __forceinline__ double lean_log_gamma(const GsmT6& t6, double 
     const double tmp = x + 607.0 / 128.0 + .5;
     return ((x + .5) * gsm_log6_hi(t6, tmp)) - tmp + 0.91893853320467274178 + gsm_log6_hi(t6, sum * lean_rcp(x));
 }
+
+#ifndef GSM_PK_TMA_DOORBELL
+#define GSM_PK_TMA_DOORBELL 0
+#endif
+// named barriers of the persistent kernel (gsm_lean_pk.cuh): 0 __syncthreads, 2 consumers, then
+#define GSM_PK_BAR_STAGE 3    // + stage: a consumer warp has taken its share of the chunk in this stage (wakes the copy warp)
+#define GSM_PK_BAR_SCAL 6     // + buffer: the consumers are through with a tree (wakes the scalar warp, two trees ahead)
+#define GSM_PK_BAR_GAMMA 8    // + buffer: ... (wakes the Gamma warps, one tree ahead)
 
 // ---- the ring -------------------------------------------------------------------------------------------
 // Virtual chunk v: v < nlc is leaf chunk v (nodes [v * 2 BLOCK, ...) up to L), else internal chunk v - nlc (nodes from
@@ -754,16 +764,16 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
 
 // virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
 // (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi.  PAIRS node pairs per thread and chunk (pair tid + p BLOCK).
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, bool PROD>
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD>
 static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
                                                      const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
                                                      int32_t* sh_root_nroot, double2* __restrict__ orate2,
-                                                     double2* __restrict__ owsp2) {
+                                                     double2* __restrict__ owsp2, uint32_t& s, uint32_t& ph) {
+    // s, ph: ring stage of chunk v0 and the parity of its full barrier; on return those of chunk v1 (one tree per CTA:
+    // v0 % NST, (v0 / NST) & 1; the persistent kernel's ring runs on across trees)
     constexpr int HB = BLOCK * PAIRS;            // pairs per chunk
     constexpr uint32_t STAGE = HB * 64u;
     const bool counts = STDW || rg.nst != nullptr;
-    uint32_t s = static_cast<uint32_t>(v0) % NST;
-    uint32_t ph = (static_cast<uint32_t>(v0) / NST) & 1u;
     int i0 = first + 2 * tid;
     // this thread's slot of stage 0 and the first mbarrier: kept in registers (opaque to the compiler, which otherwise
     // re-derives them from the kernel parameters in every iteration)
@@ -773,7 +783,15 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
     const uint32_t a_empty = a_full + static_cast<uint32_t>(rg.a_empty - rg.a_full);
 #pragma unroll 1
     for (int v = v0; v < v1; ++v) {
+#ifdef GSM_PHASE_TIMING
+        const long long tw_ = clock64();
+#endif
+        // (testing the barrier of chunk v + 1 before the body of chunk v, so that the latency of the test passes under the
+        // body, measured 2.5 % slower: profiles/r02_tuning.md)
         mbar_wait_a(a_full + s * 8u, ph);
+#ifdef GSM_PHASE_TIMING
+        if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[7], static_cast<unsigned long long>(clock64() - tw_));   // waiting for a chunk
+#endif
         double2 rr[PAIRS], ss[PAIRS], h2[PAIRS];
         int2 kk[PAIRS], pp[PAIRS];
 #pragma unroll
@@ -789,6 +807,11 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
             pp[p] = lds_v2s32(sq + HB * 56u);
         }
         __syncwarp();
+        // PROD == 2 (persistent kernel): the copy warp sleeps on a named barrier per stage (a polling warp takes issue slots
+        // from the consumers); the mbarrier carries the ordering, the named barrier only wakes the sleeper
+#if GSM_PK_TMA_DOORBELL
+        if (PROD == 2) asm volatile("bar.arrive %0, %1;" ::"r"(GSM_PK_BAR_STAGE + s), "n"(BLOCK + 32) : "memory");
+#endif
         if ((tid & 31) == 0) {
             mbar_arrive_a(a_empty + s * 8u);
             // Chunk v + STAGES - 1 goes into the stage chunk v - 1 came from, once every warp has taken its pairs of v - 1.
@@ -817,14 +840,14 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
 
 // main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
 // chunks were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, bool PROD>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
                                                    int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
-                                                   double2* __restrict__ owsp2) {
+                                                   double2* __restrict__ owsp2, uint32_t& s, uint32_t& ph) {
     lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2,
-                                                                                  owsp2);
+                                                                                  owsp2, s, ph);
     lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid,
-                                                                                  sh_root_nroot, orate2, owsp2);
+                                                                                  sh_root_nroot, orate2, owsp2, s, ph);
 }
 
 // MIXK: the mixture-mode spike prior (BSP:102-172) is a kernel of its own, so that its body does not weigh on the register
@@ -1252,7 +1275,8 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
     const bool stdw = gsm_lean_std_wiring(c);
     int32_t* rn = &sh.root;   // {root, nroot}
-#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M, PROD>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2)
+    uint32_t ring_s = 0u, ring_ph = 0u;
+#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M, PROD>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2, ring_s, ring_ph)
 #define GSM_PASS_B3(G, LT) { if constexpr (MIXK) GSM_PASS_B(G, false, LT, true); else { if (stdw) GSM_PASS_B(G, true, LT, false); else GSM_PASS_B(G, false, LT, false); } }
     if (general) {
         if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
@@ -1352,6 +1376,8 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
         }
     }
 }
+
+#include "gsm_lean_pk.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // BranchSpikePrior.getCumulativeProbs (BSP:315-389) for one branch; log-time only, one thread.
@@ -1620,8 +1646,8 @@ cudaError_t gsm_init_tables() {
 size_t gsm_scratch_row_bytes() { return sizeof(GsmLeanRow); }
 
 static size_t generic_smem_bytes(int64_t stride) { return static_cast<size_t>(stride) * 22u; }
-static size_t lean_smem_bytes(int32_t n_nodes, int a_dyn, int pairs_per_chunk, int stages) {
-    return gsm_lean_layout(static_cast<uint32_t>(a_dyn), gsm_lean_si(n_nodes), static_cast<uint32_t>(stages) * pairs_per_chunk * 64u).total;
+static size_t lean_smem_bytes(int32_t n_nodes, int a_dyn, int pairs_per_chunk, int stages, bool pk = false) {
+    return gsm_lean_layout(static_cast<uint32_t>(a_dyn), gsm_lean_si(n_nodes), static_cast<uint32_t>(stages) * pairs_per_chunk * 64u, pk).total;
 }
 
 // Kernel attributes are set once per handle and kernel, to values that do not depend on the batch (the device's opt-in
@@ -1725,8 +1751,8 @@ static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmSc
 #define GSM_LAUNCH_LEAN(R, M)                                                                        \
     {                                                                                                \
         auto kern = gsm_lean_kernel<BLOCK, MINB, R, M, PROD>;                                        \
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;                                    \
-        kern<<<grid, BLOCK + (PROD ? GSM_PROD_THREADS : 0), smem, st>>>(b, rows, cnt, cnt_next, list, r, w);       \
+        if ((e = prep(ctx, kern, smem + ctx.smem_pad)) != cudaSuccess) return e;                     \
+        kern<<<grid, BLOCK + (PROD ? GSM_PROD_THREADS : 0), smem + ctx.smem_pad, st>>>(b, rows, cnt, cnt_next, list, r, w); \
     }
     if (r || w) {
         if (mixk) GSM_LAUNCH_LEAN(true, true) else GSM_LAUNCH_LEAN(true, false)
@@ -1734,6 +1760,44 @@ static cudaError_t launch_lean(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmSc
         if (mixk) GSM_LAUNCH_LEAN(false, true) else GSM_LAUNCH_LEAN(false, false)
     }
 #undef GSM_LAUNCH_LEAN
+    return cudaGetLastError();
+}
+
+// persistent lean kernel (gsm_lean_pk.cuh): 3 CTAs per SM, each walking over trees blockIdx.x, blockIdx.x + gridDim.x, ...
+static cudaError_t lean_pk_cta_bytes(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, bool rates, cudaStream_t st, size_t* dyn,
+                                     size_t* all) {
+    int* a_dyn = ctx.a_dyn + 2 * 5;
+    const int k = rates ? 1 : 0;
+    if (a_dyn[k] < 0) {
+        cudaError_t e;
+        if (rates) e = lean_probe(gsm_lean_pk_kernel<true>, GSM_PK_THREADS, b, sc, st, &a_dyn[k]);
+        else e = lean_probe(gsm_lean_pk_kernel<false>, GSM_PK_THREADS, b, sc, st, &a_dyn[k]);
+        if (e != cudaSuccess) return e;
+    }
+    *dyn = lean_smem_bytes(b.n_nodes, a_dyn[k], GSM_PK_CONSUMERS, GSM_RING_STAGES, true);
+    *all = static_cast<size_t>(a_dyn[k]) + *dyn;
+    return cudaSuccess;
+}
+static cudaError_t launch_lean_pk(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
+    int64_t g = static_cast<int64_t>(ctx.sm_count) * 3;
+    if (g > b.n_trees) g = b.n_trees;
+    const dim3 grid(static_cast<unsigned>(g));
+    GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
+    int32_t* cnt = sc.redo + (sc.epoch & 1);
+    int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
+    int32_t* list = sc.redo + 4;
+    cudaError_t e;
+    size_t smem = 0, all = 0;
+    if ((e = lean_pk_cta_bytes(ctx, b, sc, r || w, st, &smem, &all)) != cudaSuccess) return e;
+    if (r || w) {
+        auto kern = gsm_lean_pk_kernel<true>;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, GSM_PK_THREADS, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    } else {
+        auto kern = gsm_lean_pk_kernel<false>;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, GSM_PK_THREADS, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    }
     return cudaGetLastError();
 }
 
@@ -1806,8 +1870,20 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
         }
         if (ctx.block > 0) block = ctx.block;
         if (ctx.minb > 0) minb = ctx.minb;
-        // 128 x 3 runs with a producer warp (160 threads per CTA) unless gsm_set_option("producer", 0)
-        if (block == 128 && minb == 3 && ctx.producer != 0) {
+        // the persistent kernel (known-n spike prior) whenever three of its CTAs fit an SM, unless gsm_set_option("persistent", 0)
+        bool pk = ctx.persistent != 0 && ctx.block <= 0 && ctx.minb <= 0 && !gsm_lean_mixture(b.flags, b.stub_mode);
+        if (ctx.persistent == 2) pk = !gsm_lean_mixture(b.flags, b.stub_mode);   // forced (tuning runs)
+        if (pk) {
+            size_t dyn = 0, all = 0;
+            cudaError_t pe = lean_pk_cta_bytes(ctx, b, sc, d_out_rates || d_out_wspikes, stream, &dyn, &all);
+            if (pe != cudaSuccess) return -static_cast<int>(pe);
+            if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) > ctx.smem_per_sm) pk = false;
+        }
+        if (pk) {
+            e = launch_lean_pk(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
+        } else if (block == 128 && minb == 3 && ctx.producer != 0 && !gsm_lean_mixture(b.flags, b.stub_mode)) {
+            // 128 x 3 runs with a producer warp unless "producer" is 0 (the mixture flavour wants the 168 registers of the
+            // four-warp CTA: 1.59e10 against 1.79e10 branch evals/s with 136)
             e = launch_lean<128, 3, true>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         } else {
 #define GSM_CFG(B, M) \

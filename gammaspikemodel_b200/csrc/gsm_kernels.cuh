@@ -48,12 +48,14 @@ struct GsmLaunchCtx {
     int sm_count = 0;
     size_t smem_per_sm = 0;      // cudaDevAttrMaxSharedMemoryPerMultiprocessor
     size_t smem_optin = 0;       // cudaDevAttrMaxSharedMemoryPerBlockOptin
-    int a_dyn[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // shared-window address of the dynamic segment per (lean config, rates)
+    int a_dyn[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // shared-window address of the dynamic segment per (lean config, rates)
     const void* prepared[GSM_CTX_MAX_KERNELS] = {};    // kernels whose attributes were set on this handle's device
     int n_prepared = 0;
     // gsm_set_option (tuning / tests; 0 = automatic)
     int force_generic = 0, block = 0, minb = 0;
     int producer = 1;            // 128 x 3: run the lean kernel with a producer warp
+    size_t smem_pad = 0;         // extra dynamic shared memory per CTA of gsm_lean_kernel (occupancy experiments)
+    int persistent = 0;          // 1: the persistent lean kernel where it applies (measured slower than one CTA per tree: off)
 };
 cudaError_t gsm_launch_ctx_init(GsmLaunchCtx& ctx, int device);
 

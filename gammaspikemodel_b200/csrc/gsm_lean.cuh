@@ -467,7 +467,16 @@ GSM_HD void gsm_lean_b_node(const GsmLeanC& c, GsmLeanAccB& S, int32_t i, bool r
         S.k_nk += (int32_t)ni * (ke + 64);
     } else {
         const uint32_t mi = (uint32_t)m < (uint32_t)(GSM_LEAN_MTAB_N - 1) ? (uint32_t)m : (uint32_t)(GSM_LEAN_MTAB_N - 1);
-        const GsmLogEntry me = c.mtab[mi];              // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}
+        // {shape m - 1, log shape - logGamma(shape m)}; m = 0: {-1, 0}.  Without an mtab (persistent kernel) the same numbers
+        // come from ntab[m - 1].
+        GsmLogEntry me;
+        if (c.mtab) {
+            me = c.mtab[mi];
+        } else {
+            const GsmLeanN q = c.ntab[mi == 0u ? 0u : mi - 1u];
+            me.invc = mi == 0u ? -1.0 : q.w;
+            me.logc = mi == 0u ? 0.0 : q.gcon;
+        }
         S.gam = fma(ys, me.invc, S.gam);
         S.gamc += me.logc;
         S.k_mk += ((int32_t)mi - 1) * ks;               // (MIX: m is 0 or 1; log 1 is K = 1, y = -ln2/64 in this table)

@@ -403,3 +403,38 @@ def test_whole_tree_stub_cdf_and_choice_match_oracle():
     eng.set_mode(abi.STUBS_COUNTS, flags)
     assert np.all(eng.stub_choose(u, sel) == -1)
     eng.close()
+
+
+@pytest.mark.parametrize("opts", [{"producer": 0}, {"persistent": 1}], ids=["no-producer-warp", "persistent-kernel"])
+def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
+    """The lean kernel runs with a producer warp by default; the same kernel without it and the persistent kernel
+    (gsm_lean_pk.cuh, off by default) do the same arithmetic in the same order: bit-identical rows, rates and weighted
+    spikes, on ordinary trees, sampled-ancestor trees, ragged batches and the case table's invalid states."""
+    batches = [("C4", 700, 2000), ("C3", 600, 1000), ("C2", 1500, 200), ("C3", 40, 3), ("C4", 5, 2)]
+    for kind, T, n in batches:
+        b = synthetic.make_batch(kind, T, n)
+        a = host_arrays(b)
+        ref = run_oracle(a, b.flags, b.stub_mode)
+        base = run_capi(a, b.flags, b.stub_mode)
+        eng = GsmEngine(max_trees=T, max_nodes=b.n_nodes)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        got = run_capi(a, b.flags, b.stub_mode, engine=eng)
+        eng.close()
+        assert_results_match(got, ref, what="%s %dx%d %s" % (kind, T, n, opts))
+        for key in ("out", "rates", "wspikes"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), (kind, T, n, key)
+    for name, a, flags, mode, nc in CASES:
+        if mode == abi.STUBS_NOSTUB and (flags & abi.F_STUBS_TO_SPIKE_PRIOR):
+            continue                                      # mixture-mode wiring: its own kernel flavour, no variants
+        if a.get("stubs") is not None:
+            continue
+        base = run_capi(a, flags, mode, node_count=nc)
+        T, N = a["height"].shape
+        eng = GsmEngine(max_trees=max(T, 1), max_nodes=max(N, 1))
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        got = run_capi(a, flags, mode, node_count=nc, engine=eng)
+        eng.close()
+        for key in ("out", "rates", "wspikes"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), (name, key)

@@ -5,4 +5,4 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p build
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ -DGSM_PHASE_TIMING $GSM_DBG_FLAGS \
-  -shared -o ${GSM_DBG_OUT:-build/libgsm_b200_dbg.so} gammaspikemodel_b200/csrc/gsm_kernels.cu gammaspikemodel_b200/csrc/gsm_capi.cu
+  -shared -o ${GSM_DBG_OUT:-build/libgsm_b200_dbg.so} gammaspikemodel_b200/csrc/gsm_kernels.cu gammaspikemodel_b200/csrc/gsm_capi.cu gammaspikemodel_b200/csrc/gsm_treelog.cpp
