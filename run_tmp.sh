@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-: > gpurun_out/p10.log
-GSM_LIB_PATH=$PWD/build/libA.so timeout 90 python tools/tune.py C4 60000 2000 128x3 128x3n pk 128x3 >> gpurun_out/p10.log 2>&1
-GSM_LIB_PATH=$PWD/build/libA.so timeout 90 python tools/tune.py C3 50000 1000 128x3 128x3n pk >> gpurun_out/p10.log 2>&1
-cut -c1-175 gpurun_out/p10.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/n2_bench.json 2> gpurun_out/n2_bench.err
+tail -3 gpurun_out/n2_bench.err; cut -c1-700 gpurun_out/n2_bench.json
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/n2_bench_ref.json 2>> gpurun_out/n2_bench.err
+cut -c1-300 gpurun_out/n2_bench_ref.json
