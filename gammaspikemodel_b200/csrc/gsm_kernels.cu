@@ -154,6 +154,8 @@ static __device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+static __device__ __forceinline__ void sts_f64(uint32_t a, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory"); }
+static __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 static __device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
@@ -564,6 +566,12 @@ __host__ __device__ inline GsmLeanLayout gsm_lean_layout(uint32_t a_dyn, int si,
 }
 // ring stages (<= GSM_RING_STAGES)
 __host__ __device__ constexpr int gsm_lean_stages(int block, int minb) { return (void)block, (void)minb, GSM_RING_STAGES; }
+#define GSM_TAIL_SLOTS 5
+struct __align__(8) GsmLeanXPair {
+    int32_t i0, pad;      // first node of the pair, -1: none
+    int32_t i[2][2];      // parent, stub count
+    double d[2][3];       // height, rate, spike
+};
 template <int NWARP>
 struct GsmLeanShared {
     GsmTreeConsts K;
@@ -572,11 +580,14 @@ struct GsmLeanShared {
     uint64_t empty[GSM_RING_STAGES];   // ring: every warp holds its pairs of the chunk in registers
     int32_t root, nroot, bad, root_last;
     int32_t pa_next;         // pass A: next batch of pairs
-    double tail_d[3][3];     // height, rate, spike of the up to three tail nodes (asynchronous copies, phase 0)
-    int32_t tail_i[3][2];    // parent, stub count
-    double tail_s6[3][6];    // their combined sums ...
-    int32_t tail_c[3][6];    // ... counts (leafterm, plain, fake, extant, extinct, da) ...
-    uint32_t tail_u[3][4];   // ... and check words (chk, chk_n, hmax, chk_p)
+    // tail nodes: slots 0-2 = L-1, L (odd L) and n-1, rows fetched by asynchronous copies in phase 0; slots 3-4 = the pair of
+    // internal nodes that holds the root when the root is not node n-1 (xp, handed over by the thread that met it in pass B)
+    double tail_d[3][3];                  // height, rate, spike
+    int32_t tail_i[3][2];                 // parent, stub count
+    GsmLeanXPair xp;
+    double tail_s6[GSM_TAIL_SLOTS][6];    // their combined sums ...
+    int32_t tail_c[GSM_TAIL_SLOTS][6];    // ... counts (leafterm, plain, fake, extant, extinct, da) ...
+    uint32_t tail_u[GSM_TAIL_SLOTS][4];   // ... and check words (chk, chk_n, hmax, chk_p)
     double red[6][NWARP];
     int32_t redi[7][NWARP];
     uint32_t redu[5][NWARP];
@@ -697,8 +708,10 @@ struct LeanBCtx {
 };
 
 // one node pair (i0, i0 + 1), both leaves (LEAF = 1) or both internal (LEAF = 0)
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, bool MIX>
-static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, int i0, bool on,
+// XPD: distance in shared memory from the ring's first full barrier to the GsmLeanXPair hand-over slots (both members of the
+// kernel's shared struct; 0: the kernel has none); a_full: address of that barrier (live in the chunk loop anyway)
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, bool MIX, int XPD>
+static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, uint32_t a_full, int i0, bool on,
                                                    const double2 rr, const double2 ss, double2 h2, const int2 kk, int2 pp,
                                                    int32_t* sh_root_nroot, double2* __restrict__ orate2, double2* __restrict__ owsp2) {
     double2 a2;
@@ -717,6 +730,28 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
         if (!on) return;
         h2 = lds_v2f64(x.a_hs + i0 * 8);
         a2 = lds_v2f64(x.a_as + i0 * 8);
+        if (!GENERAL && (pp.x | pp.y) < 0) {
+            // An ordinary tree whose root is not node n-1 (BEAST's operators leave the root anywhere): the pair that holds it
+            // goes to two tail lanes, which evaluate single nodes with the GENERAL flavour after pass B; every other pair of
+            // the tree keeps the CLEAN body.  (A second such pair, or no hand-over slots: not a tree this path finishes.)
+            if (XPD == 0) {
+                SB.chk = 0xffffffffu;
+                return;
+            }
+            const uint32_t a_xpair = a_full + static_cast<uint32_t>(XPD);
+            uint32_t old;
+            asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a_xpair), "r"(0xffffffffu), "r"(static_cast<uint32_t>(i0)) : "memory");
+            if (old != 0xffffffffu) {
+                SB.chk = 0xffffffffu;
+                return;
+            }
+            const uint32_t a_xi = a_xpair + 8u, a_xd = a_xpair + 24u;   // GsmLeanXPair::i, ::d
+            sts_f64(a_xd + 0, h2.x); sts_f64(a_xd + 8, rr.x); sts_f64(a_xd + 16, ss.x);
+            sts_f64(a_xd + 24, h2.y); sts_f64(a_xd + 32, rr.y); sts_f64(a_xd + 40, ss.y);
+            sts_u32(a_xi + 0, static_cast<uint32_t>(pp.x)); sts_u32(a_xi + 4, static_cast<uint32_t>(kk.x));
+            sts_u32(a_xi + 8, static_cast<uint32_t>(pp.y)); sts_u32(a_xi + 12, static_cast<uint32_t>(kk.y));
+            return;
+        }
     }
     bool root0 = false, root1 = false;
     if (GENERAL) {   // a root has no parent: it points to itself
@@ -764,7 +799,7 @@ static __device__ __forceinline__ void lean_b_pair(const GsmLeanC& c, GsmLeanAcc
 
 // virtual chunks [v0, v1) of pass B, all of one LEAF class; `first` = first node of chunk v0, `lo`/`hi`: a thread's pair
 // (i0, i0 + 1) is processed when lo <= i0 and i0 + 1 < hi.  PAIRS node pairs per thread and chunk (pair tid + p BLOCK).
-template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD>
+template <bool GENERAL, bool WANT_RATES, int LEAF, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD, int XPD>
 static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x,
                                                      const LeanRing& rg, int v0, int v1, int first, int lo, int hi, int tid,
                                                      int32_t* sh_root_nroot, double2* __restrict__ orate2,
@@ -827,8 +862,8 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
         for (int p = 0; p < PAIRS; p++) {
             const int ip = i0 + 2 * p * BLOCK;
             const bool on = ip >= lo && ip + 1 < hi;
-            lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT, MIX>(c, SA, SB, x, ip, on, rr[p], ss[p], h2[p], kk[p], pp[p], sh_root_nroot,
-                                                                  orate2, owsp2);
+            lean_b_pair<GENERAL, WANT_RATES, LEAF, STDW, LT, MIX, XPD>(c, SA, SB, x, a_full, ip, on, rr[p], ss[p], h2[p], kk[p], pp[p],
+                                                                       sh_root_nroot, orate2, owsp2);
         }
         i0 += 2 * HB;
         if (++s == NST) {
@@ -840,13 +875,13 @@ static __device__ __forceinline__ void lean_b_chunks(const GsmLeanC& c, GsmLeanA
 
 // main loop of pass B: leaf chunks (pairs below L), internal chunks (pairs from L on, up to n - 1).  The first three
 // chunks were requested in phase 0.
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int BLOCK, int PAIRS, int NST, bool MIX, int PROD, int XPD>
 static __device__ __forceinline__ void lean_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, const LeanRing& rg,
                                                    int n, int tid, int32_t* sh_root_nroot, double2* __restrict__ orate2,
                                                    double2* __restrict__ owsp2, uint32_t& s, uint32_t& ph) {
-    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2,
+    lean_b_chunks<GENERAL, WANT_RATES, 1, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD, XPD>(c, SA, SB, x, rg, 0, rg.nlc, 0, 0, rg.L, tid, sh_root_nroot, orate2,
                                                                                   owsp2, s, ph);
-    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid,
+    lean_b_chunks<GENERAL, WANT_RATES, 0, STDW, LT, BLOCK, PAIRS, NST, MIX, PROD, XPD>(c, SA, SB, x, rg, rg.nlc, rg.nvc, rg.L4, rg.L, n - 1, tid,
                                                                                   sh_root_nroot, orate2, owsp2, s, ph);
 }
 
@@ -992,6 +1027,7 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
         sh.nroot = 0;
         sh.bad = 0;
         sh.pa_next = 0;
+        sh.xp.i0 = -1;
     }
     __syncthreads();
     // requests spread over the warps (a bulk copy costs its issuing thread a few hundred cycles)
@@ -1011,12 +1047,15 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     // The tail nodes (node n-1 and, when L is odd, L-1 and L) are evaluated by three lanes after pass B from rows read
     // straight from global memory: requested now, as asynchronous copies, so that their latency is long gone by then.
     const bool tail_lane = warp == (NWARP > 1 ? 1 : 0) && lane >= 29;
+    // (lanes 27-28 of the same warp take the root's pair when it is handed over: slots 3-4; nothing of that is kept in
+    // registers across pass B)
+#define GSM_TSLOT(lane_) ((lane_) >= 29 ? (lane_) - 29 : (lane_) - 24)
     int tail_node = -1;
     if (tail_lane) {
         if (lane == 31) tail_node = n - 1;
         else if (L & 1) tail_node = lane == 29 ? L - 1 : L;
         if (tail_node >= 0) {
-            const int k = lane - 29;
+            const int k = GSM_TSLOT(lane);
             cp_async_8(smem_u32(&sh.tail_d[k][0]), b.height + row + tail_node);
             cp_async_8(smem_u32(&sh.tail_d[k][1]), b.rate + row + tail_node);
             cp_async_8(smem_u32(&sh.tail_d[k][2]), b.spike + row + tail_node);
@@ -1067,6 +1106,7 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     x.a_fL = x.a_fk + static_cast<uint32_t>(L);
     x.chk_p = 0u;
     x.nL = static_cast<uint32_t>(n - L);
+    static_assert(offsetof(GsmLeanXPair, i) == 8 && offsetof(GsmLeanXPair, d) == 24, "GsmLeanXPair layout (lean_b_pair)");
 
     // ---- phase 1: Gamma tables (64 lanes), fake flags ----
     // Sampled ancestors are expected where the tree prior generates them (psi > 0, origin / root conditioning): those trees
@@ -1151,14 +1191,16 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     auto tail_eval = [&](bool early, bool gen) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         const int i = tail_node;
-        const int k = lane - 29;
+        const int k = GSM_TSLOT(lane);
+        const double* td = k < 3 ? sh.tail_d[k] : sh.xp.d[k - 3];
+        const int32_t* ti = k < 3 ? sh.tail_i[k] : sh.xp.i[k - 3];
         GsmLeanAccB ST;
         gsm_lean_acc_b_zero(ST);
         GsmLeanAccA STA;
         gsm_lean_acc_a_zero(STA);
         uint32_t chk_p = 0u;
-        const double h = sh.tail_d[k][0];
-        int32_t p = sh.tail_i[k][0];
+        const double h = td[0];
+        int32_t p = ti[0];
         const bool root = p < 0;
         if (root) {
             atomicAdd(&sh.nroot, 1);
@@ -1182,9 +1224,9 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
             else if (c.leaf_term == 2) gsm_lean_leaf_term<2>(c, STA, !da, h, aux, e, G);
         }
         int32_t nst = -1;
-        if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? sh.tail_i[k][1] : 0;
+        if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? ti[1] : 0;
         double er, ew;
-        gsm_lean_b_node<true, WANT_RATES, 2, false, MIXK>(c, ST, i, root, pf, fs, h, hp, aux, auxp, sh.tail_d[k][1], sh.tail_d[k][2], nst, &er,
+        gsm_lean_b_node<true, WANT_RATES, 2, false, MIXK>(c, ST, i, root, pf, fs, h, hp, aux, auxp, td[1], td[2], nst, &er,
                                                           &ew);
         if (WANT_RATES) {
             if (out_rates) out_rates[row + i] = er;
@@ -1265,7 +1307,9 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     GSM_PHASE_MARK(3);   // pass A (thread 0's share)
     const bool any = csync_or(anyda);
     GSM_PHASE_MARK(4);   // waiting for the other warps
-    const bool general = any || !sh.root_last;
+    // GENERAL bodies for trees with sampled ancestors; an ordinary tree whose root is not node n-1 keeps the CLEAN bodies and
+    // hands the pair with the root to the tail lanes (lean_b_pair)
+    const bool general = any;
 
     // ---- phase 3: pass B ----
     GSM_WARP_T0();
@@ -1276,7 +1320,9 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     const bool stdw = gsm_lean_std_wiring(c);
     int32_t* rn = &sh.root;   // {root, nroot}
     uint32_t ring_s = 0u, ring_ph = 0u;
-#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M, PROD>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2, ring_s, ring_ph)
+    constexpr int XPD = static_cast<int>(offsetof(GsmLeanShared<NWARP>, xp)) - static_cast<int>(offsetof(GsmLeanShared<NWARP>, full));
+    static_assert(XPD != 0, "hand-over slots");
+#define GSM_PASS_B(G, W, LT, M) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, PAIRS, NST, M, PROD, XPD>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2, ring_s, ring_ph)
 #define GSM_PASS_B3(G, LT) { if constexpr (MIXK) GSM_PASS_B(G, false, LT, true); else { if (stdw) GSM_PASS_B(G, true, LT, false); else GSM_PASS_B(G, false, LT, false); } }
     if (general) {
         if (!detect) for (int k = tid; k < (SI + 3) >> 2; k += BLOCK) reinterpret_cast<uint32_t*>(sh_fk)[k] = 0u;
@@ -1294,7 +1340,12 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     GSM_WARP_T1(0);
     // ---- tail: node n-1 (no stub count in COUNTS mode, Stubs:354; the root of an ordinary tree) and, when L is odd, the
     // pair (L-1, L) that straddles the leaf / internal boundary ----
-    const bool tail_on = tail_lane && tail_node >= 0;
+    const bool xpair_lane = warp == (NWARP > 1 ? 1 : 0) && (lane == 27 || lane == 28);
+    if (!general && !sh.root_last) {   // the root was met in pass B
+        csync();   // the hand-over slots were written by whichever thread met it
+        if (xpair_lane && sh.xp.i0 >= 0) tail_node = sh.xp.i0 + (lane - 27);
+    }
+    const bool tail_on = (tail_lane || xpair_lane) && tail_node >= 0;
     if (tail_on && !early_tail) tail_eval(false, general);
     GsmLean6 s6;
     if (general) {
@@ -1305,7 +1356,7 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
     int32_t t_leafterm = 0, t_plain = 0, t_fake = 0, t_extant = 0, t_extinct = 0, t_da = 0;
     uint32_t t_chk = 0u, t_chk_n = 0u, t_hmax = 0u;
     if (tail_on) {
-        const int k = lane - 29;
+        const int k = GSM_TSLOT(lane);
         const double* o = sh.tail_s6[k];
         s6.tree += o[0]; s6.stub += o[1]; s6.spike += o[2]; s6.rate += o[3]; s6.burst += o[4]; s6.dist += o[5];
         const int32_t* oc = sh.tail_c[k];
@@ -1882,7 +1933,7 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
         if (pk) {
             e = launch_lean_pk(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         } else if (block == 128 && minb == 3 && ctx.producer != 0 && !gsm_lean_mixture(b.flags, b.stub_mode)) {
-            // 128 x 3 runs with a producer warp unless "producer" is 0 (the mixture flavour wants the 168 registers of the
+            // gsm_set_option("producer", 1): 128 x 3 with a producer warp (the mixture flavour keeps the 168 registers of the
             // four-warp CTA: 1.59e10 against 1.79e10 branch evals/s with 136)
             e = launch_lean<128, 3, true>(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         } else {

@@ -53,7 +53,8 @@ struct GsmLaunchCtx {
     int n_prepared = 0;
     // gsm_set_option (tuning / tests; 0 = automatic)
     int force_generic = 0, block = 0, minb = 0;
-    int producer = 1;            // 128 x 3: run the lean kernel with a producer warp
+    int producer = 0;            // 1: 128 x 3 runs with a producer warp (second warpgroup, setmaxnreg); measured equal to the
+                                 // four-warp CTA on C4 and 3 % slower on C3 once its 136-register consumers spill: off
     size_t smem_pad = 0;         // extra dynamic shared memory per CTA of gsm_lean_kernel (occupancy experiments)
     int persistent = 0;          // 1: the persistent lean kernel where it applies (measured slower than one CTA per tree: off)
 };

@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(GSM_PK_THREADS, 3) gsm_lean_pk_kernel(const Gs
         double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
         const bool stdw = gsm_lean_std_wiring(c);
         int32_t* rn = &sh.root;   // {root, nroot}
-#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, 1, NST, false, 2>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2, ring_s, ring_ph)
+#define GSM_PASS_B(G, W, LT) lean_pass_b<G, WANT_RATES, W, LT, BLOCK, 1, NST, false, 2, 0>(c, SA, SB, x, rg, n, tid, rn, orate2, owsp2, ring_s, ring_ph)
 #define GSM_PASS_B3(G, LT) { if (stdw) GSM_PASS_B(G, true, LT); else GSM_PASS_B(G, false, LT); }
         if (general) {
             if (c.leaf_term == 0) GSM_PASS_B3(true, 0)

@@ -405,11 +405,15 @@ def test_whole_tree_stub_cdf_and_choice_match_oracle():
     eng.close()
 
 
-@pytest.mark.parametrize("opts", [{"producer": 0}, {"persistent": 1}], ids=["no-producer-warp", "persistent-kernel"])
+@pytest.mark.parametrize("opts", [{"producer": 1}, {"persistent": 1}], ids=["producer-warp", "persistent-kernel"])
 def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
-    """The lean kernel runs with a producer warp by default; the same kernel without it and the persistent kernel
-    (gsm_lean_pk.cuh, off by default) do the same arithmetic in the same order: bit-identical rows, rates and weighted
-    spikes, on ordinary trees, sampled-ancestor trees, ragged batches and the case table's invalid states."""
+    """The lean kernel's launch variants (producer warp: gsm_set_option("producer", 1); persistent kernel gsm_lean_pk.cuh:
+    "persistent", 1; both off by default) do the same arithmetic in the same order as the default launch: bit-identical
+    rows, rates and weighted spikes on ordinary trees, sampled-ancestor trees and ragged batches; on the case table
+    (invalid states, roots that are not the last node, ...) bit-identical for the producer variant and within the parity
+    tolerance for the persistent kernel, which evaluates a tree whose root is not node n-1 with the GENERAL bodies where
+    the default hands the root's pair to the tail lanes."""
+    bitwise_cases = "persistent" not in opts
     batches = [("C4", 700, 2000), ("C3", 600, 1000), ("C2", 1500, 200), ("C3", 40, 3), ("C4", 5, 2)]
     for kind, T, n in batches:
         b = synthetic.make_batch(kind, T, n)
@@ -436,5 +440,47 @@ def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
             eng.set_option(k, v)
         got = run_capi(a, flags, mode, node_count=nc, engine=eng)
         eng.close()
+        if bitwise_cases:
+            for key in ("out", "rates", "wspikes"):
+                assert np.array_equal(got[key], base[key], equal_nan=True), (name, key)
+        else:
+            assert_results_match(got, base, node_count=nc, what=name + " persistent vs default")
+
+
+def _move_root(a, j):
+    """The same trees with node labels n-1 (the root of the synthetic batches) and j exchanged: BEAST's operators leave the
+    root at any internal node number."""
+    a = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    n1 = a["height"].shape[1] - 1
+    for key in ("height", "rate", "spike", "nstubs", "parent"):
+        x = a[key]
+        t = x[:, n1].copy()
+        x[:, n1] = x[:, j]
+        x[:, j] = t
+    p = a["parent"]
+    is1, isj = p == n1, p == j
+    p[is1] = j
+    p[isj] = n1
+    return a
+
+
+@pytest.mark.parametrize("kind,T,n", [("C4", 300, 2000), ("C2", 400, 200), ("C3", 300, 500), ("C4", 64, 501), ("C2", 64, 6)])
+def test_root_at_any_internal_node_matches_oracle(kind, T, n):
+    """Ordinary trees whose root is not node n-1 keep the CLEAN bodies of the lean kernel: the pair that holds the root is
+    handed to two tail lanes.  Root moved to the first / second internal node (the pair that straddles the leaf boundary
+    when the leaf count is odd), to n-2, n-3 and to the middle; with and without the producer warp."""
+    b = synthetic.make_batch(kind, T, n)
+    a0 = host_arrays(b)
+    L, N = n, b.n_nodes
+    for j in sorted({L, L + 1, N - 2, N - 3, (L + N) // 2, (L + N) // 2 + 1} & set(range(L, N - 1))):
+        a = _move_root(a0, j)
+        ref = run_oracle(a, b.flags, b.stub_mode)
+        assert np.isfinite(ref["out"][:, :5]).all() or kind == "C3"
+        got = run_capi(a, b.flags, b.stub_mode)
+        assert_results_match(got, ref, what="%s root at %d" % (kind, j))
+        eng = GsmEngine(max_trees=T, max_nodes=N)
+        eng.set_option("producer", 1)
+        got_p = run_capi(a, b.flags, b.stub_mode, engine=eng)
+        eng.close()
         for key in ("out", "rates", "wspikes"):
-            assert np.array_equal(got[key], base[key], equal_nan=True), (name, key)
+            assert np.array_equal(got_p[key], got[key], equal_nan=True), (kind, j, key)
