@@ -221,9 +221,11 @@ def run_extras(dev, device_index, peak_gbs):
     from gammaspikemodel_b200 import GsmEngine, abi, synthetic
     res = []
 
-    def resident(name, kind, trees, taxa, mode=None, flags=None, steps=10, note=""):
+    def resident(name, kind, trees, taxa, mode=None, flags=None, steps=10, note="", root_at=None):
         try:
             b = synthetic.make_batch_chunked(kind, trees, taxa, seed=synthetic.SEEDS[kind], device=dev, chunk=31250)
+            if root_at is not None:
+                synthetic.move_root(b, b.n_nodes + root_at if root_at < 0 else root_at)
             e = GsmEngine(device=device_index)
             e.set_mode(b.stub_mode if mode is None else mode, b.flags if flags is None else flags)
             e.bind_batch(b)
@@ -255,6 +257,8 @@ def run_extras(dev, device_index, peak_gbs):
 
     resident("BASELINE config 3: 100k trees x 1,000 taxa, FBDWS, sampled ancestors, rho<1, indicator per state", "C3", 100_000, 1000)
     resident("BASELINE config 2: 10k trees x 200 taxa, BDWS, spikes on", "C2", 10_000, 200, steps=20)
+    resident("config 4 trees with the root at node n-2 instead of n-1 (as MCMC operators leave them): 60k trees x 2,000 taxa", "C4", 60_000, 2000,
+             root_at=-2, note="the pair of nodes that holds the root goes to the tail lanes, every other pair keeps the ordinary-tree bodies")
     resident("mixture-mode spike prior (Stubs nostub mode, BSP:102-172; the wiring of both BEAUti templates): 20k trees x 1,000 taxa",
              "C3", 20_000, 1000, mode=abi.STUBS_NOSTUB, steps=5, note="fp64-bound: Poisson x Gamma mixture over the stub count of every branch")
     try:

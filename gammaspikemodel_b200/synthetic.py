@@ -247,6 +247,25 @@ def make_batch_chunked(kind, n_trees, n_taxa, seed=None, device="cpu", chunk=163
     return out
 
 
+def move_root(batch, j):
+    """In place: node labels n-1 (the root of the generated trees) and j (an internal node) exchanged in every tree.  BEAST's
+    tree operators leave the root at any internal node number; the generators here (like the reference's simulators) put it
+    last."""
+    n1 = batch.n_nodes - 1
+    if not (batch.n_taxa <= j < n1):
+        raise ValueError("j must be an internal node other than the last")
+    for name in ("height", "rate", "spike", "nstubs", "parent"):
+        x = getattr(batch, name)
+        t = x[:, n1].clone()
+        x[:, n1] = x[:, j]
+        x[:, j] = t
+    p = batch.parent
+    is1, isj = p == n1, p == j
+    p[is1] = j
+    p[isj] = n1
+    return batch
+
+
 def make_chain_states(n_chains, n_taxa, seed=None, device="cpu", kind="C2"):
     """BASELINE config 5: ONE tree (topology, heights, tree-prior parameters) replicated to `n_chains` chain states; every
     chain has its own branch rates, spikes, stub counts (drawn for that tree) and clock / spike hyper-parameters

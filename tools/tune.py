@@ -18,12 +18,8 @@ def parse(c):
 cfgs = [parse(c) for c in sys.argv[4:]]
 dev = torch.device("cuda", 0)
 b = synthetic.make_batch_chunked(kind, trees, taxa, device=dev, chunk=31250)
-if os.environ.get("GSM_ROOT_SWAP"):   # the root becomes node n-2 (trees as MCMC operators leave them: the lean kernel's GENERAL flavour)
-    n1, n2 = b.n_nodes - 1, b.n_nodes - 2
-    for name in ("height", "rate", "spike", "nstubs", "parent"):
-        x = getattr(b, name); t = x[:, n1].clone(); x[:, n1] = x[:, n2]; x[:, n2] = t
-    p = b.parent; is1, is2 = p == n1, p == n2
-    p[is1] = n2; p[is2] = n1
+if os.environ.get("GSM_ROOT_SWAP"):   # the root becomes node n-2 (trees as MCMC operators leave them)
+    synthetic.move_root(b, b.n_nodes - 2)
 eng = GsmEngine(device=0); eng.set_mode(b.stub_mode, b.flags); eng.bind_batch(b)
 out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
