@@ -205,11 +205,18 @@ static void lean_b_all(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, GsmL
         else gsm_lean_b_node<GENERAL, WANT, 0, STDW, MIX>(c, B, i, rt, pf, fs, h[i], hp, aux, auxp, rate[i], spike[i], k, o_r, o_w);
     };
     for (int i0 = 0; i0 + 1 < L; i0 += 2) { node(i0, 1, SA, SB, false); node(i0 + 1, 1, SA, SB, false); }
+    int xpair = -1;   // the pair that holds the root of an ordinary tree whose root is not node n-1: handed to the tail lanes
     for (int i0 = L4; i0 + 1 < n - 1; i0 += 2) {
         if (i0 < L) continue;
+        if (!GENERAL && (par[i0] | par[i0 + 1]) < 0) {
+            if (xpair >= 0) *bad = true;   // a second pair with a root
+            else xpair = i0;
+            continue;
+        }
         node(i0, 0, SA, SB, false);
         node(i0 + 1, 0, SA, SB, false);
     }
+    if (xpair >= 0) { node(xpair, 2, STA, ST, true); node(xpair + 1, 2, STA, ST, true); }
     if (L & 1) { node(L - 1, 2, STA, ST, true); node(L, 2, STA, ST, true); }
     node(n - 1, 2, STA, ST, true);
 }
@@ -276,7 +283,7 @@ static bool eval_tree_lean(uint32_t flags, int32_t stub_mode, int32_t n, const d
         double e, G;
         aux_int[i - L4] = gsm_lean_aux(c, SA, h[i], e, G);
     }
-    const bool general = anyda || !(par_in[n - 1] < 0);
+    const bool general = anyda;   // (a root that is not node n-1 alone keeps the CLEAN bodies)
     GsmLeanAccB SB, ST;
     gsm_lean_acc_b_zero(SB);
     gsm_lean_acc_b_zero(ST);

@@ -54,3 +54,22 @@ def test_lean_path_covers_ordinary_states(case):
     name, a, flags, mode, nc = case
     got = run_emu_lean(a, flags, mode, node_count=nc)
     assert got is not None and got["n_lean"] == a["height"].shape[0], (name, got and got["n_lean"])
+
+
+@pytest.mark.parametrize("kind,T,n", [("C4", 12, 60), ("C2", 12, 33), ("C4", 6, 5), ("C3", 24, 40)])
+def test_lean_path_keeps_trees_whose_root_is_not_the_last_node(kind, T, n):
+    """BEAST's operators leave the root at any internal node number.  The lean path finishes such ordinary trees itself
+    (the pair of nodes that holds the root goes to the tail lanes; tests/emu mirrors lean_b_pair / tail_eval) and agrees
+    with the oracle, for the root at the first / second internal node, in the middle and at n-2 / n-3."""
+    from gammaspikemodel_b200 import synthetic
+    from helpers import host_arrays
+    L, N = n, 2 * n - 1
+    for j in sorted({L, L + 1, (L + N) // 2, (L + N) // 2 + 1, N - 3, N - 2} & set(range(L, N - 1))):
+        b = synthetic.make_batch(kind, T, n)
+        synthetic.move_root(b, j)
+        a = host_arrays(b)
+        got = run_emu_lean(a, b.flags, b.stub_mode)
+        assert got is not None
+        if kind != "C3":                                   # (C3 trees with sampled ancestors may be handed back)
+            assert got["n_lean"] == T, (kind, j, got["n_lean"])
+        assert_results_match(got, run_oracle(a, b.flags, b.stub_mode), what="%s root at %d" % (kind, j))
