@@ -292,6 +292,8 @@ int gsm_set_option(gsm_handle* h, const char* name, int64_t value) {
         h->ctx.minb = static_cast<int>(value);
     } else if (!strcmp(name, "producer")) {
         h->ctx.producer = value != 0;
+    } else if (!strcmp(name, "warp_kernel")) {
+        h->ctx.warp_kernel = value != 0;
     } else if (!strcmp(name, "smem_pad")) {
         h->ctx.smem_pad = static_cast<size_t>(value);
     } else if (!strcmp(name, "persistent")) {

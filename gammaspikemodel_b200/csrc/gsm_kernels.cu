@@ -1429,6 +1429,7 @@ __global__ void GSM_LEAN_BOUNDS(BLOCK, MINB, PROD) gsm_lean_kernel(const GsmBatc
 }
 
 #include "gsm_lean_pk.cuh"
+#include "gsm_lean_warp.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // BranchSpikePrior.getCumulativeProbs (BSP:315-389) for one branch; log-time only, one thread.
@@ -1852,6 +1853,32 @@ static cudaError_t launch_lean_pk(GsmLaunchCtx& ctx, const GsmBatch& b, const Gs
     return cudaGetLastError();
 }
 
+// small trees: one warp per tree (gsm_lean_warp.cuh), one resident CTA per SM
+static cudaError_t launch_lean_warp(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* r, double* w, cudaStream_t st) {
+    const int si = gsm_lean_si(b.n_nodes);
+    int warps = GSM_WARP_WARPS;
+    while (warps > 1 && gsm_warp_cta_bytes(si, warps) + 64u > ctx.smem_optin) --warps;
+    const size_t smem = gsm_warp_cta_bytes(si, warps);
+    int64_t g = (b.n_trees + warps - 1) / warps;
+    if (g > ctx.sm_count) g = ctx.sm_count;
+    const dim3 grid(static_cast<unsigned>(g));
+    GsmLeanRow* rows = reinterpret_cast<GsmLeanRow*>(sc.rows);
+    int32_t* cnt = sc.redo + (sc.epoch & 1);
+    int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
+    int32_t* list = sc.redo + 4;
+    cudaError_t e;
+    if (r || w) {
+        auto kern = gsm_lean_warp_kernel<true>;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, 32 * warps, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    } else {
+        auto kern = gsm_lean_warp_kernel<false>;
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
+        kern<<<grid, 32 * warps, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    }
+    return cudaGetLastError();
+}
+
 template <int BLOCK, int MINB>
 static cudaError_t launch_post(GsmLaunchCtx& ctx, const GsmBatch& b, const GsmScratch& sc, double* o, double* r, double* w,
                                cudaStream_t st) {
@@ -1930,7 +1957,12 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
             if (pe != cudaSuccess) return -static_cast<int>(pe);
             if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) > ctx.smem_per_sm) pk = false;
         }
-        if (pk) {
+        // small trees (up to 256 taxa): one warp per tree unless gsm_set_option("warp_kernel", 0)
+        const bool wk = ctx.warp_kernel != 0 && ctx.block <= 0 && ctx.minb <= 0 && ctx.persistent == 0 && b.n_nodes <= GSM_WARP_MAX_NODES &&
+                        !gsm_lean_mixture(b.flags, b.stub_mode);
+        if (wk) {
+            e = launch_lean_warp(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
+        } else if (pk) {
             e = launch_lean_pk(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         } else if (block == 128 && minb == 3 && ctx.producer != 0 && !gsm_lean_mixture(b.flags, b.stub_mode)) {
             // gsm_set_option("producer", 1): 128 x 3 with a producer warp (the mixture flavour keeps the 168 registers of the

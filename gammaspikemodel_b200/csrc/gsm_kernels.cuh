@@ -55,6 +55,7 @@ struct GsmLaunchCtx {
     int force_generic = 0, block = 0, minb = 0;
     int producer = 0;            // 1: 128 x 3 runs with a producer warp (second warpgroup, setmaxnreg); measured equal to the
                                  // four-warp CTA on C4 and 3 % slower on C3 once its 136-register consumers spill: off
+    int warp_kernel = 1;         // trees of up to 256 taxa are evaluated one warp per tree (gsm_lean_warp.cuh); 0: by the CTA kernel
     size_t smem_pad = 0;         // extra dynamic shared memory per CTA of gsm_lean_kernel (occupancy experiments)
     int persistent = 0;          // 1: the persistent lean kernel where it applies (measured slower than one CTA per tree: off)
 };

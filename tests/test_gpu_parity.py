@@ -405,6 +405,16 @@ def test_whole_tree_stub_cdf_and_choice_match_oracle():
     eng.close()
 
 
+def _run_with(opts, a, flags, mode, node_count=None):
+    T, N = a["height"].shape
+    eng = GsmEngine(max_trees=max(T, 1), max_nodes=max(N, 1))
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    got = run_capi(a, flags, mode, node_count=node_count, engine=eng)
+    eng.close()
+    return got
+
+
 @pytest.mark.parametrize("opts", [{"producer": 1}, {"persistent": 1}], ids=["producer-warp", "persistent-kernel"])
 def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
     """The lean kernel's launch variants (producer warp: gsm_set_option("producer", 1); persistent kernel gsm_lean_pk.cuh:
@@ -419,12 +429,8 @@ def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
         b = synthetic.make_batch(kind, T, n)
         a = host_arrays(b)
         ref = run_oracle(a, b.flags, b.stub_mode)
-        base = run_capi(a, b.flags, b.stub_mode)
-        eng = GsmEngine(max_trees=T, max_nodes=b.n_nodes)
-        for k, v in opts.items():
-            eng.set_option(k, v)
-        got = run_capi(a, b.flags, b.stub_mode, engine=eng)
-        eng.close()
+        base = _run_with({"warp_kernel": 0}, a, b.flags, b.stub_mode)        # the CTA kernel also for small trees
+        got = _run_with(dict(opts, warp_kernel=0), a, b.flags, b.stub_mode)
         assert_results_match(got, ref, what="%s %dx%d %s" % (kind, T, n, opts))
         for key in ("out", "rates", "wspikes"):
             assert np.array_equal(got[key], base[key], equal_nan=True), (kind, T, n, key)
@@ -433,13 +439,8 @@ def test_launch_variants_of_the_lean_kernel_give_the_default_rows(opts):
             continue                                      # mixture-mode wiring: its own kernel flavour, no variants
         if a.get("stubs") is not None:
             continue
-        base = run_capi(a, flags, mode, node_count=nc)
-        T, N = a["height"].shape
-        eng = GsmEngine(max_trees=max(T, 1), max_nodes=max(N, 1))
-        for k, v in opts.items():
-            eng.set_option(k, v)
-        got = run_capi(a, flags, mode, node_count=nc, engine=eng)
-        eng.close()
+        base = _run_with({"warp_kernel": 0}, a, flags, mode, node_count=nc)
+        got = _run_with(dict(opts, warp_kernel=0), a, flags, mode, node_count=nc)
         if bitwise_cases:
             for key in ("out", "rates", "wspikes"):
                 assert np.array_equal(got[key], base[key], equal_nan=True), (name, key)
@@ -476,11 +477,60 @@ def test_root_at_any_internal_node_matches_oracle(kind, T, n):
         a = _move_root(a0, j)
         ref = run_oracle(a, b.flags, b.stub_mode)
         assert np.isfinite(ref["out"][:, :5]).all() or kind == "C3"
-        got = run_capi(a, b.flags, b.stub_mode)
+        assert_results_match(run_capi(a, b.flags, b.stub_mode), ref, what="%s root at %d (default launch)" % (kind, j))
+        got = _run_with({"warp_kernel": 0}, a, b.flags, b.stub_mode)
         assert_results_match(got, ref, what="%s root at %d" % (kind, j))
-        eng = GsmEngine(max_trees=T, max_nodes=N)
-        eng.set_option("producer", 1)
-        got_p = run_capi(a, b.flags, b.stub_mode, engine=eng)
-        eng.close()
+        got_p = _run_with({"warp_kernel": 0, "producer": 1}, a, b.flags, b.stub_mode)
         for key in ("out", "rates", "wspikes"):
             assert np.array_equal(got_p[key], got[key], equal_nan=True), (kind, j, key)
+
+
+def test_one_warp_per_tree_kernel_matches_oracle_and_the_cta_kernel():
+    """Trees of up to 256 taxa are evaluated one warp per tree (gsm_lean_warp.cuh).  Same node arithmetic as the CTA kernel,
+    another partition of the nodes over threads: against the oracle at the parity tolerance, against the CTA kernel
+    (gsm_set_option("warp_kernel", 0)) at 1e-12, integer outputs and weighted spikes bit-exact; ordinary trees, sampled
+    ancestors, tiny trees, odd / even leaf counts, ragged batches, roots that are not the last node, the case table."""
+    on, off = {"warp_kernel": 1}, {"warp_kernel": 0}
+    for kind, T, n in [("C2", 3000, 200), ("C3", 1200, 200), ("C4", 900, 256), ("C3", 500, 101), ("C2", 700, 33), ("C4", 300, 5),
+                       ("C3", 100, 2), ("C2", 50, 1), ("C4", 64, 130)]:
+        b = synthetic.make_batch(kind, T, n)
+        a = host_arrays(b)
+        ref = run_oracle(a, b.flags, b.stub_mode)
+        got = _run_with(on, a, b.flags, b.stub_mode)
+        assert_results_match(got, ref, what="warp kernel %s %dx%d" % (kind, T, n))
+        cta = _run_with(off, a, b.flags, b.stub_mode)
+        assert_close(got["out"], cta["out"], rtol=1e-12, atol=1e-11, what="warp vs CTA kernel %s %dx%d" % (kind, T, n))
+        assert np.array_equal(got["wspikes"], cta["wspikes"], equal_nan=True)
+        if n >= 5:
+            for j in (n, n + 1, 2 * n - 3):
+                if n <= j < 2 * n - 2:
+                    am = _move_root(a, j)
+                    assert_results_match(_run_with(on, am, b.flags, b.stub_mode), run_oracle(am, b.flags, b.stub_mode),
+                                         what="warp kernel %s root at %d" % (kind, j))
+    for name, a, flags, mode, nc in CASES:
+        if a["height"].shape[1] > 511 or a.get("stubs") is not None:
+            continue
+        if name in ("c3-lambda-le-mu", "c3-lambda-eq-mu") and mode == abi.STUBS_NOSTUB:
+            continue
+        got = _run_with(on, a, flags, mode, node_count=nc)
+        assert_results_match(got, run_oracle(a, flags, mode, node_count=nc), node_count=nc, what="warp kernel " + name)
+    # ragged: 3 ... 511 nodes in one launch
+    sizes = [2, 3, 26, 129, 200, 256]
+    per = 64
+    Nmax = 2 * max(sizes) - 1
+    parts, counts = [], []
+    for k, taxa in enumerate(sizes):
+        b = synthetic.make_batch("C3", per, taxa, seed=synthetic.SEEDS["C3"] + k)
+        a = host_arrays(b)
+        pad = {}
+        for key, fill in (("height", 0.0), ("parent", -1), ("rate", 1.0), ("spike", 0.0), ("nstubs", 0)):
+            xx = np.full((per, Nmax), fill, dtype=a[key].dtype)
+            xx[:, :b.n_nodes] = a[key]
+            pad[key] = xx
+        pad["params"], pad["use_spike"] = a["params"], a["use_spike"]
+        parts.append(pad)
+        counts.append(np.full(per, b.n_nodes, np.int32))
+    a = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    nc = np.concatenate(counts)
+    got = _run_with(on, a, synthetic.DEFAULT_FLAGS, abi.STUBS_COUNTS, node_count=nc)
+    assert_results_match(got, run_oracle(a, synthetic.DEFAULT_FLAGS, abi.STUBS_COUNTS, node_count=nc), node_count=nc, what="warp kernel ragged")

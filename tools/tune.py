@@ -14,6 +14,10 @@ kind, trees, taxa = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 def parse(c):
     if c == "pk":
         return (0, 0, 1, 1)
+    if c == "wk":                      # one warp per tree (small trees)
+        return (0, 0, 0, -1)
+    if c == "auto":
+        return (0, 0, 0, 0)
     return tuple(map(int, c.rstrip("n").split("x"))) + (0 if c.endswith("n") else 1, 0)
 cfgs = [parse(c) for c in sys.argv[4:]]
 dev = torch.device("cuda", 0)
@@ -25,7 +29,7 @@ out = torch.empty((b.n_trees, abi.NOUT), dtype=torch.float64, device=dev)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 ref = None
 for blk, minb, prod, pk in cfgs:
-    eng.set_option("block", blk); eng.set_option("minb", minb); eng.set_option("producer", prod); eng.set_option("persistent", pk)
+    eng.set_option("block", blk); eng.set_option("minb", minb); eng.set_option("producer", prod); eng.set_option("persistent", max(pk, 0)); eng.set_option("warp_kernel", 1 if pk < 0 else 0)
     eng.set_option("smem_pad", int(os.environ.get("GSM_SMEM_PAD", "0")))
     for _ in range(3): eng.eval_device(out, None, None, st.cuda_stream)
     torch.cuda.synchronize()
