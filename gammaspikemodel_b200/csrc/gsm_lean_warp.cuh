@@ -13,8 +13,12 @@
 // threads differs, so rows agree with the CTA kernel to rounding (1e-13), not bit for bit.
 #pragma once
 
+#ifndef GSM_WARP_MAX_NODES
 #define GSM_WARP_MAX_NODES 511      // trees of up to 256 taxa
+#endif
+#ifndef GSM_WARP_WARPS
 #define GSM_WARP_WARPS 12           // warps per CTA (one CTA per SM: 12 x 32 x 168 registers)
+#endif
 
 struct __align__(16) GsmWarpTree {  // a warp's shared memory, fixed part; the height / aux / fake-flag arrays follow
     GsmTreeConsts K;
