@@ -114,7 +114,8 @@ int  gsm_set_mode(gsm_handle* h, int32_t stub_mode, uint32_t flags);
  * streaming chunk of gsm_eval_host / gsm_eval_dirty, default 256), "force_generic" (1: every wiring runs the
  * statement-by-statement kernel), "block" / "minb" (launch configuration override, 0 = automatic), "producer" (1: the
  * 128 x 3 lean kernel runs with a producer warp), "persistent" (1: the persistent lean kernel where three of its CTAs fit
- * an SM; both variants give bit-identical rows and are off by default: measured no faster), "smem_pad" (extra dynamic
+ * an SM; both variants give bit-identical rows and are off by default: measured no faster), "warp_kernel" (0: trees of up to 256 taxa are evaluated by the CTA kernel instead of one warp per
+ * tree), "smem_pad" (extra dynamic
  * shared memory per CTA of the lean kernel, bytes: occupancy experiments).  Stored in the handle: the library reads no
  * environment variables and keeps no process-global mutable state. */
 int  gsm_set_option(gsm_handle* h, const char* name, int64_t value);
