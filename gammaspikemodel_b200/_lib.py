@@ -35,6 +35,8 @@ SIGNATURES = {
     "gsm_stub_cdf_trees": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "gsm_stub_choose": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "gsm_format_newick": (_i64, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.c_char_p, _vp, _vp, C.c_char_p, _i64]),
+    "gsm_parse_newick": (_i64, [C.c_char_p, _i32, _vp, _vp, _vp, _vp, _vp, _i32, C.c_char_p, _vp]),
+    "gsm_effective_leaf_rates": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "gsm_java_double_to_string": (_i64, [C.c_double, C.c_char_p, _i64]),
     "gsm_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gsm_host_free": (C.c_int, [_vp]),

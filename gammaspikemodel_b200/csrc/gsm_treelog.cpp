@@ -8,8 +8,10 @@
 #include <charconv>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gsm_b200.h"
@@ -128,9 +130,166 @@ void to_newick(const NewickArgs& a, int32_t node, std::string& buf) {
     java_double(root ? 0.0 : a.height[a.parent[node]] - a.height[node], buf);   // Node.getLength
 }
 
+// ---- the inverse: one logged tree back into arrays (what util/GetEffectiveRates.java reads through BEAST's tree-log parser) ----
+struct ParsedNode {
+    int32_t left = -1, right = -1, parent = -1, label = -1;
+    double length = 0.0;
+    std::vector<std::pair<std::string, double>> meta;
+};
+struct NewickParser {
+    const char* p;
+    std::vector<ParsedNode> nodes;
+    bool ok = true;
+    void skip() { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p; }
+    double number() {
+        skip();
+        // Double.toString spellings incl. NaN / Infinity (strtod accepts "nan" / "inf" / "infinity" case-insensitively)
+        char* e = nullptr;
+        const double v = strtod(p, &e);
+        if (e == p) { ok = false; return 0.0; }
+        p = e;
+        return v;
+    }
+    // subtree := ( '(' subtree (',' subtree)* ')' | label ) [ '[&' key=value,... ']' ] [ ':' length ]
+    int32_t subtree() {
+        skip();
+        const int32_t me = static_cast<int32_t>(nodes.size());
+        nodes.emplace_back();
+        if (*p == '(') {
+            ++p;
+            int nchild = 0;
+            for (;;) {
+                const int32_t c = subtree();
+                if (!ok) return me;
+                nodes[c].parent = me;
+                if (nchild == 0) nodes[me].left = c;
+                else if (nchild == 1) nodes[me].right = c;
+                else { ok = false; return me; }              // BEAST trees are binary
+                ++nchild;
+                skip();
+                if (*p == ',') { ++p; continue; }
+                if (*p == ')') { ++p; break; }
+                ok = false;
+                return me;
+            }
+        } else {
+            char* e = nullptr;
+            const long v = strtol(p, &e, 10);              // STL:87 prints the node number + 1
+            if (e == p || v < 1) { ok = false; return me; }
+            nodes[me].label = static_cast<int32_t>(v - 1);
+            p = e;
+        }
+        skip();
+        if (p[0] == '[' && p[1] == '&') {
+            p += 2;
+            for (;;) {
+                skip();
+                if (*p == ']') { ++p; break; }
+                const char* k0 = p;
+                while (*p && *p != '=' && *p != ',' && *p != ']') ++p;
+                if (*p != '=') { ok = false; return me; }
+                std::string key(k0, p);
+                ++p;
+                const double v = number();
+                if (!ok) return me;
+                nodes[me].meta.emplace_back(std::move(key), v);
+                skip();
+                if (*p == ',') ++p;
+            }
+        }
+        skip();
+        if (*p == ':') {
+            ++p;
+            nodes[me].length = number();
+        }
+        return me;
+    }
+};
+
 }  // namespace
 
 extern "C" {
+
+int64_t gsm_parse_newick(const char* newick, int32_t cap_nodes, int32_t* parent, int32_t* left, int32_t* right, double* length,
+                         double* height, int32_t n_keys, const char* keys, double* values) {
+    if (!newick || cap_nodes <= 0 || !parent || n_keys < 0 || (n_keys > 0 && (!keys || !values))) return -1;
+    NewickParser ps{newick};
+    const int32_t root = ps.subtree();
+    ps.skip();
+    if (!ps.ok || (*ps.p != 0 && *ps.p != ';')) return -1;
+    const int32_t n = static_cast<int32_t>(ps.nodes.size());
+    if (n > cap_nodes || (n & 1) == 0) return n > cap_nodes ? n : -1;
+    const int32_t L = (n + 1) / 2;
+    // BEAST numbering: a leaf takes the number its label gives it, internal nodes follow in post-order, the root last
+    std::vector<int32_t> nr(n, -1);
+    std::vector<char> seen(L, 0);
+    int32_t next = L;
+    // post-order without recursion: parse order is pre-order, children have larger parse indices than their parent
+    std::vector<int32_t> order;
+    order.reserve(n);
+    {
+        std::vector<std::pair<int32_t, int>> st;
+        st.emplace_back(root, 0);
+        while (!st.empty()) {
+            auto& [v, state] = st.back();
+            const ParsedNode& nd = ps.nodes[v];
+            if (state == 0) { state = 1; if (nd.left >= 0) { st.emplace_back(nd.left, 0); continue; } }
+            if (state == 1) { state = 2; if (nd.right >= 0) { st.emplace_back(nd.right, 0); continue; } }
+            order.push_back(v);
+            st.pop_back();
+        }
+    }
+    for (int32_t v : order) {
+        const ParsedNode& nd = ps.nodes[v];
+        if (nd.left < 0) {
+            if (nd.label < 0 || nd.label >= L || seen[nd.label]) return -1;
+            seen[nd.label] = 1;
+            nr[v] = nd.label;
+        } else {
+            if (nd.right < 0 || next >= n) return -1;
+            nr[v] = next++;
+        }
+    }
+    std::vector<std::string> ks;
+    const char* q = keys;
+    for (int32_t k = 0; k < n_keys; k++) {
+        const char* e = q;
+        while (*e && *e != '\n') e++;
+        ks.emplace_back(q, e);
+        q = *e ? e + 1 : e;
+    }
+    const double nan = std::nan("");
+    for (int32_t k = 0; k < n_keys; k++)
+        for (int32_t i = 0; i < n; i++) values[static_cast<int64_t>(k) * cap_nodes + i] = nan;
+    // depth of every node below the root, then heights with the youngest leaf at 0
+    std::vector<double> depth(n, 0.0);
+    double deepest = 0.0;
+    for (auto it = order.rbegin(); it != order.rend(); ++it) {   // reverse post-order: parents before children
+        const int32_t v = *it;
+        const ParsedNode& nd = ps.nodes[v];
+        depth[v] = nd.parent < 0 ? 0.0 : depth[nd.parent] + nd.length;
+        if (nd.left < 0 && depth[v] > deepest) deepest = depth[v];
+    }
+    for (int32_t v = 0; v < n; v++) {
+        const ParsedNode& nd = ps.nodes[v];
+        const int32_t i = nr[v];
+        parent[i] = nd.parent < 0 ? -1 : nr[nd.parent];
+        if (left) left[i] = nd.left < 0 ? -1 : nr[nd.left];
+        if (right) right[i] = nd.right < 0 ? -1 : nr[nd.right];
+        if (length) length[i] = nd.parent < 0 ? 0.0 : nd.length;
+        if (height) height[i] = deepest - depth[v];
+        for (const auto& kv : nd.meta)
+            for (int32_t k = 0; k < n_keys; k++)
+                if (kv.first == ks[k]) values[static_cast<int64_t>(k) * cap_nodes + i] = kv.second;
+    }
+    return n;
+}
+
+int gsm_effective_leaf_rates(int32_t n_leaves, const double* rate, const double* spike, const double* length, double* out) {
+    if (n_leaves < 0 || !rate || !spike || !length || !out) return GSM_E_ARG;
+    for (int32_t i = 0; i < n_leaves; i++) out[i] = rate[i] + spike[i] / length[i];   // GetEffectiveRates.java:58-61
+    return 0;
+}
 
 int64_t gsm_java_double_to_string(double d, char* out, int64_t cap) {
     std::string s;

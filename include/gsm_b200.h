@@ -229,6 +229,18 @@ int  gsm_stub_choose(gsm_handle* h, int64_t n_sel, const int64_t* trees, const d
 int64_t gsm_format_newick(int32_t n_nodes, const int32_t* left, const int32_t* right, const int32_t* parent,
                           const double* height, const int32_t* nstubs, const double* rate, int32_t n_meta,
                           const char* meta_ids, const double* meta_values, const int32_t* meta_dim, char* out, int64_t cap);
+/* The inverse reader: one logged tree back into arrays, as util/GetEffectiveRates.java:30-83 reads them through BEAST's
+ * tree-log parser.  newick: `(...)[&key=value,...]:length` as gsm_format_newick / StumpedTreeLogger write it (leaf labels are
+ * node numbers + 1, STL:87; an optional trailing ';').  Node numbers on return: a leaf keeps the number of its label, internal
+ * nodes follow in post-order, the root is last (BEAST's convention).  parent (-1 = root) is required; left / right / length
+ * (root: 0) / height (youngest leaf at 0) may be NULL.  keys: n_keys metadata names separated by '\n'; values
+ * [n_keys][cap_nodes] receives each key's number per node, NaN where a node does not carry it.  Returns the number of nodes;
+ * a value > cap_nodes means the arrays are too small (nothing written); -1: not a binary tree in this format. */
+int64_t gsm_parse_newick(const char* newick, int32_t cap_nodes, int32_t* parent, int32_t* left, int32_t* right, double* length,
+                         double* height, int32_t n_keys, const char* keys, double* values);
+/* GetEffectiveRates.java:55-62: eRate_i = branchRates_i + spikes_i / length_i of the leaves (the per-leaf columns of its
+ * output table; rate / spike = the metadata the XML logs under those ids, length = Node.getLength). */
+int  gsm_effective_leaf_rates(int32_t n_leaves, const double* rate, const double* spike, const double* length, double* out);
 /* Java's Double.toString(d) (as used by every Loggable of the package: SPL:60, SpikeSize:74-78, STL:201-203). */
 int64_t gsm_java_double_to_string(double d, char* out, int64_t cap);
 

@@ -62,6 +62,9 @@ public final class GsmB200 {
     public static final MethodHandle STUB_CHOOSE = mh("gsm_stub_choose", fi(ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
     public static final MethodHandle FORMAT_NEWICK = mh("gsm_format_newick", FunctionDescriptor.of(JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS,
             ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
+    public static final MethodHandle PARSE_NEWICK = mh("gsm_parse_newick", FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, ADDRESS,
+            ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    public static final MethodHandle EFFECTIVE_LEAF_RATES = mh("gsm_effective_leaf_rates", fi(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     public static final MethodHandle JAVA_DOUBLE_TO_STRING = mh("gsm_java_double_to_string", FunctionDescriptor.of(JAVA_LONG, JAVA_DOUBLE, ADDRESS, JAVA_LONG));
     public static final MethodHandle HOST_ALLOC = mh("gsm_host_alloc", fi(ADDRESS, JAVA_LONG));
     public static final MethodHandle HOST_FREE = mh("gsm_host_free", fi(ADDRESS));

@@ -137,3 +137,84 @@ def test_newick_writer_matches_the_restated_java_method(kind, n):
             assert lib.gsm_format_newick(*args, buf, need + 1) == need
             want = py_newick(a, t, left, right, nst if use_stubs else None, rate if use_rate else None, metas)
             assert buf.value.decode() == want
+
+
+def _write(lib, N, left, right, par, h, nst, rate, metas):
+    p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    ids = "\n".join(m[0] for m in metas).encode()
+    vals = np.ascontiguousarray(np.stack([m[1] for m in metas])) if metas else None
+    dims = np.array([m[2] for m in metas], np.int32) if metas else None
+    args = (N, p(left), p(right), p(par), p(h), p(nst), p(rate), len(metas), ids if metas else None, p(vals), p(dims))
+    need = lib.gsm_format_newick(*args, None, 0)
+    buf = C.create_string_buffer(need + 1)
+    assert lib.gsm_format_newick(*args, buf, need + 1) == need
+    return buf.value
+
+
+def _parse(lib, s, cap, keys):
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    par, left, right = (np.full(cap, -7, np.int32) for _ in range(3))
+    length, height = np.zeros(cap), np.zeros(cap)
+    vals = np.zeros((max(len(keys), 1), cap))
+    n = lib.gsm_parse_newick(s, cap, p(par), p(left), p(right), p(length), p(height), len(keys), "\n".join(keys).encode(), p(vals))
+    return n, par, left, right, length, height, vals
+
+
+@pytest.mark.parametrize("kind,n", [("C3", 40), ("C2", 7), ("C4", 2), ("C4", 129)])
+def test_newick_reader_inverts_the_writer_and_gives_the_effective_leaf_rates(kind, n):
+    """gsm_parse_newick (what util/GetEffectiveRates.java:30-83 reads through BEAST's tree-log parser) on the writer's output:
+    same tree (leaves keep their numbers, every parent / child relation and branch length survives the internal renumbering),
+    same metadata to the last bit (Double.toString round-trips), heights with the youngest leaf at 0; eRate = rate + spike /
+    length for the leaves as GetEffectiveRates.java:58-61 computes it."""
+    lib = _lib.load()
+    b = synthetic.make_batch(kind, 3, n, seed=11)
+    a = host_arrays(b)
+    N, L = b.n_nodes, n
+    for t in range(3):
+        par = np.ascontiguousarray(a["parent"][t])
+        left, right = np.full(N, -1, np.int32), np.full(N, -1, np.int32)
+        for i in range(N):
+            if par[i] >= 0:
+                if left[par[i]] < 0:
+                    left[par[i]] = i
+                else:
+                    right[par[i]] = i
+        h = np.ascontiguousarray(a["height"][t])
+        nst = np.ascontiguousarray(a["nstubs"][t])
+        rate = np.ascontiguousarray(a["rate"][t])
+        spk = np.ascontiguousarray(a["spike"][t] * 0.013)
+        s = _write(lib, N, left, right, par, h, nst, rate, [("spikes", spk, N), ("branchRates", rate, N)])
+        got_n, p2, l2, r2, len2, h2, vals = _parse(lib, s + b";", N, ["nstubs", "rate", "spikes", "branchRates", "absent"])
+        assert got_n == N
+        # leaves keep their numbers; map the internal nodes through the parent relation of matching children
+        m = {i: i for i in range(L)}
+        for i in sorted(range(N), key=lambda i: h[i]):                 # children before parents
+            if par[i] >= 0:
+                assert m.setdefault(int(par[i]), int(p2[m[i]])) == int(p2[m[i]])
+        assert len(set(m.values())) == N and p2[m[int(np.where(par < 0)[0][0])]] == -1 and m[int(np.where(par < 0)[0][0])] == N - 1
+        for i in range(N):
+            j = m[i]
+            want_len = 0.0 if par[i] < 0 else h[par[i]] - h[i]
+            assert len2[j] == want_len                                 # Double.toString round-trips exactly
+            assert vals[1][j] == rate[i] and vals[2][j] == spk[i] and vals[3][j] == rate[i] and np.isnan(vals[4][j])
+            assert (np.isnan(vals[0][j]) if par[i] < 0 else vals[0][j] == nst[i])
+            assert {int(l2[j]), int(r2[j])} == ({-1} if left[i] < 0 else {m[int(left[i])], m[int(right[i])]})
+        assert np.allclose(h2[[m[i] for i in range(N)]] - h2[:L].min(), h - h[:L].min(), rtol=0, atol=1e-9 * max(1.0, h.max()))
+        out = np.zeros(L)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        assert lib.gsm_effective_leaf_rates(L, p(vals[3]), p(vals[2]), p(len2), p(out)) == 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = rate[:L] + spk[:L] / np.array([h[par[i]] - h[i] for i in range(L)])
+        assert np.array_equal(out, want, equal_nan=True)
+
+
+def test_newick_reader_rejects_what_it_cannot_represent():
+    lib = _lib.load()
+    assert _parse(lib, b"((1:1.0,2:1.0):1.0,3:2.0);", 8, [])[0] == 5
+    assert _parse(lib, b"((1:1.0,2:1.0):1.0,3:2.0);", 3, [])[0] == 5                 # arrays too small: the size needed
+    for bad in (b"((1:1.0,2:1.0,3:1.0):1.0,4:2.0);", b"((1:1.0,2:1.0):1.0,5:2.0);", b"((1:1.0,1:1.0):1.0,3:2.0);", b"(1:1.0,2:1.0", b"(1:x,2:1.0);",
+                b"((1[&a]:1.0,2:1.0):1.0,3:2.0);"):
+        assert _parse(lib, bad, 16, ["a"])[0] == -1, bad
+    n, par, left, right, length, height, vals = _parse(lib, b"((1[&r=1.0E-4,s=NaN]:0.5,2[&r=Infinity]:1.5)[&r=2.0]:1.0,3:3.0)", 8, ["r", "s"])
+    assert n == 5 and list(par[:5]) == [3, 3, 4, 4, -1] and list(height[:5]) == [1.5, 0.5, 0.0, 2.0, 3.0]
+    assert vals[0][0] == 1e-4 and np.isnan(vals[1][0]) and vals[0][1] == np.inf and vals[0][3] == 2.0 and np.isnan(vals[0][2])
