@@ -1867,15 +1867,19 @@ static cudaError_t launch_lean_warp(GsmLaunchCtx& ctx, const GsmBatch& b, const 
     int32_t* cnt_next = sc.redo + ((sc.epoch + 1) & 1);
     int32_t* list = sc.redo + 4;
     cudaError_t e;
-    if (r || w) {
-        auto kern = gsm_lean_warp_kernel<true>;
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, 32 * warps, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
-    } else {
-        auto kern = gsm_lean_warp_kernel<false>;
-        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;
-        kern<<<grid, 32 * warps, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);
+    const bool mixk = gsm_lean_mixture(b.flags, b.stub_mode);
+#define GSM_LAUNCH_WARP(R, M)                                                          \
+    {                                                                                  \
+        auto kern = gsm_lean_warp_kernel<R, M>;                                        \
+        if ((e = prep(ctx, kern, smem)) != cudaSuccess) return e;                      \
+        kern<<<grid, 32 * warps, smem, st>>>(b, rows, cnt, cnt_next, list, r, w);      \
     }
+    if (r || w) {
+        if (mixk) GSM_LAUNCH_WARP(true, true) else GSM_LAUNCH_WARP(true, false)
+    } else {
+        if (mixk) GSM_LAUNCH_WARP(false, true) else GSM_LAUNCH_WARP(false, false)
+    }
+#undef GSM_LAUNCH_WARP
     return cudaGetLastError();
 }
 
@@ -1958,8 +1962,7 @@ int gsm_launch_eval(GsmLaunchCtx& ctx, const GsmBatch& b, GsmScratch& sc, double
             if (3 * ((all + 1023) & ~static_cast<size_t>(1023)) > ctx.smem_per_sm) pk = false;
         }
         // small trees (up to 256 taxa): one warp per tree unless gsm_set_option("warp_kernel", 0)
-        const bool wk = ctx.warp_kernel != 0 && ctx.block <= 0 && ctx.minb <= 0 && ctx.persistent == 0 && b.n_nodes <= GSM_WARP_MAX_NODES &&
-                        !gsm_lean_mixture(b.flags, b.stub_mode);
+        const bool wk = ctx.warp_kernel != 0 && ctx.block <= 0 && ctx.minb <= 0 && ctx.persistent == 0 && b.n_nodes <= GSM_WARP_MAX_NODES;
         if (wk) {
             e = launch_lean_warp(ctx, b, sc, d_out_rates, d_out_wspikes, stream);
         } else if (pk) {

@@ -9,6 +9,7 @@
 // memory / L2 with 128-bit loads one iteration ahead (a warp's 32 node pairs are 512 contiguous bytes per array), only what
 // is gathered at random (internal heights, aux, fake flags) and the per-tree tables live in the warp's 8 KB of shared
 // memory, and the Gamma table is built only as far as the tree's largest stub count needs it.
+// Both spike-prior flavours (known stub count; MIXK: the Poisson mixture of the templates' wiring), as in the CTA kernel.
 // Same node arithmetic as gsm_lean_kernel (lean_b_pair / gsm_lean_b_node / gsm_lean_combine); the partition of the nodes over
 // threads differs, so rows agree with the CTA kernel to rounding (1e-13), not bit for bit.
 #pragma once
@@ -25,7 +26,8 @@ struct __align__(16) GsmWarpTree {  // a warp's shared memory, fixed part; the h
     GsmLeanXPair xp;
     int32_t root, nroot;
     int32_t pad[2];
-    GsmLeanN ntab[GSM_LEAN_MAX_NST + 1];
+    GsmLogEntry mtab[2];            // mixture mode: {shape m - 1, log shape - logGamma(shape m)} for m = 0, 1 (the only ones it uses)
+    GsmLeanN ntab[GSM_LEAN_MAX_NST + 1];   // mixture mode: overlaid by the Gamma-ratio tables (128 x 16 bytes), as in the CTA kernel
 };
 __host__ __device__ inline uint32_t gsm_warp_fixed_bytes() { return (static_cast<uint32_t>(sizeof(GsmWarpTree)) + 15u) & ~15u; }
 __host__ __device__ inline uint32_t gsm_warp_bytes(int si) {
@@ -60,7 +62,7 @@ static __device__ __forceinline__ void lean_warp_load(LeanWarpRegs& r, bool in, 
 
 // pass B of one tree by one warp: leaf pairs (i0, i0 + 1 < L), internal pairs from L4 on (L <= i0, i0 + 1 < n - 1); the loads of
 // the next 32 pairs are issued before the bodies of these
-template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int XPD>
+template <bool GENERAL, bool WANT_RATES, bool STDW, int LT, int XPD, bool MIX>
 static __device__ __forceinline__ void lean_warp_pass_b(const GsmLeanC& c, GsmLeanAccA& SA, GsmLeanAccB& SB, LeanBCtx& x, uint32_t a_base, int n,
                                                         int L, int L4, int lane, const double* rrow, const double* srow, const double* hrow,
                                                         const int32_t* nrow, const int32_t* prow, int32_t* root_nroot,
@@ -73,7 +75,7 @@ static __device__ __forceinline__ void lean_warp_pass_b(const GsmLeanC& c, GsmLe
         for (int base = 0; base < L; base += 64) {
             const int i1 = i0 + 64;
             lean_warp_load<1>(nxt, base + 64 < L && i1 + 1 < L, rrow, srow, hrow, nrow, prow, i1);
-            lean_b_pair<GENERAL, WANT_RATES, 1, STDW, LT, false, XPD>(c, SA, SB, x, a_base, i0, i0 + 1 < L, cur.rr, cur.ss, cur.h2, cur.kk, cur.pp,
+            lean_b_pair<GENERAL, WANT_RATES, 1, STDW, LT, MIX, XPD>(c, SA, SB, x, a_base, i0, i0 + 1 < L, cur.rr, cur.ss, cur.h2, cur.kk, cur.pp,
                                                                       root_nroot, orate2, owsp2);
             cur = nxt;
             i0 = i1;
@@ -88,7 +90,7 @@ static __device__ __forceinline__ void lean_warp_pass_b(const GsmLeanC& c, GsmLe
         for (int base = L4; base + 1 < hi; base += 64) {
             const int i1 = i0 + 64;
             lean_warp_load<0>(nxt, base + 65 < hi && i1 + 1 < hi, rrow, srow, hrow, nrow, prow, i1);
-            lean_b_pair<GENERAL, WANT_RATES, 0, STDW, LT, false, XPD>(c, SA, SB, x, a_base, i0, i0 >= L && i0 + 1 < hi, cur.rr, cur.ss, cur.h2, cur.kk,
+            lean_b_pair<GENERAL, WANT_RATES, 0, STDW, LT, MIX, XPD>(c, SA, SB, x, a_base, i0, i0 >= L && i0 + 1 < hi, cur.rr, cur.ss, cur.h2, cur.kk,
                                                                       cur.pp, root_nroot, orate2, owsp2);
             cur = nxt;
             i0 = i1;
@@ -96,7 +98,8 @@ static __device__ __forceinline__ void lean_warp_pass_b(const GsmLeanC& c, GsmLe
     }
 }
 
-template <bool WANT_RATES>
+// MIXK: the mixture-mode spike prior (BSP:102-172, Stubs nostub mode) is a kernel of its own, as for the CTA kernel
+template <bool WANT_RATES, bool MIXK>
 __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(const GsmBatch b, GsmLeanRow* __restrict__ rows,
                                                                                int32_t* __restrict__ redo_count,
                                                                                int32_t* __restrict__ redo_count_next,
@@ -164,8 +167,8 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
             W.xp.i0 = -1;
         }
         __syncwarp();
-        // invalid states (lambda <= mu, shape <= 0, ...) and the mixture-mode wiring go to the generic path
-        if (!(valid && gsm_lean_consts_ok(K) && K.spike_known_n != 0)) {
+        // invalid states (lambda <= mu, shape <= 0, ...) go to the generic path (the kernel flavour follows the wiring)
+        if (!(valid && gsm_lean_consts_ok(K) && (K.spike_known_n == 0) == MIXK)) {
             if (lane == 0) lean_redo(redo_count, redo_list, rows, t);
             continue;
         }
@@ -179,9 +182,9 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
         GsmLeanC c;
         gsm_lean_consts(K, c, n);
         c.t6 = t6;
-        c.mtab = nullptr;
+        c.mtab = MIXK ? W.mtab : nullptr;
         c.ntab = W.ntab;
-        c.mixtab = nullptr;
+        c.mixtab = reinterpret_cast<const GsmLogEntry*>(W.ntab);   // mixture mode has no stub counts: the two tables share the space
         LeanBCtx x;
         x.a_hs = smem_u32(sh_hs) - static_cast<uint32_t>(L4) * 8u;
         x.a_as = smem_u32(sh_as) - static_cast<uint32_t>(L4) * 8u;
@@ -196,7 +199,36 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
 
         // ---- Gamma table, as far as the largest stub count of the tree needs it:
         //      ntab[k] = {log shape - logGamma(shape (k + 1)), -log k!, shape (k + 1) - 1, k}   (BSP:97-99, STP:567)
-        {
+        if (MIXK) {
+            // g[m] = Gamma(shape m) / Gamma(shape (m + 1)); [m - 1] = {g[m] / m, 1 / m}, [64 + m] = {g[m] / (m + 1), 1 / (m + 1)}
+            const double shape = K.shape;
+            GsmLogEntry* mt = reinterpret_cast<GsmLogEntry*>(W.ntab);
+            for (int m = lane + 1; m <= GSM_LEAN_MTAB_N - 1; m += 32) {
+                const double logc = gsm_log6_hi(t6, shape) - lean_log_gamma(t6, shape * m);
+                if (m == 1) {
+                    W.mtab[1].invc = shape * m - 1;
+                    W.mtab[1].logc = logc;
+                    W.mtab[0].invc = -1.0;
+                    W.mtab[0].logc = 0.0;
+                }
+                const double lg_m = gsm_log6_hi(t6, shape) - logc;   // logGamma(shape m)
+                const double g = gsm_exp6(t6, lg_m - lean_log_gamma(t6, shape * (m + 1)));
+                GsmLogEntry r;
+                r.logc = lean_rcp(static_cast<double>(m));
+                r.invc = g * r.logc;
+                mt[m - 1] = r;
+                if (m < GSM_LEAN_MAX_NST) {
+                    r.logc = lean_rcp(static_cast<double>(m + 1));
+                    r.invc = g * r.logc;
+                    mt[GSM_LEAN_MAX_NST + 1 + m] = r;
+                }
+                if (m == 1) {   // [64 + 0]: only its 1 / (k + 1) is used (the k = 0 term of a fake node's child is zero)
+                    r.logc = 1.0;
+                    r.invc = 0.0;
+                    mt[GSM_LEAN_MAX_NST + 1] = r;
+                }
+            }
+        } else {
             uint32_t nmax = static_cast<uint32_t>(GSM_LEAN_MAX_NST);
             if (nrow) {
                 nmax = 0u;
@@ -277,8 +309,8 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
         double2* owsp2 = (WANT_RATES && out_wspikes) ? reinterpret_cast<double2*>(out_wspikes + row) : nullptr;
         const bool stdw = gsm_lean_std_wiring(c);
         int32_t* rn = &W.root;   // {root, nroot}
-#define GSM_WPASS_B(G, W_, LT) lean_warp_pass_b<G, WANT_RATES, W_, LT, XPD>(c, SA, SB, x, a_w, n, L, L4, lane, rrow, srow, hrow, nrow, prow, rn, orate2, owsp2)
-#define GSM_WPASS_B3(G, LT) { if (stdw) GSM_WPASS_B(G, true, LT); else GSM_WPASS_B(G, false, LT); }
+#define GSM_WPASS_B(G, W_, LT, M_) lean_warp_pass_b<G, WANT_RATES, W_, LT, XPD, M_>(c, SA, SB, x, a_w, n, L, L4, lane, rrow, srow, hrow, nrow, prow, rn, orate2, owsp2)
+#define GSM_WPASS_B3(G, LT) { if constexpr (MIXK) GSM_WPASS_B(G, false, LT, true); else { if (stdw) GSM_WPASS_B(G, true, LT, false); else GSM_WPASS_B(G, false, LT, false); } }
         if (general) {
             if (c.leaf_term == 0) GSM_WPASS_B3(true, 0)
             else if (c.leaf_term == 1) GSM_WPASS_B3(true, 1)
@@ -335,7 +367,7 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
             int32_t nst = -1;
             if (c.use_counts) nst = (i < n - 1 || b.stub_mode == GSM_STUBS_EXACT) ? __ldg(nrow + i) : 0;
             double er, ew;
-            gsm_lean_b_node<true, WANT_RATES, 2, false, false>(c, ST, i, root, pf, fs, h, hp, aux, auxp, __ldg(rrow + i), __ldg(srow + i), nst, &er, &ew);
+            gsm_lean_b_node<true, WANT_RATES, 2, false, MIXK>(c, ST, i, root, pf, fs, h, hp, aux, auxp, __ldg(rrow + i), __ldg(srow + i), nst, &er, &ew);
             if (WANT_RATES) {
                 if (out_rates) out_rates[row + i] = er;
                 if (out_wspikes) out_wspikes[row + i] = ew;

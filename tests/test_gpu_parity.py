@@ -501,6 +501,12 @@ def test_one_warp_per_tree_kernel_matches_oracle_and_the_cta_kernel():
         cta = _run_with(off, a, b.flags, b.stub_mode)
         assert_close(got["out"], cta["out"], rtol=1e-12, atol=1e-11, what="warp vs CTA kernel %s %dx%d" % (kind, T, n))
         assert np.array_equal(got["wspikes"], cta["wspikes"], equal_nan=True)
+        if T <= 1200:                                      # mixture-mode spike prior (the templates' wiring): its own flavour
+            refm = run_oracle(a, b.flags, abi.STUBS_NOSTUB)
+            gotm = _run_with(on, a, b.flags, abi.STUBS_NOSTUB)
+            assert_results_match(gotm, refm, what="warp kernel, mixture mode %s %dx%d" % (kind, T, n))
+            ctam = _run_with(off, a, b.flags, abi.STUBS_NOSTUB)
+            assert_close(gotm["out"], ctam["out"], rtol=1e-12, atol=1e-11, what="warp vs CTA kernel, mixture mode %s %dx%d" % (kind, T, n))
         if n >= 5:
             for j in (n, n + 1, 2 * n - 3):
                 if n <= j < 2 * n - 2:
