@@ -197,6 +197,19 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
         const bool detect = !(c.leaf_term == 0 && K.psi == 0.0);   // sampled ancestors are looked for where the tree prior generates them
         c.sa_unscanned = !detect;
 
+        // The heights of the internal nodes (pass A) are requested before the Gamma table is built: their latency passes under it.
+        constexpr int NPA_U = (GSM_WARP_MAX_NODES + 1) / 2 / 2 / 32 + 2;   // pair slots per lane (n - L4 <= (n + 1) / 2 + 3)
+        double2 hq[NPA_U];
+        const int npa = (n - L4 + 1) >> 1;
+        {
+            const double2* h2row = reinterpret_cast<const double2*>(hrow + L4);
+#pragma unroll
+            for (int u = 0; u < NPA_U; u++) {
+                const int j = lane + 32 * u;
+                hq[u] = j < npa ? __ldg(h2row + j) : make_double2(0.0, 0.0);
+                if (j < npa && L4 + 2 * j + 1 >= n) hq[u].y = hq[u].x;   // padding slot of the last pair
+            }
+        }
         // ---- Gamma table, as far as the largest stub count of the tree needs it:
         //      ntab[k] = {log shape - logGamma(shape (k + 1)), -log k!, shape (k + 1) - 1, k}   (BSP:97-99, STP:567)
         if (MIXK) {
@@ -231,8 +244,17 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
         } else {
             uint32_t nmax = static_cast<uint32_t>(GSM_LEAN_MAX_NST);
             if (nrow) {
+                // (all loads of a lane are issued before the first is used)
+                constexpr int NU = (GSM_WARP_MAX_NODES + 31) / 32;
+                uint32_t v[NU];
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    const int i = lane + 32 * u;
+                    v[u] = i < n ? static_cast<uint32_t>(__ldg(nrow + i)) : 0u;
+                }
                 nmax = 0u;
-                for (int i = lane; i < n; i += 32) nmax = gsm_umax(nmax, static_cast<uint32_t>(__ldg(nrow + i)));
+#pragma unroll
+                for (int u = 0; u < NU; u++) nmax = gsm_umax(nmax, v[u]);
                 nmax = warp_max_u32(nmax);
                 if (nmax > static_cast<uint32_t>(GSM_LEAN_MAX_NST)) nmax = static_cast<uint32_t>(GSM_LEAN_MAX_NST);   // (such a tree is handed back below)
             }
@@ -251,30 +273,23 @@ __global__ void __launch_bounds__(32 * GSM_WARP_WARPS, 1) gsm_lean_warp_kernel(c
         GsmLeanAccA SA;
         gsm_lean_acc_a_zero(SA);
         {
-            const int npa = (n - L4 + 1) >> 1;
             const uint32_t a_h0 = smem_u32(sh_hs), a_a0 = smem_u32(sh_as);
-            const double2* h2row = reinterpret_cast<const double2*>(hrow + L4);
-#pragma unroll 1
-            for (int j = lane; j < npa; j += 64) {
-                const int j2 = j + 32;
-                if (j2 < npa) {
-                    const double2 ha = __ldg(h2row + j);
-                    double2 hb = __ldg(h2row + j2);
-                    if (L4 + 2 * j2 + 1 >= n) hb.y = hb.x;   // padding slot of the last pair
-                    const double h4[4] = {ha.x, ha.y, hb.x, hb.y};
+#pragma unroll
+            for (int u = 0; u < NPA_U; u += 2) {
+                const int j = lane + 32 * u, j2 = j + 32;
+                if (u + 1 < NPA_U && j2 < npa) {   // two pairs = four nodes, staged (gsm_lean_aux4)
+                    const double h4[4] = {hq[u].x, hq[u].y, hq[u + 1 < NPA_U ? u + 1 : u].x, hq[u + 1 < NPA_U ? u + 1 : u].y};
                     double a4[4];
                     gsm_lean_aux4(c, SA, h4, a4);
-                    sts_v2f64(a_h0 + j * 16, ha.x, ha.y);
-                    sts_v2f64(a_h0 + j2 * 16, hb.x, hb.y);
+                    sts_v2f64(a_h0 + j * 16, h4[0], h4[1]);
+                    sts_v2f64(a_h0 + j2 * 16, h4[2], h4[3]);
                     sts_v2f64(a_a0 + j * 16, a4[0], a4[1]);
                     sts_v2f64(a_a0 + j2 * 16, a4[2], a4[3]);
-                } else {
-                    double2 h2 = __ldg(h2row + j);
-                    if (L4 + 2 * j + 1 >= n) h2.y = h2.x;
+                } else if (j < npa) {
                     double e0, G0, e1, G1;
-                    const double a0 = gsm_lean_aux(c, SA, h2.x, e0, G0);
-                    const double a1 = gsm_lean_aux(c, SA, h2.y, e1, G1);
-                    sts_v2f64(a_h0 + j * 16, h2.x, h2.y);
+                    const double a0 = gsm_lean_aux(c, SA, hq[u].x, e0, G0);
+                    const double a1 = gsm_lean_aux(c, SA, hq[u].y, e1, G1);
+                    sts_v2f64(a_h0 + j * 16, hq[u].x, hq[u].y);
                     sts_v2f64(a_a0 + j * 16, a0, a1);
                 }
             }
